@@ -1,0 +1,103 @@
+// device_scene.h -- the POD block the kernels read: scalars by value (kernel parameter,
+// __grid_constant__) and pointers into one table arena in HBM.  Built by the engine from
+// SceneTables (tables.h).  Everything the reference bakes into JIT-compiled constants
+//  lives here instead.
+#pragma once
+
+#include <cstdint>
+
+namespace clsimcu {
+
+constexpr int kMaxWlenGenerators = 8;
+constexpr int kMaxSubdetectors = 9; // sparse_collision_kernel.c.cl:455-457
+
+struct DevWlenGenerator {
+    int kind, n;
+    float x0, dx, min_val, range, value;
+    const float *xs, *density, *cumulative;
+};
+
+struct DevCellGrid {
+    int num_x, num_y;
+    float start_x, start_y, width_x, width_y;
+    float inv_width_x, inv_width_y; // fast kernel only
+    const uint16_t *cell_to_string;
+};
+
+struct DevMedium {
+    int num_layers;
+    float z0, h, inv_h;
+    float kappa, A, B, D, E, alpha, inv_ref_wlen;
+    float n_phase[5], n_group[5], c_light;
+    int scat_kind;
+    float f_sl, one_minus_f_sl, g, g2, sl_beta;
+    int tilt_nd, tilt_nz;
+    float tilt_z0, tilt_dz, tilt_lnx, tilt_lny;
+    int anisotropy, pre_renorm, post_renorm;
+    float l[3], rl[3], azx, azy, neg_azy, B2;
+    float pre[9], post[9];
+    const float *a_dust400, *delta_tau, *b400; // [num_layers]
+    const float *abs_dust, *abs_tau;           // fast kernel: D*aDust400+E, 1+0.01*deltaTau
+    const float *tilt_dist, *tilt_corr;
+};
+
+struct DevBias {
+    int kind, n;
+    float x0, dx, value;
+    const float *v;
+};
+
+struct DevGeometry {
+    int num_strings, num_sets, max_layers, num_grids, layer_table_size;
+    float om_radius, string_max_radius;
+    float tmpl_scale_x, tmpl_scale_y;
+    DevCellGrid grids[kMaxSubdetectors];
+    const float *string_x, *string_y, *string_min_z, *string_max_z;
+    const uint8_t *string_set;
+    const uint16_t *set_layer_count;
+    const float *set_start_z, *set_layer_height;
+    const uint16_t *layer_to_dom;
+    const int16_t *tmpl_dx, *tmpl_dy;
+    const float *tmpl_z;
+    const uint32_t *string_tmpl_start;
+    const float *string_mean_x, *string_mean_y;
+    // index -> ID rewrite on the device (…ConverterOpenCL.cxx:1565-1602 does it on the host)
+    const int16_t *string_index_to_id;
+    const uint32_t *dom_id_offset; // per string into dom_ids
+    const uint16_t *dom_ids;
+};
+
+struct DevScene {
+    DevMedium medium;
+    DevWlenGenerator generators[kMaxWlenGenerators];
+    int num_generators;
+    DevBias bias;
+    DevGeometry geo;
+    int stop_detected, save_all, fixed_abs, pancake, history_entries;
+    float prescale, fixed_abs_lens, pancake_factor;
+};
+
+// Per-launch arguments.
+struct LaunchArgs {
+    const void *steps;         // clsimcu_step[num_steps]
+    uint32_t num_steps;
+    uint32_t max_hits;         // capacity of photons[]
+    void *photons;             // clsimcu_photon[max_hits]
+    float *history;            // [max_hits][history_entries][4] or nullptr
+    uint32_t *hit_counter;     // device counter (keeps counting past max_hits, quirk 10)
+    unsigned long long *stats; // [0] photons created, [1] segments
+    uint32_t *work_counter;    // fast kernel: next step to hand out
+    uint64_t *rng_x;           // RNG streams used by this launch
+    uint32_t *rng_a;
+    uint64_t *rng_tag_x;       // optional (save-all debugging): RNG state at photon creation
+    uint32_t *rng_tag_a;
+    int count_stats;
+};
+
+// kernel launchers (defined in kernel_reference.cu / kernel_fast.cu)
+int launch_reference_kernel(const DevScene &scene, const LaunchArgs &args, void *stream);
+int launch_fast_kernel(const DevScene &scene, const LaunchArgs &args, int grid_blocks, void *stream);
+bool fast_kernel_supports(const DevScene &scene, const char **why);
+void fast_kernel_geometry(int device, int *grid_blocks, int *threads_per_block);
+
+} // namespace clsimcu

@@ -1,0 +1,911 @@
+// engine.cu -- host runtime of libclsimcuda and the C ABI of include/clsimcuda.h.
+//
+// Replaces the host driver of the reference (private/opencl/I3CLSimStepToPhotonConverterOpenCL.cxx:
+// Initialize :217-388, worker thread :1142-1315, upload :778-902, download :994-1086,
+// statistics :1088-1140, 1621-1640) with a CUDA-runtime design for one B200:
+//
+//   caller -> bounded queue(5) -> submit thread: stage into pinned memory, async H2D on the
+//   slot's transfer stream, kernel on the single compute stream (kernels serialise, so the
+//   per-thread RNG streams are never shared by two launches), async D2H of the counters
+//   -> in-flight queue -> drain thread: waits for the counters, copies exactly the hits
+//   that were produced, hands a result to the unbounded output queue.
+//
+// With double buffering three slots rotate, so bunch k+1 uploads and bunch k-1 downloads
+// while bunch k computes; without it one slot gives the reference's strictly serial order.
+// There is no CPU fallback: without a usable device clsimcu_create fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/clsimcuda.h"
+#include "device_scene.h"
+#include "tables.h"
+
+namespace clsimcu {
+namespace {
+
+thread_local std::string t_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    t_last_error = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define CUDA_OK(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+// Blocking queue with optional bound, the role of I3CLSimQueue (public/clsim/I3CLSimQueue.h:58-171).
+template <class T> class BlockingQueue {
+public:
+    explicit BlockingQueue(size_t bound) : bound_(bound) {}
+    bool put(T v)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        not_full_.wait(lk, [&] { return closed_ || bound_ == 0 || q_.size() < bound_; });
+        if (closed_) return false;
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+        return true;
+    }
+    bool get(T &out)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        not_empty_.wait(lk, [&] { return closed_ || !q_.empty(); });
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    size_t size() const
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        return q_.size();
+    }
+    bool empty() const { return size() == 0; }
+    void close()
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        closed_ = true;
+        not_empty_.notify_all();
+        not_full_.notify_all();
+    }
+
+private:
+    mutable std::mutex m_;
+    std::condition_variable not_empty_, not_full_;
+    std::deque<T> q_;
+    size_t bound_;
+    bool closed_ = false;
+};
+
+struct Bunch {
+    uint32_t identifier = 0;
+    std::vector<clsimcu_step> steps;
+};
+
+struct HostResult {
+    uint32_t identifier = 0;
+    std::vector<clsimcu_photon> photons;
+    std::vector<float> history;
+    uint64_t generated = 0, counted = 0;
+};
+
+struct Slot {
+    int index = 0;
+    cudaStream_t xfer = nullptr;
+    cudaEvent_t uploaded = nullptr, k_start = nullptr, k_stop = nullptr, counted = nullptr;
+    clsimcu_step *d_steps = nullptr, *h_steps = nullptr;
+    clsimcu_photon *d_photons = nullptr, *h_photons = nullptr;
+    float *d_history = nullptr, *h_history = nullptr;
+    uint32_t *d_counters = nullptr, *h_counters = nullptr;           // [0] hits, [1] work
+    unsigned long long *d_stats = nullptr, *h_stats = nullptr;      // [0] photons, [1] segments
+    uint32_t identifier = 0;
+    size_t num_steps = 0;
+    uint64_t generated = 0;
+};
+
+// Collects table arrays into one arena; pointers are fixed up after the upload.
+class Arena {
+public:
+    template <class T> size_t add(const std::vector<T> &v)
+    {
+        const size_t at = (bytes_.size() + 15) & ~size_t(15);
+        bytes_.resize(at + std::max<size_t>(16, v.size() * sizeof(T)), 0);
+        if (!v.empty()) std::memcpy(bytes_.data() + at, v.data(), v.size() * sizeof(T));
+        return at;
+    }
+    const std::vector<uint8_t> &bytes() const { return bytes_; }
+
+private:
+    std::vector<uint8_t> bytes_;
+};
+
+template <class T> const T *at(const uint8_t *base, size_t off) { return reinterpret_cast<const T *>(base + off); }
+
+} // namespace
+} // namespace clsimcu
+
+using namespace clsimcu;
+
+struct clsimcu_engine {
+    int device = 0;
+    int kernel_mode = CLSIMCU_KERNEL_FAST;
+    size_t max_items = 0, granularity = 1, max_hits = 0;
+    int history_entries = 0;
+    bool save_all = false;
+    SceneTables tables;
+    DevScene scene;
+    uint8_t *d_arena = nullptr;
+    uint64_t *d_rng_x = nullptr;
+    uint32_t *d_rng_a = nullptr;
+    size_t rng_n = 0;
+    int fast_blocks = 0, fast_threads = 0;
+    cudaStream_t compute = nullptr;
+    std::vector<Slot> slots;
+    BlockingQueue<Bunch> inbox{5};                 // queueToOpenCL_ depth 5 (…OpenCL.cxx:77)
+    BlockingQueue<int> free_slots{0}, in_flight{0};
+    BlockingQueue<std::shared_ptr<HostResult>> outbox{0};
+    std::thread submit_thread, drain_thread;
+    std::atomic<bool> stopping{false};
+    std::mutex error_mutex;
+    std::string async_error;
+    // statistics (…OpenCL.h:377-381)
+    std::mutex stats_mutex;
+    double device_ns = 0., host_ns = 0.;
+    uint64_t kernel_calls = 0, photons_generated = 0, photons_at_doms = 0;
+    std::chrono::steady_clock::time_point last_stamp;
+    // resident path
+    std::mutex compute_mutex;
+    clsimcu_step *d_res_steps = nullptr;
+    clsimcu_photon *d_res_photons = nullptr;
+    uint32_t *d_res_counters = nullptr, *h_res_counters = nullptr;
+    unsigned long long *d_res_stats = nullptr, *h_res_stats = nullptr;
+    uint64_t *d_tag_x = nullptr;
+    uint32_t *d_tag_a = nullptr;
+    size_t res_steps = 0, res_cap = 0;
+    uint64_t res_generated_per_run = 0;
+    uint32_t res_last_hits = 0;
+
+    void set_async_error(const std::string &m)
+    {
+        std::lock_guard<std::mutex> lk(error_mutex);
+        if (async_error.empty()) async_error = m;
+    }
+    bool check_async_error(std::string &m)
+    {
+        std::lock_guard<std::mutex> lk(error_mutex);
+        m = async_error;
+        return !async_error.empty();
+    }
+};
+
+namespace clsimcu {
+namespace {
+
+void upload_tables(clsimcu_engine &e)
+{
+    const SceneTables &t = e.tables;
+    Arena arena;
+    DevScene &s = e.scene;
+    std::memset(&s, 0, sizeof s);
+
+    // ---- medium
+    const MediumTables &m = t.medium;
+    DevMedium &dm = s.medium;
+    dm.num_layers = m.num_layers;
+    dm.z0 = m.z0; dm.h = m.h; dm.inv_h = 1.f / m.h;
+    dm.kappa = m.kappa; dm.A = m.A; dm.B = m.B; dm.D = m.D; dm.E = m.E; dm.alpha = m.alpha;
+    dm.inv_ref_wlen = m.inv_ref_wlen;
+    for (int i = 0; i < 5; ++i) { dm.n_phase[i] = m.n_phase[i]; dm.n_group[i] = m.n_group[i]; }
+    dm.c_light = m.c_light;
+    dm.scat_kind = m.scat_kind;
+    dm.f_sl = m.f_sl; dm.one_minus_f_sl = m.one_minus_f_sl; dm.g = m.g; dm.g2 = m.g2; dm.sl_beta = m.sl_beta;
+    dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
+    dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
+    dm.anisotropy = m.anisotropy; dm.pre_renorm = m.pre_renorm; dm.post_renorm = m.post_renorm;
+    for (int i = 0; i < 3; ++i) { dm.l[i] = m.l[i]; dm.rl[i] = m.rl[i]; }
+    dm.azx = m.azx; dm.azy = m.azy; dm.neg_azy = m.neg_azy; dm.B2 = m.B2;
+    for (int i = 0; i < 9; ++i) { dm.pre[i] = m.pre[i]; dm.post[i] = m.post[i]; }
+    std::vector<float> abs_dust(m.num_layers), abs_tau(m.num_layers);
+    for (int i = 0; i < m.num_layers; ++i) {
+        abs_dust[i] = m.D * m.a_dust400[i] + m.E;
+        abs_tau[i] = 1.f + 0.01f * m.delta_tau[i];
+    }
+    const size_t o_adust = arena.add(m.a_dust400), o_dtau = arena.add(m.delta_tau), o_b400 = arena.add(m.b400);
+    const size_t o_absd = arena.add(abs_dust), o_abst = arena.add(abs_tau);
+    const size_t o_tdist = arena.add(m.tilt_dist), o_tcorr = arena.add(m.tilt_corr);
+
+    // ---- wavelength generators and bias
+    if (t.generators.size() > static_cast<size_t>(kMaxWlenGenerators))
+        throw std::runtime_error("at most " + std::to_string(kMaxWlenGenerators) + " wavelength generators are supported");
+    s.num_generators = static_cast<int>(t.generators.size());
+    size_t o_gx[kMaxWlenGenerators], o_gd[kMaxWlenGenerators], o_gc[kMaxWlenGenerators];
+    for (int i = 0; i < s.num_generators; ++i) {
+        const WlenGeneratorTable &g = t.generators[i];
+        DevWlenGenerator &dg = s.generators[i];
+        dg.kind = g.kind; dg.n = g.n; dg.x0 = g.x0; dg.dx = g.dx;
+        dg.min_val = g.min_val; dg.range = g.range; dg.value = g.value;
+        o_gx[i] = arena.add(g.xs);
+        o_gd[i] = arena.add(g.density);
+        o_gc[i] = arena.add(g.cumulative);
+    }
+    s.bias.kind = t.bias.kind; s.bias.n = t.bias.n; s.bias.x0 = t.bias.x0; s.bias.dx = t.bias.dx; s.bias.value = t.bias.value;
+    const size_t o_bias = arena.add(t.bias.v);
+
+    // ---- geometry
+    const GeometryTables &g = t.geometry;
+    DevGeometry &dg = s.geo;
+    size_t o_grid[kMaxSubdetectors] = {0};
+    size_t o_sx = 0, o_sy = 0, o_smin = 0, o_smax = 0, o_sset = 0, o_lcount = 0, o_lstart = 0, o_lheight = 0, o_l2d = 0;
+    size_t o_tdx = 0, o_tdy = 0, o_tz = 0, o_tstart = 0, o_mx = 0, o_my = 0, o_sid = 0, o_doff = 0, o_dids = 0;
+    if (t.has_geometry) {
+        dg.num_strings = g.num_strings; dg.num_sets = g.num_sets; dg.max_layers = g.max_layers;
+        dg.num_grids = static_cast<int>(g.grids.size());
+        dg.layer_table_size = static_cast<int>(g.layer_to_dom.size());
+        dg.om_radius = g.om_radius; dg.string_max_radius = g.string_max_radius;
+        dg.tmpl_scale_x = g.tmpl_scale_x; dg.tmpl_scale_y = g.tmpl_scale_y;
+        for (int i = 0; i < dg.num_grids; ++i) {
+            const CellGridTable &c = g.grids[i];
+            DevCellGrid &dc = dg.grids[i];
+            dc.num_x = c.num_x; dc.num_y = c.num_y;
+            dc.start_x = c.start_x; dc.start_y = c.start_y; dc.width_x = c.width_x; dc.width_y = c.width_y;
+            dc.inv_width_x = 1.f / c.width_x; dc.inv_width_y = 1.f / c.width_y;
+            o_grid[i] = arena.add(c.cell_to_string);
+        }
+        o_sx = arena.add(g.string_x); o_sy = arena.add(g.string_y);
+        o_smin = arena.add(g.string_min_z); o_smax = arena.add(g.string_max_z);
+        o_sset = arena.add(g.string_set);
+        o_lcount = arena.add(g.set_layer_count); o_lstart = arena.add(g.set_start_z); o_lheight = arena.add(g.set_layer_height);
+        o_l2d = arena.add(g.layer_to_dom);
+        o_tdx = arena.add(g.tmpl_dx); o_tdy = arena.add(g.tmpl_dy); o_tz = arena.add(g.tmpl_z);
+        o_tstart = arena.add(g.string_tmpl_start);
+        o_mx = arena.add(g.string_mean_x); o_my = arena.add(g.string_mean_y);
+        // index -> ID tables with the reference's range checks (…OpenCL.cxx:1579-1590)
+        std::vector<int16_t> sid(g.num_strings);
+        std::vector<uint32_t> doff(g.num_strings);
+        std::vector<uint16_t> dids;
+        for (int i = 0; i < g.num_strings; ++i) {
+            const int id = g.string_index_to_id[i];
+            if (id < -32768 || id > 32767)
+                throw std::runtime_error("Your detector I3Geometry uses a string ID \"" + std::to_string(id) + "\". Large IDs like that are currently not supported by clsim.");
+            sid[i] = static_cast<int16_t>(id);
+            doff[i] = static_cast<uint32_t>(dids.size());
+            for (uint32_t d : g.dom_index_to_id[i]) {
+                if (d > 65535u)
+                    throw std::runtime_error("Your detector I3Geometry uses a OM ID \"" + std::to_string(d) + "\". Large IDs like that are currently not supported by clsim.");
+                dids.push_back(static_cast<uint16_t>(d));
+            }
+        }
+        o_sid = arena.add(sid); o_doff = arena.add(doff); o_dids = arena.add(dids);
+    }
+
+    s.stop_detected = t.stop_detected; s.save_all = t.save_all; s.fixed_abs = t.fixed_abs; s.pancake = t.pancake;
+    s.history_entries = t.history_entries;
+    s.prescale = t.prescale; s.fixed_abs_lens = t.fixed_abs_lens; s.pancake_factor = t.pancake_factor;
+
+    CUDA_OK(cudaMalloc(&e.d_arena, arena.bytes().size()));
+    CUDA_OK(cudaMemcpy(e.d_arena, arena.bytes().data(), arena.bytes().size(), cudaMemcpyHostToDevice));
+    const uint8_t *b = e.d_arena;
+    dm.a_dust400 = at<float>(b, o_adust); dm.delta_tau = at<float>(b, o_dtau); dm.b400 = at<float>(b, o_b400);
+    dm.abs_dust = at<float>(b, o_absd); dm.abs_tau = at<float>(b, o_abst);
+    dm.tilt_dist = at<float>(b, o_tdist); dm.tilt_corr = at<float>(b, o_tcorr);
+    for (int i = 0; i < s.num_generators; ++i) {
+        s.generators[i].xs = at<float>(b, o_gx[i]);
+        s.generators[i].density = at<float>(b, o_gd[i]);
+        s.generators[i].cumulative = at<float>(b, o_gc[i]);
+    }
+    s.bias.v = at<float>(b, o_bias);
+    if (t.has_geometry) {
+        for (int i = 0; i < dg.num_grids; ++i) dg.grids[i].cell_to_string = at<uint16_t>(b, o_grid[i]);
+        dg.string_x = at<float>(b, o_sx); dg.string_y = at<float>(b, o_sy);
+        dg.string_min_z = at<float>(b, o_smin); dg.string_max_z = at<float>(b, o_smax);
+        dg.string_set = at<uint8_t>(b, o_sset);
+        dg.set_layer_count = at<uint16_t>(b, o_lcount);
+        dg.set_start_z = at<float>(b, o_lstart); dg.set_layer_height = at<float>(b, o_lheight);
+        dg.layer_to_dom = at<uint16_t>(b, o_l2d);
+        dg.tmpl_dx = at<int16_t>(b, o_tdx); dg.tmpl_dy = at<int16_t>(b, o_tdy); dg.tmpl_z = at<float>(b, o_tz);
+        dg.string_tmpl_start = at<uint32_t>(b, o_tstart);
+        dg.string_mean_x = at<float>(b, o_mx); dg.string_mean_y = at<float>(b, o_my);
+        dg.string_index_to_id = at<int16_t>(b, o_sid);
+        dg.dom_id_offset = at<uint32_t>(b, o_doff);
+        dg.dom_ids = at<uint16_t>(b, o_dids);
+    }
+}
+
+std::string prime_cache_path()
+{
+    if (const char *p = std::getenv("CLSIMCU_SAFEPRIMES_CACHE")) return p;
+    // next to the shared library: <dir of libclsimcuda.so>/data/safeprimes_base32.bin
+    Dl_info info;
+    if (dladdr(reinterpret_cast<const void *>(&prime_cache_path), &info) && info.dli_fname) {
+        std::string path(info.dli_fname);
+        const size_t slash = path.rfind('/');
+        if (slash != std::string::npos) return path.substr(0, slash) + "/data/safeprimes_base32.bin";
+    }
+    return std::string();
+}
+
+void launch(clsimcu_engine &e, const LaunchArgs &args, cudaStream_t stream)
+{
+    int rc;
+    if (e.kernel_mode == CLSIMCU_KERNEL_REFERENCE) rc = launch_reference_kernel(e.scene, args, stream);
+    else rc = launch_fast_kernel(e.scene, args, e.fast_blocks, stream);
+    if (rc != 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+}
+
+void submit_loop(clsimcu_engine *e)
+{
+    try {
+        CUDA_OK(cudaSetDevice(e->device));
+        Bunch bunch;
+        while (e->inbox.get(bunch)) {
+            int si;
+            if (!e->free_slots.get(si)) break;
+            Slot &s = e->slots[si];
+            s.identifier = bunch.identifier;
+            s.num_steps = bunch.steps.size();
+            uint64_t generated = 0;
+            for (const clsimcu_step &st : bunch.steps) generated += st.num_photons;
+            s.generated = generated;
+            std::memcpy(s.h_steps, bunch.steps.data(), s.num_steps * sizeof(clsimcu_step));
+            CUDA_OK(cudaMemcpyAsync(s.d_steps, s.h_steps, s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
+            CUDA_OK(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), s.xfer));
+            CUDA_OK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.xfer));
+            CUDA_OK(cudaEventRecord(s.uploaded, s.xfer));
+            {
+                std::lock_guard<std::mutex> lk(e->compute_mutex);
+                CUDA_OK(cudaStreamWaitEvent(e->compute, s.uploaded, 0));
+                CUDA_OK(cudaEventRecord(s.k_start, e->compute));
+                LaunchArgs a{};
+                a.steps = s.d_steps;
+                a.num_steps = static_cast<uint32_t>(s.num_steps);
+                a.max_hits = static_cast<uint32_t>(e->max_hits);
+                a.photons = s.d_photons;
+                a.history = s.d_history;
+                a.hit_counter = s.d_counters;
+                a.work_counter = s.d_counters + 1;
+                a.stats = s.d_stats;
+                a.rng_x = e->d_rng_x;
+                a.rng_a = e->d_rng_a;
+                a.count_stats = 0;
+                launch(*e, a, e->compute);
+                CUDA_OK(cudaEventRecord(s.k_stop, e->compute));
+            }
+            CUDA_OK(cudaStreamWaitEvent(s.xfer, s.k_stop, 0));
+            CUDA_OK(cudaMemcpyAsync(s.h_counters, s.d_counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.xfer));
+            CUDA_OK(cudaEventRecord(s.counted, s.xfer));
+            if (!e->in_flight.put(si)) break;
+        }
+    } catch (const std::exception &ex) {
+        e->set_async_error(ex.what());
+    }
+    e->in_flight.close();
+}
+
+// Device ring layout -> forward order, unused rows NaN (…OpenCL.cxx:940-989)
+void unroll_history(const float *raw, const clsimcu_photon *photons, size_t n, int entries, std::vector<float> &out)
+{
+    out.assign(n * entries * 4, std::nanf(""));
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t scat = photons[i].num_scatters;
+        if (scat == 0) continue;
+        const uint32_t recorded = std::min<uint32_t>(scat, static_cast<uint32_t>(entries));
+        uint32_t at = (scat <= static_cast<uint32_t>(entries)) ? 0u : scat % entries;
+        for (uint32_t j = 0; j < recorded; ++j) {
+            std::memcpy(&out[(i * entries + j) * 4], &raw[(i * entries + at) * 4], 4 * sizeof(float));
+            if (++at >= static_cast<uint32_t>(entries)) at = 0;
+        }
+    }
+}
+
+void drain_loop(clsimcu_engine *e)
+{
+    try {
+        CUDA_OK(cudaSetDevice(e->device));
+        int si;
+        while (e->in_flight.get(si)) {
+            Slot &s = e->slots[si];
+            CUDA_OK(cudaEventSynchronize(s.counted));
+            const auto now = std::chrono::steady_clock::now();
+            float k_ms = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&k_ms, s.k_start, s.k_stop));
+            const uint32_t counted = s.h_counters[0];
+            const size_t n = std::min<size_t>(counted, e->max_hits);
+            if (counted > e->max_hits)
+                std::fprintf(stderr, "clsimcuda: Maximum number of photons exceeded, only receiving %zu of %u photons\n", e->max_hits, counted);
+            auto res = std::make_shared<HostResult>();
+            res->identifier = s.identifier;
+            res->generated = s.generated;
+            res->counted = counted;
+            if (n > 0) {
+                CUDA_OK(cudaMemcpyAsync(s.h_photons, s.d_photons, n * sizeof(clsimcu_photon), cudaMemcpyDeviceToHost, s.xfer));
+                if (e->history_entries > 0)
+                    CUDA_OK(cudaMemcpyAsync(s.h_history, s.d_history, n * e->history_entries * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.xfer));
+                CUDA_OK(cudaStreamSynchronize(s.xfer));
+                res->photons.assign(s.h_photons, s.h_photons + n);
+                if (e->history_entries > 0) unroll_history(s.h_history, s.h_photons, n, e->history_entries, res->history);
+            }
+            {
+                std::lock_guard<std::mutex> lk(e->stats_mutex);
+                e->device_ns += static_cast<double>(k_ms) * 1e6;
+                e->host_ns += std::chrono::duration<double, std::nano>(now - e->last_stamp).count();
+                e->last_stamp = now;
+                e->kernel_calls += 1;
+                e->photons_generated += s.generated;
+                e->photons_at_doms += counted;
+            }
+            e->free_slots.put(si);
+            e->outbox.put(res);
+        }
+    } catch (const std::exception &ex) {
+        e->set_async_error(ex.what());
+    }
+    e->outbox.close();
+}
+
+void free_engine(clsimcu_engine *e)
+{
+    cudaSetDevice(e->device);
+    for (Slot &s : e->slots) {
+        if (s.xfer) cudaStreamSynchronize(s.xfer);
+        cudaFree(s.d_steps); cudaFree(s.d_photons); cudaFree(s.d_history); cudaFree(s.d_counters); cudaFree(s.d_stats);
+        cudaFreeHost(s.h_steps); cudaFreeHost(s.h_photons); cudaFreeHost(s.h_history); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_stats);
+        if (s.uploaded) cudaEventDestroy(s.uploaded);
+        if (s.k_start) cudaEventDestroy(s.k_start);
+        if (s.k_stop) cudaEventDestroy(s.k_stop);
+        if (s.counted) cudaEventDestroy(s.counted);
+        if (s.xfer) cudaStreamDestroy(s.xfer);
+    }
+    cudaFree(e->d_arena); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
+    cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
+    cudaFree(e->d_tag_x); cudaFree(e->d_tag_a);
+    cudaFreeHost(e->h_res_counters); cudaFreeHost(e->h_res_stats);
+    if (e->compute) cudaStreamDestroy(e->compute);
+    delete e;
+}
+
+} // namespace
+} // namespace clsimcu
+
+extern "C" {
+
+const char *clsimcu_last_error(void) { return t_last_error.c_str(); }
+const char *clsimcu_version(void) { return "clsimcuda 0.1 (sm_100a)"; }
+size_t clsimcu_sizeof_config(void) { return sizeof(clsimcu_config); }
+
+int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
+{
+    if (!config || !out) return fail(CLSIMCU_ERR_INVALID, "config or engine pointer is NULL");
+    *out = nullptr;
+    if (config->struct_size != static_cast<int32_t>(sizeof(clsimcu_config)))
+        return fail(CLSIMCU_ERR_INVALID, "clsimcu_config.struct_size does not match this library");
+    if (config->kernel_mode != CLSIMCU_KERNEL_FAST && config->kernel_mode != CLSIMCU_KERNEL_REFERENCE)
+        return fail(CLSIMCU_ERR_INVALID, "unknown kernel_mode");
+    clsimcu_engine *e = new clsimcu_engine();
+    try {
+        build_scene_tables(*config, e->tables);
+    } catch (const std::exception &ex) {
+        delete e;
+        return fail(CLSIMCU_ERR_INVALID, ex.what());
+    }
+    try {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count == 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); libclsimcuda has no CPU fallback");
+        if (config->device < 0 || config->device >= count) throw CudaError("CUDA device ordinal " + std::to_string(config->device) + " does not exist");
+        e->device = config->device;
+        CUDA_OK(cudaSetDevice(e->device));
+        e->kernel_mode = config->kernel_mode;
+        e->history_entries = config->photon_history_entries;
+        e->save_all = config->save_all_photons != 0;
+        e->granularity = config->workgroup_size ? config->workgroup_size : 1;
+        e->max_items = config->max_num_workitems ? config->max_num_workitems : 10240; // class default (…OpenCL.cxx:94)
+        if (e->max_items % e->granularity != 0)
+            throw std::runtime_error("The maximum number of work items (" + std::to_string(e->max_items) + ") must be a multiple of the workgroup size (" + std::to_string(e->granularity) + ").");
+        // output capacity (…OpenCL.cxx:266-277)
+        size_t per_item = config->output_photons_per_workitem ? config->output_photons_per_workitem : 10;
+        if (e->save_all && !config->output_photons_per_workitem) {
+            per_item = static_cast<size_t>(10000. * config->save_all_photons_prescale);
+            if (per_item < 1) per_item = 1;
+        }
+        e->max_hits = std::min<size_t>(e->max_items * per_item, 0xffffffffull);
+        if (!e->save_all && e->max_hits < 1000) e->max_hits = 1000;
+
+        upload_tables(*e);
+        if (e->kernel_mode == CLSIMCU_KERNEL_FAST) {
+            const char *why = nullptr;
+            if (!fast_kernel_supports(e->scene, &why))
+                throw std::runtime_error(std::string("the fast kernel does not support this configuration (") + why + "); use CLSIMCU_KERNEL_REFERENCE");
+            fast_kernel_geometry(e->device, &e->fast_blocks, &e->fast_threads);
+        }
+
+        // RNG streams: one per work item (reference order) or one per resident thread (fast)
+        size_t need = (e->kernel_mode == CLSIMCU_KERNEL_REFERENCE) ? e->max_items : static_cast<size_t>(e->fast_blocks) * e->fast_threads;
+        e->rng_n = config->rng_n ? static_cast<size_t>(config->rng_n) : need;
+        if (e->rng_n < need)
+            throw std::runtime_error("rng_n (" + std::to_string(e->rng_n) + ") is smaller than the number of RNG streams this configuration needs (" + std::to_string(need) + ")");
+        std::vector<uint32_t> a(e->rng_n);
+        std::vector<uint64_t> x(e->rng_n);
+        if (config->rng_a) {
+            if (!config->rng_x) throw std::runtime_error("rng_a given without rng_x");
+            std::memcpy(a.data(), config->rng_a, e->rng_n * sizeof(uint32_t));
+            std::memcpy(x.data(), config->rng_x, e->rng_n * sizeof(uint64_t));
+        } else {
+            safeprime_multipliers(config->rng_first_multiplier, e->rng_n, a.data(), prime_cache_path());
+            seed_rng_states(config->rng_seed, a.data(), x.data(), e->rng_n);
+        }
+        CUDA_OK(cudaMalloc(&e->d_rng_x, e->rng_n * sizeof(uint64_t)));
+        CUDA_OK(cudaMalloc(&e->d_rng_a, e->rng_n * sizeof(uint32_t)));
+        CUDA_OK(cudaMemcpy(e->d_rng_x, x.data(), e->rng_n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(e->d_rng_a, a.data(), e->rng_n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+        CUDA_OK(cudaStreamCreateWithFlags(&e->compute, cudaStreamNonBlocking));
+        const int nslots = config->enable_double_buffering ? 3 : 1;
+        e->slots.resize(nslots);
+        for (int i = 0; i < nslots; ++i) {
+            Slot &s = e->slots[i];
+            s.index = i;
+            CUDA_OK(cudaStreamCreateWithFlags(&s.xfer, cudaStreamNonBlocking));
+            CUDA_OK(cudaEventCreate(&s.uploaded));
+            CUDA_OK(cudaEventCreate(&s.k_start));
+            CUDA_OK(cudaEventCreate(&s.k_stop));
+            CUDA_OK(cudaEventCreate(&s.counted));
+            CUDA_OK(cudaMalloc(&s.d_steps, e->max_items * sizeof(clsimcu_step)));
+            CUDA_OK(cudaMalloc(&s.d_photons, e->max_hits * sizeof(clsimcu_photon)));
+            CUDA_OK(cudaMalloc(&s.d_counters, 2 * sizeof(uint32_t)));
+            CUDA_OK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
+            CUDA_OK(cudaHostAlloc(&s.h_steps, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&s.h_photons, e->max_hits * sizeof(clsimcu_photon), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&s.h_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            if (e->history_entries > 0) {
+                const size_t hb = e->max_hits * e->history_entries * 4 * sizeof(float);
+                CUDA_OK(cudaMalloc(&s.d_history, hb));
+                CUDA_OK(cudaHostAlloc(&s.h_history, hb, cudaHostAllocDefault));
+            }
+            e->free_slots.put(i);
+        }
+        e->last_stamp = std::chrono::steady_clock::now();
+        e->submit_thread = std::thread(submit_loop, e);
+        e->drain_thread = std::thread(drain_loop, e);
+    } catch (const CudaError &ex) {
+        const std::string msg = ex.what();
+        free_engine(e);
+        return fail(CLSIMCU_ERR_CUDA, msg);
+    } catch (const std::exception &ex) {
+        const std::string msg = ex.what();
+        free_engine(e);
+        return fail(CLSIMCU_ERR_INVALID, msg);
+    }
+    *out = e;
+    return CLSIMCU_OK;
+}
+
+int clsimcu_destroy(clsimcu_engine *e)
+{
+    if (!e) return fail(CLSIMCU_ERR_INVALID, "engine is NULL");
+    e->stopping = true;
+    e->inbox.close();
+    e->free_slots.close();
+    if (e->submit_thread.joinable()) e->submit_thread.join();
+    e->in_flight.close();
+    if (e->drain_thread.joinable()) e->drain_thread.join();
+    e->outbox.close();
+    free_engine(e);
+    return CLSIMCU_OK;
+}
+
+int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint32_t identifier)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    std::string err;
+    if (e->check_async_error(err)) return fail(CLSIMCU_ERR_CUDA, err);
+    // same preconditions, same order as EnqueueSteps (…OpenCL.cxx:1527-1540)
+    if (!steps) return fail(CLSIMCU_ERR_INVALID, "Steps pointer is (null)!");
+    if (n == 0) return fail(CLSIMCU_ERR_INVALID, "Steps are empty!");
+    if (n > e->max_items) return fail(CLSIMCU_ERR_INVALID, "Number of steps is greater than maximum number of work items!");
+    if (n % e->granularity != 0) return fail(CLSIMCU_ERR_INVALID, "The number of steps is not a multiple of the workgroup size!");
+    Bunch b;
+    b.identifier = identifier;
+    b.steps.assign(steps, steps + n);
+    if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    return CLSIMCU_OK;
+}
+
+int clsimcu_get_result(clsimcu_engine *e, clsimcu_result *r)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    if (!r) return fail(CLSIMCU_ERR_INVALID, "result pointer is NULL");
+    std::shared_ptr<HostResult> res;
+    if (!e->outbox.get(res)) {
+        std::string err;
+        if (e->check_async_error(err)) return fail(CLSIMCU_ERR_CUDA, err);
+        return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    }
+    auto *holder = new std::shared_ptr<HostResult>(res);
+    static clsimcu_photon empty_photon;
+    r->identifier = res->identifier;
+    r->reserved0 = 0;
+    r->num_photons = res->photons.size();
+    r->photons = res->photons.empty() ? &empty_photon : res->photons.data();
+    r->history = (e->history_entries > 0 && !res->history.empty()) ? res->history.data() : nullptr;
+    r->num_photons_generated = res->generated;
+    r->num_hits_counted = res->counted;
+    r->opaque = holder;
+    return CLSIMCU_OK;
+}
+
+int clsimcu_release_result(clsimcu_engine *, clsimcu_result *r)
+{
+    if (!r) return fail(CLSIMCU_ERR_INVALID, "result pointer is NULL");
+    delete static_cast<std::shared_ptr<HostResult> *>(r->opaque);
+    std::memset(r, 0, sizeof *r);
+    return CLSIMCU_OK;
+}
+
+int clsimcu_queue_size(clsimcu_engine *e, size_t *size)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    *size = e->inbox.size();
+    return CLSIMCU_OK;
+}
+
+int clsimcu_more_photons_available(clsimcu_engine *e, int *available)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    *available = e->outbox.empty() ? 0 : 1;
+    return CLSIMCU_OK;
+}
+
+int clsimcu_workgroup_size(clsimcu_engine *e, size_t *size)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    *size = e->granularity;
+    return CLSIMCU_OK;
+}
+
+int clsimcu_max_num_workitems(clsimcu_engine *e, size_t *size)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    *size = e->max_items;
+    return CLSIMCU_OK;
+}
+
+int clsimcu_get_statistics(clsimcu_engine *e, double out[8])
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    std::lock_guard<std::mutex> lk(e->stats_mutex);
+    const double gen = static_cast<double>(e->photons_generated);
+    out[0] = e->device_ns;
+    out[1] = e->host_ns;
+    out[2] = static_cast<double>(e->kernel_calls);
+    out[3] = gen;
+    out[4] = static_cast<double>(e->photons_at_doms);
+    out[5] = e->device_ns / gen;
+    out[6] = e->host_ns / gen;
+    out[7] = e->device_ns / e->host_ns;
+    return CLSIMCU_OK;
+}
+
+// ---- resident path ---------------------------------------------------------------------------
+
+int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t n)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (!steps || n == 0) return fail(CLSIMCU_ERR_INVALID, "Steps are empty!");
+    if (n > e->max_items) return fail(CLSIMCU_ERR_INVALID, "Number of steps is greater than maximum number of work items!");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        if (!e->d_res_steps) {
+            CUDA_OK(cudaMalloc(&e->d_res_steps, e->max_items * sizeof(clsimcu_step)));
+            e->res_cap = e->max_hits;
+            CUDA_OK(cudaMalloc(&e->d_res_photons, e->res_cap * sizeof(clsimcu_photon)));
+            CUDA_OK(cudaMalloc(&e->d_res_counters, 2 * sizeof(uint32_t)));
+            CUDA_OK(cudaMalloc(&e->d_res_stats, 2 * sizeof(unsigned long long)));
+            CUDA_OK(cudaHostAlloc(&e->h_res_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&e->h_res_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            if (e->save_all) {
+                CUDA_OK(cudaMalloc(&e->d_tag_x, 2 * e->res_cap * sizeof(uint64_t)));
+                CUDA_OK(cudaMalloc(&e->d_tag_a, e->res_cap * sizeof(uint32_t)));
+            }
+        }
+        CUDA_OK(cudaMemcpy(e->d_res_steps, steps, n * sizeof(clsimcu_step), cudaMemcpyHostToDevice));
+        e->res_steps = n;
+        uint64_t gen = 0;
+        for (size_t i = 0; i < n; ++i) gen += steps[i].num_photons;
+        e->res_generated_per_run = gen;
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint64_t *photons_generated, uint64_t *hits_counted,
+                         uint64_t *segments)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (e->res_steps == 0) return fail(CLSIMCU_ERR_STATE, "no resident bunch uploaded");
+    if (repeat < 1) return fail(CLSIMCU_ERR_INVALID, "repeat must be >= 1");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        std::vector<cudaEvent_t> ev(2 * repeat);
+        for (auto &x : ev) CUDA_OK(cudaEventCreate(&x));
+        uint64_t hits = 0, segs = 0;
+        double ms = 0.;
+        CUDA_OK(cudaMemsetAsync(e->d_res_stats, 0, 2 * sizeof(unsigned long long), e->compute));
+        for (int r = 0; r < repeat; ++r) {
+            CUDA_OK(cudaMemsetAsync(e->d_res_counters, 0, 2 * sizeof(uint32_t), e->compute));
+            LaunchArgs a{};
+            a.steps = e->d_res_steps;
+            a.num_steps = static_cast<uint32_t>(e->res_steps);
+            a.max_hits = static_cast<uint32_t>(e->res_cap);
+            a.photons = e->d_res_photons;
+            a.history = nullptr;
+            a.hit_counter = e->d_res_counters;
+            a.work_counter = e->d_res_counters + 1;
+            a.stats = e->d_res_stats;
+            a.rng_x = e->d_rng_x;
+            a.rng_a = e->d_rng_a;
+            a.rng_tag_x = e->d_tag_x;
+            a.rng_tag_a = e->d_tag_a;
+            a.count_stats = 1;
+            CUDA_OK(cudaEventRecord(ev[2 * r], e->compute));
+            launch(*e, a, e->compute);
+            CUDA_OK(cudaEventRecord(ev[2 * r + 1], e->compute));
+            CUDA_OK(cudaMemcpyAsync(e->h_res_counters, e->d_res_counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->compute));
+            CUDA_OK(cudaStreamSynchronize(e->compute));
+            hits += e->h_res_counters[0];
+            e->res_last_hits = e->h_res_counters[0];
+            float one = 0.f;
+            CUDA_OK(cudaEventElapsedTime(&one, ev[2 * r], ev[2 * r + 1]));
+            ms += one;
+        }
+        CUDA_OK(cudaMemcpy(e->h_res_stats, e->d_res_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        segs = e->h_res_stats[1];
+        for (auto &x : ev) cudaEventDestroy(x);
+        if (kernel_ms) *kernel_ms = ms;
+        if (photons_generated) *photons_generated = e->res_generated_per_run * static_cast<uint64_t>(repeat);
+        if (hits_counted) *hits_counted = hits;
+        if (segments) *segments = segs;
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+int clsimcu_download_resident(clsimcu_engine *e, clsimcu_photon *out, size_t cap, size_t *n)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        const size_t have = std::min<size_t>(e->res_last_hits, e->res_cap);
+        const size_t k = std::min(have, cap);
+        if (k > 0 && out) CUDA_OK(cudaMemcpy(out, e->d_res_photons, k * sizeof(clsimcu_photon), cudaMemcpyDeviceToHost));
+        if (n) *n = have;
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+int clsimcu_download_resident_rng_tags(clsimcu_engine *e, uint64_t *x, uint32_t *a, size_t cap)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (!e->d_tag_x) return fail(CLSIMCU_ERR_STATE, "RNG tags are only recorded in save-all mode on the resident path");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        const size_t k = std::min(std::min<size_t>(e->res_last_hits, e->res_cap), cap);
+        if (k > 0) {
+            CUDA_OK(cudaMemcpy(x, e->d_tag_x, 2 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(a, e->d_tag_a, k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        }
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+// ---- test hooks --------------------------------------------------------------------------------
+
+int clsimcu_rng_get(clsimcu_engine *e, uint64_t *x, uint32_t *a, size_t n)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (n > e->rng_n) return fail(CLSIMCU_ERR_INVALID, "more RNG streams requested than exist");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        CUDA_OK(cudaStreamSynchronize(e->compute));
+        if (x) CUDA_OK(cudaMemcpy(x, e->d_rng_x, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (a) CUDA_OK(cudaMemcpy(a, e->d_rng_a, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+int clsimcu_rng_set(clsimcu_engine *e, const uint64_t *x, const uint32_t *a, size_t n)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (n > e->rng_n) return fail(CLSIMCU_ERR_INVALID, "more RNG streams given than exist");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        CUDA_OK(cudaStreamSynchronize(e->compute));
+        if (x) CUDA_OK(cudaMemcpy(e->d_rng_x, x, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        if (a) CUDA_OK(cudaMemcpy(e->d_rng_a, a, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+static int copy_text(const std::string &s, char *buf, size_t cap, size_t *needed)
+{
+    if (needed) *needed = s.size() + 1;
+    if (!buf) return CLSIMCU_OK;
+    if (cap < s.size() + 1) return fail(CLSIMCU_ERR_INVALID, "buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return CLSIMCU_OK;
+}
+
+int clsimcu_describe_tables(clsimcu_engine *e, char *buf, size_t cap, size_t *needed)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    return copy_text(describe_scene_tables(e->tables), buf, cap, needed);
+}
+
+int clsimcu_describe_tables_from_config(const clsimcu_config *config, char *buf, size_t cap, size_t *needed)
+{
+    if (!config) return fail(CLSIMCU_ERR_INVALID, "config is NULL");
+    if (config->struct_size != static_cast<int32_t>(sizeof(clsimcu_config)))
+        return fail(CLSIMCU_ERR_INVALID, "clsimcu_config.struct_size does not match this library");
+    try {
+        SceneTables t;
+        build_scene_tables(*config, t);
+        return copy_text(describe_scene_tables(t), buf, cap, needed);
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_INVALID, ex.what());
+    }
+}
+
+int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a)
+{
+    if (!a && n) return fail(CLSIMCU_ERR_INVALID, "output pointer is NULL");
+    try {
+        safeprime_multipliers(first, n, a, prime_cache_path());
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_INVALID, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+} // extern "C"

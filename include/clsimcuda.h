@@ -1,0 +1,296 @@
+/*
+ * clsimcuda.h -- C ABI of libclsimcuda.so, the B200 (sm_100a) step -> photon engine.
+ *
+ * This is the drop-in boundary for clsim's step-to-photon hot path.  Every entry
+ * point below is what a reference-side I3CLSimStepToPhotonConverterCUDA (C++,
+ * INTEGRATION.md) binds; each cites the reference interface it replaces.  All
+ * citations are relative to the reference tree (claudiok/clsim).
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions cross the
+ * boundary.  Every function returns CLSIMCU_OK (0) or a negative error code and
+ * leaves a human-readable message in clsimcu_last_error() (thread-local).
+ * Units follow the reference (I3Units): metres, nanoseconds, radians; wavelengths
+ * in METRES (400 nm == 400e-9).
+ *
+ * The configuration structs carry the *model-level* numbers in double precision,
+ * exactly what the reference's description objects hold (I3CLSimMediumProperties,
+ * I3CLSimSimpleGeometry, I3CLSimRandomValue*, I3CLSimFunction*).  The library does
+ * the flattening the reference does in its code generators
+ * (private/opencl/I3CLSimHelperGenerate{Geometry,MediumProperties}Source*.cxx):
+ * float-literal rounding, cell grids, string sets, z layers, quantised DOM
+ * positions, cumulative wavelength tables.
+ */
+#ifndef CLSIMCUDA_H_INCLUDED
+#define CLSIMCUDA_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLSIMCU_OK                 0
+#define CLSIMCU_ERR_INVALID       -1   /* bad argument / violated precondition        */
+#define CLSIMCU_ERR_UNSUPPORTED   -2   /* model class or option outside the hot path   */
+#define CLSIMCU_ERR_CUDA          -3   /* CUDA runtime failure (no CPU fallback)       */
+#define CLSIMCU_ERR_STATE         -4   /* wrong life-cycle state                       */
+#define CLSIMCU_ERR_INTERRUPTED   -5   /* engine is shutting down                      */
+
+/* ---- wire formats ------------------------------------------------------- */
+
+/* 48-byte step record; bit-identical to struct I3CLSimStep
+ * (resources/kernels/propagation_kernel.h.cl:52-63,
+ *  public/clsim/I3CLSimStep.h:68-155). */
+typedef struct clsimcu_step {
+    float x, y, z, t;                 /* posAndTime                       */
+    float theta, phi, length, beta;   /* dirAndLengthAndBeta              */
+    uint32_t num_photons;
+    float weight;
+    uint32_t identifier;
+    uint8_t source_type;              /* 0 = Cherenkov, >=1 = flasher #   */
+    uint8_t dummy1;
+    uint16_t dummy2;
+} clsimcu_step;
+
+/* 80-byte photon record; bit-identical to struct I3CLSimPhoton
+ * (resources/kernels/propagation_kernel.h.cl:65-81,
+ *  public/clsim/I3CLSimPhoton.h:67-213).  string_id / om_id are the real IDs
+ * (the index -> ID rewrite of I3CLSimStepToPhotonConverterOpenCL.cxx:1565-1619
+ * is done on the device). */
+typedef struct clsimcu_photon {
+    float x, y, z, t;                 /* position relative to the hit DOM, time */
+    float theta, phi;                 /* direction of travel                    */
+    float wavelength;
+    float cherenkov_dist;
+    uint32_t num_scatters;
+    float weight;
+    uint32_t identifier;
+    int16_t string_id;
+    uint16_t om_id;
+    float start_x, start_y, start_z, start_t;
+    float start_theta, start_phi;
+    float group_velocity;
+    float dist_in_abs_lens;
+} clsimcu_photon;
+
+/* ---- configuration (model-level, double precision) ---------------------- */
+
+/* A wavelength generator (reference: I3CLSimRandomValue subclasses handed to
+ * SetWlenGenerators, public/clsim/I3CLSimStepToPhotonConverter.h:90-100). */
+#define CLSIMCU_WLEN_INTERP_EQUAL    0  /* I3CLSimRandomValueInterpolatedDistribution(xFirst,xSpacing,y) */
+#define CLSIMCU_WLEN_INTERP_UNEQUAL  1  /* I3CLSimRandomValueInterpolatedDistribution(x,y)               */
+#define CLSIMCU_WLEN_NO_DISPERSION   2  /* I3CLSimRandomValueWlenCherenkovNoDispersion(from,to)          */
+#define CLSIMCU_WLEN_CONSTANT        3  /* I3CLSimRandomValueConstant(value)                             */
+typedef struct clsimcu_wlen_generator {
+    int32_t kind;
+    int32_t n;            /* entries in y (and x)                               */
+    double x0, dx;        /* INTERP_EQUAL                                       */
+    const double *x;      /* INTERP_UNEQUAL                                     */
+    const double *y;      /* INTERP_*: un-normalised density at the nodes       */
+    double from_wlen;     /* NO_DISPERSION                                      */
+    double to_wlen;
+    double value;         /* CONSTANT                                           */
+} clsimcu_wlen_generator;
+
+/* Wavelength bias (reference: SetWlenBias; I3CLSimFunctionFromTable in equal
+ * spacing mode, or I3CLSimFunctionConstant). */
+#define CLSIMCU_BIAS_CONSTANT 0
+#define CLSIMCU_BIAS_TABLE    1
+typedef struct clsimcu_wlen_bias {
+    int32_t kind;
+    int32_t n;
+    double x0, dx;
+    const double *v;
+    double value;         /* CONSTANT */
+} clsimcu_wlen_bias;
+
+/* Layered medium (reference: I3CLSimMediumProperties filled the way
+ * python/MakeIceCubeMediumProperties.py:166-230 fills it). */
+#define CLSIMCU_SCAT_MIXED_SL_HG 0   /* I3CLSimRandomValueMixed(f, SimplifiedLiu(g), HenyeyGreenstein(g)) */
+#define CLSIMCU_SCAT_HG          1   /* I3CLSimRandomValueHenyeyGreenstein(g)                             */
+#define CLSIMCU_SCAT_SL          2   /* I3CLSimRandomValueSimplifiedLiu(g)                                */
+typedef struct clsimcu_medium {
+    int32_t num_layers;
+    int32_t scat_kind;
+    double layers_zstart;
+    double layers_height;
+    /* I3CLSimFunctionAbsLenIceCube per layer (kappa,A,B,D,E equal in all layers) */
+    double kappa, A, B, D, E;
+    const double *a_dust400;     /* [num_layers] */
+    const double *delta_tau;     /* [num_layers] */
+    /* I3CLSimFunctionScatLenIceCube per layer (alpha equal in all layers) */
+    double alpha;
+    const double *b400;          /* [num_layers] */
+    /* I3CLSimFunctionRefIndexIceCube, phase + group override (layer independent) */
+    double n_phase[5];
+    double n_group[5];
+    /* scattering angle distribution */
+    double f_sl;                 /* fractionOfFirstDistribution (MIXED) */
+    double mean_cos;             /* g */
+    /* ice tilt: I3CLSimScalarFieldIceTiltZShift, or constant 0 when tilt_num_dist == 0 */
+    int32_t tilt_num_dist;
+    int32_t tilt_num_z;
+    const double *tilt_dist;     /* [tilt_num_dist] distancesFromOriginAlongTilt      */
+    const double *tilt_corr;     /* [tilt_num_dist][tilt_num_z] zCorrections           */
+    double tilt_z0, tilt_dz;     /* firstZCoordinate, zCoordinateSpacing               */
+    double tilt_azimuth;         /* directionOfTiltAzimuth [rad]                       */
+    /* anisotropy: I3CLSimScalarFieldAnisotropyAbsLenScaling + 2x I3CLSimVectorTransformMatrix */
+    int32_t has_anisotropy;
+    int32_t pre_renormalize, post_renormalize;
+    int32_t reserved0;
+    double aniso_azimuth;        /* anisotropyDirAzimuth [rad] */
+    double aniso_along;          /* magnitudeAlongDir          */
+    double aniso_perp;           /* magnitudePerpToDir         */
+    double pre_matrix[9];        /* row major                  */
+    double post_matrix[9];
+} clsimcu_medium;
+
+/* Flat DOM list (reference: I3CLSimSimpleGeometry, public/clsim/I3CLSimSimpleGeometry.h). */
+typedef struct clsimcu_geometry {
+    int32_t num_doms;
+    int32_t reserved0;
+    const int32_t *string_id;    /* [num_doms] */
+    const uint32_t *dom_id;      /* [num_doms] */
+    const double *x, *y, *z;     /* [num_doms] */
+    const int32_t *subdetector;  /* [num_doms] rank of the subdetector NAME in sorted order
+                                    (the reference keys a std::set<std::string>) */
+    double om_radius;            /* includes the oversize factor */
+} clsimcu_geometry;
+
+#define CLSIMCU_KERNEL_FAST       0  /* persistent kernel, per-lane RNG streams (default)        */
+#define CLSIMCU_KERNEL_REFERENCE  1  /* one thread per step, the reference's RNG-stream mapping,
+                                        precise math; all options supported                      */
+
+typedef struct clsimcu_config {
+    int32_t struct_size;         /* sizeof(clsimcu_config), ABI check                          */
+    int32_t device;              /* CUDA ordinal (SetDevice)                                   */
+    int32_t kernel_mode;         /* CLSIMCU_KERNEL_*                                           */
+    int32_t enable_double_buffering;      /* SetEnableDoubleBuffering                          */
+    int32_t stop_detected_photons;        /* SetStopDetectedPhotons                            */
+    int32_t save_all_photons;             /* SetSaveAllPhotons                                 */
+    int32_t photon_history_entries;       /* SetPhotonHistoryEntries                           */
+    int32_t num_wlen_generators;
+    double save_all_photons_prescale;     /* SetSaveAllPhotonsPrescale                         */
+    double fixed_number_of_absorption_lengths; /* NaN = sample (SetFixedNumberOfAbsorptionLengths) */
+    double pancake_factor;                /* SetDOMPancakeFactor                               */
+    uint64_t max_num_workitems;  /* largest bunch accepted by clsimcu_enqueue (SetMaxNumWorkitems) */
+    uint32_t workgroup_size;     /* bunch-size granularity advertised (SetWorkgroupSize); 0 -> 1 */
+    uint32_t output_photons_per_workitem; /* output capacity factor; 0 -> 10 like the reference */
+    const clsimcu_wlen_generator *wlen_generators;
+    clsimcu_wlen_bias wlen_bias;
+    clsimcu_medium medium;
+    clsimcu_geometry geometry;   /* ignored when save_all_photons                              */
+    /* MWC RNG (private/opencl/mwcrng_init.h:26-117).  rng_n streams.
+       rng_a/rng_x given: used verbatim.  rng_a == NULL: multipliers are the
+       safe-prime sequence (private/make_safeprimes/main.cxx) starting at row
+       rng_first_multiplier, x[] drawn from rng_seed under the reference's
+       rejection rule. */
+    uint64_t rng_n;
+    const uint32_t *rng_a;
+    const uint64_t *rng_x;
+    uint64_t rng_seed;
+    uint64_t rng_first_multiplier;
+} clsimcu_config;
+
+typedef struct clsimcu_engine clsimcu_engine;
+
+/* ---- life cycle ---------------------------------------------------------- */
+
+/* Replaces: the setter block + Compile + Initialize of
+ * I3CLSimStepToPhotonConverterOpenCL (private/opencl/I3CLSimStepToPhotonConverterOpenCL.cxx:217-388,
+ * 485-548; factory private/clsim/I3CLSimModuleHelper.cxx:303-372).  Builds the tables,
+ * uploads them, seeds the RNG, allocates device/pinned buffers and starts the
+ * worker thread.  Fails (never falls back) when no CUDA device is usable. */
+int clsimcu_create(const clsimcu_config *config, clsimcu_engine **engine);
+
+/* Replaces: ~I3CLSimStepToPhotonConverterOpenCL (…OpenCL.cxx:110-145): interrupts and
+ * joins the worker, frees device memory. */
+int clsimcu_destroy(clsimcu_engine *engine);
+
+/* ---- the hot calls -------------------------------------------------------- */
+
+/* Replaces: EnqueueSteps (…OpenCL.cxx:1525-1544).  Copies n 48-byte steps out of
+ * the caller's buffer; blocks while 5 bunches are already queued.  Errors like the
+ * reference: n == 0, n > max_num_workitems, n % workgroup_size != 0. */
+int clsimcu_enqueue(clsimcu_engine *engine, const clsimcu_step *steps, size_t n, uint32_t identifier);
+
+/* Replaces: GetConversionResult (…OpenCL.cxx:1604-1619).  Blocks until a bunch is
+ * done.  *photons is never NULL on success (I3CLSimClientModule.cxx:589 requires
+ * it); *history is NULL unless photon_history_entries > 0, else
+ * n_photons * photon_history_entries float4 rows already in forward order with
+ * unused rows NaN (…OpenCL.cxx:940-989).  Release with clsimcu_release_result. */
+typedef struct clsimcu_result {
+    uint32_t identifier;
+    uint32_t reserved0;
+    size_t num_photons;
+    clsimcu_photon *photons;
+    float *history;              /* [num_photons][photon_history_entries][4] or NULL */
+    uint64_t num_photons_generated; /* sum of step.num_photons of the bunch */
+    uint64_t num_hits_counted;   /* device counter; > num_photons means truncated (…OpenCL.cxx:1027-1032) */
+    void *opaque;
+} clsimcu_result;
+int clsimcu_get_result(clsimcu_engine *engine, clsimcu_result *result);
+int clsimcu_release_result(clsimcu_engine *engine, clsimcu_result *result);
+
+/* Replaces: QueueSize / MorePhotonsAvailable (…OpenCL.cxx:1546-1562). */
+int clsimcu_queue_size(clsimcu_engine *engine, size_t *size);
+int clsimcu_more_photons_available(clsimcu_engine *engine, int *available);
+
+/* Replaces: GetWorkgroupSize / GetMaxNumWorkitems (sizing handshake,
+ * I3CLSimServer.cxx:95-115). */
+int clsimcu_workgroup_size(clsimcu_engine *engine, size_t *size);
+int clsimcu_max_num_workitems(clsimcu_engine *engine, size_t *size);
+
+/* Replaces: GetStatistics (…OpenCL.cxx:1621-1640).  out[0..7] =
+ * TotalDeviceTime[ns], TotalHostTime[ns], NumKernelCalls, TotalNumPhotonsGenerated,
+ * TotalNumPhotonsAtDOMs, AverageDeviceTimePerPhoton, AverageHostTimePerPhoton,
+ * DeviceUtilization. */
+int clsimcu_get_statistics(clsimcu_engine *engine, double out[8]);
+
+/* ---- device-resident path (no reference equivalent; measurement only) ------ */
+
+/* Upload a bunch once, then run the propagation kernel `repeat` times on it with
+ * inputs resident in HBM.  Timed with CUDA events on the engine's stream.
+ * Outputs: kernel milliseconds (sum over repeats), photons generated and hits
+ * counted over all repeats.  The RNG streams advance between repeats. */
+int clsimcu_upload_resident(clsimcu_engine *engine, const clsimcu_step *steps, size_t n);
+int clsimcu_run_resident(clsimcu_engine *engine, int repeat, double *kernel_ms,
+                         uint64_t *photons_generated, uint64_t *hits_counted,
+                         uint64_t *segments);
+/* Copy the hits of the last resident run back (at most cap records). */
+int clsimcu_download_resident(clsimcu_engine *engine, clsimcu_photon *out, size_t cap, size_t *n);
+
+/* ---- test hooks ------------------------------------------------------------- */
+
+/* RNG state of the first n streams (reference keeps it on the device between
+ * launches, propagation_kernel.c.cl:458-459, 911-912). */
+int clsimcu_rng_get(clsimcu_engine *engine, uint64_t *x, uint32_t *a, size_t n);
+int clsimcu_rng_set(clsimcu_engine *engine, const uint64_t *x, const uint32_t *a, size_t n);
+
+/* Flattened geometry tables (what GenerateGeometrySource emits as constants),
+ * serialised as a JSON text for comparison with the oracle's builder. */
+int clsimcu_describe_tables(clsimcu_engine *engine, char *buf, size_t cap, size_t *needed);
+
+/* Table building without a GPU (host only): same JSON as above. */
+int clsimcu_describe_tables_from_config(const clsimcu_config *config, char *buf, size_t cap, size_t *needed);
+
+/* Safe-prime MWC multipliers (private/make_safeprimes/main.cxx:32-104): writes the
+ * rows [first, first+n) of the descending sequence that starts at 4294967118. */
+int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
+
+/* In SAVE_ALL mode with kernel FAST: per saved photon two RNG states, x[2*i] before
+ * the photon was created and x[2*i+1] when its propagation started (creation runs
+ * ahead of propagation in the fast kernel), plus its multiplier a[i], so a CPU
+ * checker can replay single photons.  Parallel to the last result of
+ * clsimcu_download_resident; x has room for 2*cap entries. */
+int clsimcu_download_resident_rng_tags(clsimcu_engine *engine, uint64_t *x, uint32_t *a, size_t cap);
+
+const char *clsimcu_last_error(void);
+const char *clsimcu_version(void);
+size_t clsimcu_sizeof_config(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLSIMCUDA_H_INCLUDED */

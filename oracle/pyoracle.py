@@ -1,0 +1,165 @@
+"""ctypes wrapper of the CPU oracle (TEST INFRASTRUCTURE -- import only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs)."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+from clsim_b200.description import PHOTON_DTYPE, STEP_DTYPE, ConfigStruct, build_config
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libclsim_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.isfile(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(os.path.join(_HERE, "clsim_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.oracle_sizeof_config.restype = C.c_size_t
+        L.oracle_last_error.restype = C.c_char_p
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.POINTER(ConfigStruct)]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_propagate.restype = C.c_uint64
+        L.oracle_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_propagate_single_photon.restype = C.c_int
+        L.oracle_propagate_single_photon.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
+                                                     C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_propagate_single_photon_split.restype = C.c_int
+        L.oracle_propagate_single_photon_split.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
+                                                           C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_rng_uniform_co.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_size_t]
+        L.oracle_safeprimes.restype = C.c_int
+        L.oracle_safeprimes.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_rng_seed_states.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_describe_tables.restype = C.c_int
+        L.oracle_describe_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.oracle_eval_wlen_function.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_eval_scalar_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_eval_vector_transform.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_sample.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_size_t]
+        L.oracle_scatter_direction.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def safeprimes(first, n):
+    a = np.zeros(n, dtype=np.uint32)
+    n2 = np.zeros(n, dtype=np.uint64)
+    n1 = np.zeros(n, dtype=np.uint64)
+    if lib().oracle_safeprimes(first, n, a.ctypes.data, n2.ctypes.data, n1.ctypes.data) != 0:
+        raise RuntimeError(lib().oracle_last_error().decode())
+    return a, n2, n1
+
+
+def seed_states(seed, a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    x = np.zeros(len(a), dtype=np.uint64)
+    lib().oracle_rng_seed_states(seed, a.ctypes.data, x.ctypes.data, len(a))
+    return x
+
+
+def rng_uniform_co(x, a, n):
+    out = np.zeros(n, dtype=np.float32)
+    xs = C.c_uint64(int(x))
+    lib().oracle_rng_uniform_co(C.byref(xs), int(a), out.ctypes.data, n)
+    return out, xs.value
+
+
+def scatter_direction(in6):
+    in6 = np.ascontiguousarray(in6, dtype=np.float32)
+    out = np.zeros((len(in6), 3), dtype=np.float32)
+    lib().oracle_scatter_direction(in6.ctypes.data, out.ctypes.data, len(in6))
+    return out
+
+
+class Scene(object):
+    def __init__(self, medium, geometry, wlen_generators, wlen_bias, options):
+        self._cfg, self._keep = build_config(medium, geometry, wlen_generators, wlen_bias, options)
+        assert lib().oracle_sizeof_config() == C.sizeof(ConfigStruct)
+        self.history_entries = int(options.photon_history_entries)
+        self._h = lib().oracle_scene_create(C.byref(self._cfg))
+        if not self._h:
+            raise RuntimeError(lib().oracle_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_scene_destroy(self._h)
+            self._h = None
+
+    def propagate(self, steps, rng_x, rng_a, cap=None, num_threads=1):
+        """-> (photons[PHOTON_DTYPE], hits_counted, stats dict, new rng_x, history or None)"""
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        n = len(steps)
+        x = np.array(rng_x[:n], dtype=np.uint64, copy=True)
+        a = np.ascontiguousarray(rng_a[:n], dtype=np.uint32)
+        if cap is None:
+            cap = max(1000, 10 * n)
+        out = np.zeros(cap, dtype=PHOTON_DTYPE)
+        hist = np.zeros((cap, self.history_entries, 4), dtype=np.float32) if self.history_entries else None
+        stats = np.zeros(4, dtype=np.uint64)
+        cnt = lib().oracle_propagate(self._h, steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, out.ctypes.data, cap,
+                                     hist.ctypes.data if hist is not None else None, int(num_threads), stats.ctypes.data)
+        k = min(int(cnt), cap)
+        st = {"photons": int(stats[0]), "segments": int(stats[1]), "crossings": int(stats[2]), "draws": int(stats[3])}
+        return out[:k], int(cnt), st, x, (hist[:k] if hist is not None else None)
+
+    def single_photon(self, step, x, a, max_points=0):
+        step = np.ascontiguousarray(step, dtype=STEP_DTYPE).reshape(1)
+        out = np.zeros(1, dtype=PHOTON_DTYPE)
+        traj = np.zeros((max(1, max_points), 8), dtype=np.float32)
+        npts = C.c_int(0)
+        xs = C.c_uint64(int(x))
+        saved = lib().oracle_propagate_single_photon(self._h, step.ctypes.data, C.byref(xs), int(a), out.ctypes.data,
+                                                     traj.ctypes.data if max_points else None, max_points, C.byref(npts))
+        return bool(saved), out[0], traj[:min(npts.value, max_points)], xs.value, npts.value
+
+    def single_photon_split(self, step, x_create, x_propagate, a):
+        step = np.ascontiguousarray(step, dtype=STEP_DTYPE).reshape(1)
+        out = np.zeros(1, dtype=PHOTON_DTYPE)
+        npts = C.c_int(0)
+        saved = lib().oracle_propagate_single_photon_split(self._h, step.ctypes.data, int(x_create), int(x_propagate), int(a),
+                                                           out.ctypes.data, None, 0, C.byref(npts))
+        return bool(saved), out[0]
+
+    def tables(self):
+        need = C.c_size_t(0)
+        lib().oracle_describe_tables(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        lib().oracle_describe_tables(self._h, buf, need.value, C.byref(need))
+        return json.loads(buf.value.decode())
+
+    def eval_wlen_function(self, which, layers, wlens):
+        arr = np.ascontiguousarray(np.stack([np.asarray(layers, dtype=np.float32), np.asarray(wlens, dtype=np.float32)], axis=-1))
+        out = np.zeros(len(arr), dtype=np.float32)
+        lib().oracle_eval_wlen_function(self._h, which, arr.ctypes.data, out.ctypes.data, len(arr))
+        return out
+
+    def eval_scalar_field(self, which, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.zeros(len(xyz), dtype=np.float32)
+        lib().oracle_eval_scalar_field(self._h, which, xyz.ctypes.data, out.ctypes.data, len(xyz))
+        return out
+
+    def eval_vector_transform(self, which, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.zeros_like(xyz)
+        lib().oracle_eval_vector_transform(self._h, which, xyz.ctypes.data, out.ctypes.data, len(xyz))
+        return out
+
+    def sample(self, which, x, a, n):
+        out = np.zeros(n, dtype=np.float32)
+        xs = C.c_uint64(int(x))
+        lib().oracle_sample(self._h, which, C.byref(xs), int(a), out.ctypes.data, n)
+        return out, xs.value
