@@ -61,3 +61,21 @@ def dom_near(geo, point):
     d2 = (geo.posX - point[0]) ** 2 + (geo.posY - point[1]) ** 2 + (geo.posZ - point[2]) ** 2
     i = int(np.argmin(d2))
     return np.array([geo.posX[i], geo.posY[i], geo.posZ[i]])
+
+
+def match_photons(got, want, wl_digits=4):
+    """Pair records of two hit lists that describe the same photon: same bunch identifier,
+    DOM, scatter count and (to ~1e-4 relative) wavelength and start direction.
+    Returns (index pairs, fraction of `want` matched)."""
+    def key(p):
+        return (int(p["identifier"]), int(p["string_id"]), int(p["om_id"]), int(p["num_scatters"]),
+                round(float(p["wavelength"]) * 1e9, wl_digits - 2), round(float(p["start_theta"]), 3), round(float(p["start_phi"]), 3))
+    table = {}
+    for i, p in enumerate(want):
+        table.setdefault(key(p), []).append(i)
+    pairs = []
+    for j, p in enumerate(got):
+        lst = table.get(key(p))
+        if lst:
+            pairs.append((j, lst.pop()))
+    return np.array(pairs, dtype=np.int64).reshape(-1, 2), (len(pairs) / float(max(1, len(want))))
