@@ -198,10 +198,10 @@ class Engine(object):
         return out
 
     def download_resident_rng_tags(self, k):
-        x = np.zeros(2 * k, dtype=np.uint64)
-        a = np.zeros(k, dtype=np.uint32)
+        x = np.zeros(3 * k, dtype=np.uint64)
+        a = np.zeros(2 * k, dtype=np.uint32)
         _check(lib().clsimcu_download_resident_rng_tags(self._h, x.ctypes.data, a.ctypes.data, k))
-        return x.reshape(k, 2), a
+        return x.reshape(k, 3), a.reshape(k, 2)
 
     def rng_get(self, n):
         x = np.zeros(n, dtype=np.uint64)

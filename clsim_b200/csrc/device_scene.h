@@ -61,6 +61,19 @@ struct DevGeometry {
     const float *tmpl_z;
     const uint32_t *string_tmpl_start;
     const float *string_mean_x, *string_mean_y;
+    // Fast kernel only: conservative distance field over the xy plane.  near_d1[pixel] is a lower
+    // bound (whole metres, capped at 255) of the distance from ANY point of the pixel to the
+    // nearest string axis; a segment of length L can only touch a DOM if L + string_max_radius
+    // reaches that far, so most segments skip the collision test after one byte load.
+    // near_info[pixel] = nearest string index (low 16 bits) | lower bound of the distance to every
+    // OTHER string (bits 16-23): when the segment cannot reach that either, only one string has to
+    // be tested; otherwise the reference's cell walk is used.  Points outside the table clamp to
+    // the border pixels (the bounds stay valid: projection onto the table rectangle is
+    // non-expansive and every string lies inside it).
+    int near_nx, near_ny;
+    float near_x0, near_y0, near_inv_pixel;
+    const uint8_t *near_d1;
+    const uint32_t *near_info;
     // index -> ID rewrite on the device (…ConverterOpenCL.cxx:1565-1602 does it on the host)
     const int16_t *string_index_to_id;
     const uint32_t *dom_id_offset; // per string into dom_ids
@@ -74,7 +87,7 @@ struct DevScene {
     DevBias bias;
     DevGeometry geo;
     int stop_detected, save_all, fixed_abs, pancake, history_entries;
-    float prescale, fixed_abs_lens, pancake_factor;
+    float prescale, fixed_abs_lens, pancake_factor, inv_pancake_factor;
 };
 
 // Per-launch arguments.

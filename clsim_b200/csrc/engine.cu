@@ -265,6 +265,7 @@ void upload_tables(clsimcu_engine &e)
     size_t o_grid[kMaxSubdetectors] = {0};
     size_t o_sx = 0, o_sy = 0, o_smin = 0, o_smax = 0, o_sset = 0, o_lcount = 0, o_lstart = 0, o_lheight = 0, o_l2d = 0;
     size_t o_tdx = 0, o_tdy = 0, o_tz = 0, o_tstart = 0, o_mx = 0, o_my = 0, o_sid = 0, o_doff = 0, o_dids = 0;
+    size_t o_near_d1 = 0, o_near_info = 0;
     if (t.has_geometry) {
         dg.num_strings = g.num_strings; dg.num_sets = g.num_sets; dg.max_layers = g.max_layers;
         dg.num_grids = static_cast<int>(g.grids.size());
@@ -304,11 +305,51 @@ void upload_tables(clsimcu_engine &e)
             }
         }
         o_sid = arena.add(sid); o_doff = arena.add(doff); o_dids = arena.add(dids);
+
+        // distance field for the fast kernel (see device_scene.h)
+        {
+            const float margin = 250.f;
+            float xlo = g.string_x[0], xhi = g.string_x[0], ylo = g.string_y[0], yhi = g.string_y[0];
+            for (int i = 0; i < g.num_strings; ++i) {
+                xlo = std::min(xlo, g.string_x[i]); xhi = std::max(xhi, g.string_x[i]);
+                ylo = std::min(ylo, g.string_y[i]); yhi = std::max(yhi, g.string_y[i]);
+            }
+            // pixel size such that the byte table stays around 12 KB (it is staged in shared memory)
+            const float area = (xhi - xlo + 2 * margin) * (yhi - ylo + 2 * margin);
+            const float pixel = std::max(8.f, std::sqrt(area / 12000.f));
+            dg.near_x0 = xlo - margin;
+            dg.near_y0 = ylo - margin;
+            dg.near_inv_pixel = 1.f / pixel;
+            dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * margin) / pixel));
+            dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * margin) / pixel));
+            const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-3; // + slack for fp32 pixel assignment
+            std::vector<uint8_t> d1(static_cast<size_t>(dg.near_nx) * dg.near_ny);
+            std::vector<uint32_t> info(d1.size());
+            for (int iy = 0; iy < dg.near_ny; ++iy) {
+                for (int ix = 0; ix < dg.near_nx; ++ix) {
+                    const double cx = dg.near_x0 + (ix + 0.5) * pixel, cy = dg.near_y0 + (iy + 0.5) * pixel;
+                    double best = 1e30, second = 1e30;
+                    int who = 0;
+                    for (int k = 0; k < g.num_strings; ++k) {
+                        const double d = std::hypot(cx - g.string_x[k], cy - g.string_y[k]);
+                        if (d < best) { second = best; best = d; who = k; }
+                        else if (d < second) second = d;
+                    }
+                    const double lb1 = std::max(0.0, best - half_diag), lb2 = std::max(0.0, second - half_diag);
+                    d1[static_cast<size_t>(iy) * dg.near_nx + ix] = static_cast<uint8_t>(std::min(255.0, std::floor(lb1)));
+                    info[static_cast<size_t>(iy) * dg.near_nx + ix] =
+                        static_cast<uint32_t>(who) | (static_cast<uint32_t>(std::min(255.0, std::floor(lb2))) << 16);
+                }
+            }
+            o_near_d1 = arena.add(d1);
+            o_near_info = arena.add(info);
+        }
     }
 
     s.stop_detected = t.stop_detected; s.save_all = t.save_all; s.fixed_abs = t.fixed_abs; s.pancake = t.pancake;
     s.history_entries = t.history_entries;
     s.prescale = t.prescale; s.fixed_abs_lens = t.fixed_abs_lens; s.pancake_factor = t.pancake_factor;
+    s.inv_pancake_factor = t.pancake ? 1.f / t.pancake_factor : 1.f;
 
     CUDA_OK(cudaMalloc(&e.d_arena, arena.bytes().size()));
     CUDA_OK(cudaMemcpy(e.d_arena, arena.bytes().data(), arena.bytes().size(), cudaMemcpyHostToDevice));
@@ -336,6 +377,8 @@ void upload_tables(clsimcu_engine &e)
         dg.string_index_to_id = at<int16_t>(b, o_sid);
         dg.dom_id_offset = at<uint32_t>(b, o_doff);
         dg.dom_ids = at<uint16_t>(b, o_dids);
+        dg.near_d1 = at<uint8_t>(b, o_near_d1);
+        dg.near_info = at<uint32_t>(b, o_near_info);
     }
 }
 
@@ -735,8 +778,8 @@ int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t
             CUDA_OK(cudaHostAlloc(&e->h_res_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
             CUDA_OK(cudaMalloc(&e->d_l2_flush, kL2FlushBytes));
             if (e->save_all) {
-                CUDA_OK(cudaMalloc(&e->d_tag_x, 2 * e->res_cap * sizeof(uint64_t)));
-                CUDA_OK(cudaMalloc(&e->d_tag_a, e->res_cap * sizeof(uint32_t)));
+                CUDA_OK(cudaMalloc(&e->d_tag_x, 3 * e->res_cap * sizeof(uint64_t)));
+                CUDA_OK(cudaMalloc(&e->d_tag_a, 2 * e->res_cap * sizeof(uint32_t)));
             }
         }
         CUDA_OK(cudaMemcpy(e->d_res_steps, steps, n * sizeof(clsimcu_step), cudaMemcpyHostToDevice));
@@ -830,8 +873,8 @@ int clsimcu_download_resident_rng_tags(clsimcu_engine *e, uint64_t *x, uint32_t 
         CUDA_OK(cudaSetDevice(e->device));
         const size_t k = std::min(std::min<size_t>(e->res_last_hits, e->res_cap), cap);
         if (k > 0) {
-            CUDA_OK(cudaMemcpy(x, e->d_tag_x, 2 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-            CUDA_OK(cudaMemcpy(a, e->d_tag_a, k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(x, e->d_tag_x, 3 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(a, e->d_tag_a, 2 * k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         }
     } catch (const std::exception &ex) {
         return fail(CLSIMCU_ERR_CUDA, ex.what());

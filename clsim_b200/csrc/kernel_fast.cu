@@ -65,7 +65,12 @@ struct Mwc {
         x = static_cast<uint64_t>(static_cast<uint32_t>(x)) * a + (x >> 32);
         return __uint2float_rz(static_cast<uint32_t>(x)) * 2.3283064365386963e-10f;
     }
-    __device__ __forceinline__ float oc() { return 1.0f - co(); }
+    // 1 - u/2^32 in one FMA (the scaling is exact, so this equals the two-step form)
+    __device__ __forceinline__ float oc()
+    {
+        x = static_cast<uint64_t>(static_cast<uint32_t>(x)) * a + (x >> 32);
+        return __fmaf_rn(__uint2float_rz(static_cast<uint32_t>(x)), -2.3283064365386963e-10f, 1.0f);
+    }
 };
 
 // Shared-memory plan, carved out of the dynamic allocation.
@@ -76,13 +81,14 @@ struct SmemPlan {
     uint8_t *string_set;     // [num_strings]
     uint16_t *layer_to_dom;  // [layer_table_size]
     uint16_t *cells;         // concatenated grids
+    uint8_t *near_d1;        // distance field, one byte per pixel
     float *start;            // [2][kStartWords][kThreads]
     float *spare;            // [kSpareWords][kThreads]
     uint32_t *warp_step;     // [kWarpsPerBlock][12]
 };
 
 struct SmemLayout {
-    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_start, off_spare, off_warp_step;
+    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_start, off_spare, off_warp_step;
     uint32_t cell_offset[kMaxSubdetectors];
     uint32_t total;
 };
@@ -105,6 +111,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         cells += s.geo.grids[i].num_x * s.geo.grids[i].num_y;
     }
     at = align16(at + cells * 2);
+    L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny + 4);
     L.off_start = at; at = align16(at + 2 * kStartWords * kThreads * 4);
     L.off_spare = at; at = align16(at + kSpareWords * kThreads * 4);
     L.off_warp_step = at; at = align16(at + kWarpsPerBlock * 12 * 4);
@@ -247,6 +254,132 @@ __device__ __forceinline__ float life_of_current(const float *start0, int buffer
     return start0[buffer * (kStartWords * kThreads) + 8 * kThreads];
 }
 
+// ---- R6: DOM collision, restated for SIMT -----------------------------------------------------
+// String level (sparse_collision_kernel.c.cl:27-192): cylinder pre-test with the global maximum
+// radius (quirk 7), vertical extent, then the z-layer table of the string's set, at most one DOM
+// per layer, ray-sphere test with the pancake factor; the closest entry point wins.
+struct Collision {
+    float travel;
+    int string, dom;
+    bool hit;
+};
+
+__device__ __forceinline__ void test_string(const SmemPlan &sp, const DevGeometry &geo, int s, const V3 &pos, const V3 &dir,
+                                            float inv_xy2, float inv_pancake, Collision &c)
+{
+    const float4 sv = sp.strings[s];
+    const float cross = (pos.x - sv.x) * dir.y - (pos.y - sv.y) * dir.x;
+    if (cross * cross * inv_xy2 > geo.string_max_radius * geo.string_max_radius) return;
+    if ((dir.z > 0.f) && (pos.z > sv.z)) return;
+    if ((dir.z < 0.f) && (pos.z < sv.w)) return;
+    const float4 set = sp.sets[sp.string_set[s]];
+    const int nl = static_cast<int>(set.z);
+    const int l0 = __float2int_rz((pos.z - set.x) * set.y);
+    const int l1 = __float2int_rz((pos.z + dir.z * c.travel - set.x) * set.y);
+    const int la = min(max(min(l0, l1), 0), nl - 1), lb = min(max(max(l0, l1), 0), nl - 1);
+    const uint16_t *row = sp.layer_to_dom + static_cast<int>(set.w);
+    const float r_om2 = geo.om_radius * geo.om_radius;
+    for (int l = la; l <= lb; ++l) {
+        const int dom = row[l];
+        if (dom == 0xFFFF) continue;
+        float qx, qy, qz;
+        dom_centre(geo, s, dom, qx, qy, qz);
+        const float rx = qx - pos.x, ry = qy - pos.y, rz = qz - pos.z;
+        const float along = rx * dir.x + ry * dir.y + rz * dir.z;
+        float disc = along * along - (rx * rx + ry * ry + rz * rz) + r_om2;
+        if (disc < 0.f) continue;
+        disc = mufu_sqrt(disc) * inv_pancake;
+        const float entry = along - disc;
+        if (entry < 0.f) continue; // started inside (or behind): let it leave (quirk 9)
+        if (entry < c.travel) {
+            c.travel = entry;
+            c.hit = true;
+            c.string = s;
+            c.dom = dom;
+        }
+    }
+}
+
+// Cell level, the reference's walk over the xy cells covered by the segment
+// (sparse_collision_kernel.c.cl:194-303, 305-460).  Only taken when the distance field cannot
+// narrow the candidates down to one string, so it is kept out of line.
+__device__ __noinline__ void cell_walk(const SmemPlan sp, const DevGeometry &geo, const SmemLayout &lay, V3 pos, V3 dir, float inv_xy2,
+                                       float inv_pancake, Collision &c)
+{
+    for (int gI = 0; gI < geo.num_grids; ++gI) {
+        const DevCellGrid &cg = geo.grids[gI];
+        const float ex = pos.x + dir.x * c.travel, ey = pos.y + dir.y * c.travel;
+        const int x0 = __float2int_rz((pos.x - cg.start_x) * cg.inv_width_x), x1 = __float2int_rz((ex - cg.start_x) * cg.inv_width_x);
+        const int y0 = __float2int_rz((pos.y - cg.start_y) * cg.inv_width_y), y1 = __float2int_rz((ey - cg.start_y) * cg.inv_width_y);
+        const int xa = min(max(min(x0, x1), 0), cg.num_x - 1), xb = min(max(max(x0, x1), 0), cg.num_x - 1);
+        const int ya = min(max(min(y0, y1), 0), cg.num_y - 1), yb = min(max(max(y0, y1), 0), cg.num_y - 1);
+        const uint16_t *cells = sp.cells + lay.cell_offset[gI];
+        for (int cy = ya; cy <= yb; ++cy) {
+            for (int cx = xa; cx <= xb; ++cx) {
+                const int s = cells[cy * cg.num_x + cx];
+                if (s != 0xFFFF) test_string(sp, geo, s, pos, dir, inv_xy2, inv_pancake, c);
+            }
+        }
+    }
+}
+
+// ---- R10: hit output ----------------------------------------------------------------------------
+// Called by the lanes whose photon was just detected (or absorbed, in save-all mode): `pos` is
+// the end point, `path` the full path length.  Reservation is aggregated over the lanes that
+// arrive together; the record leaves as five 16-byte stores.
+__device__ __noinline__ void emit_record(const DevScene &scene, const LaunchArgs &args, const float *st, V3 pos, V3 dir, float path,
+                                         uint32_t scatters, int hit_string, int hit_dom, float dist_abs, bool save_all,
+                                         uint64_t tag_create, uint64_t tag_pop, uint64_t tag_resume, uint32_t interrupt_at, uint32_t rng_a)
+{
+    const unsigned peers = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(args.hit_counter, static_cast<uint32_t>(__popc(peers)));
+    base = __shfl_sync(peers, base, leader);
+    const uint32_t slot = base + __popc(peers & ((1u << lane) - 1u));
+    if (slot >= args.max_hits) return; // counted but dropped (quirk 10)
+    const DevGeometry &geo = scene.geo;
+    const float stt = st[3 * kThreads], wlen = st[7 * kThreads];
+    const uint32_t step_index = __float_as_uint(st[9 * kThreads]);
+    const clsimcu_step *step = static_cast<const clsimcu_step *>(args.steps) + step_index;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    uint32_t ids = 0;
+    if (!save_all) {
+        dom_centre(geo, hit_string, hit_dom, qx, qy, qz);
+        if (scene.pancake) {
+            // undo the pancake: shift the DOM centre along the component of (pos - dom) perpendicular
+            // to the direction (propagation_kernel.c.cl:340-355); that component is the same
+            // anywhere along the ray, so the end point can be used
+            const float px = pos.x - qx, py = pos.y - qy, pz = pos.z - qz;
+            const float along = px * dir.x + py * dir.y + pz * dir.z;
+            const float k = (scene.pancake_factor - 1.f) * scene.inv_pancake_factor;
+            qx += k * (px - along * dir.x); qy += k * (py - along * dir.y); qz += k * (pz - along * dir.z);
+        }
+        const int16_t sid = __ldg(geo.string_index_to_id + hit_string);
+        const uint16_t oid = __ldg(geo.dom_ids + __ldg(geo.dom_id_offset + hit_string) + hit_dom);
+        ids = static_cast<uint32_t>(static_cast<uint16_t>(sid)) | (static_cast<uint32_t>(oid) << 16);
+    }
+    const float ivg = inv_group_velocity(scene.medium, wlen);
+    float th, ph, sth, sph;
+    to_spherical(dir.x, dir.y, dir.z, th, ph);
+    to_spherical(st[4 * kThreads], st[5 * kThreads], st[6 * kThreads], sth, sph);
+    float4 *dst = reinterpret_cast<float4 *>(static_cast<clsimcu_photon *>(args.photons) + slot);
+    dst[0] = make_float4(pos.x - qx, pos.y - qy, pos.z - qz, stt + path * ivg);
+    dst[1] = make_float4(th, ph, wlen, path);
+    dst[2] = make_float4(__uint_as_float(scatters), __ldg(&step->weight) / bias_at(scene.bias, wlen),
+                         __uint_as_float(__ldg(&step->identifier)), __uint_as_float(ids));
+    dst[3] = make_float4(st[0 * kThreads], st[1 * kThreads], st[2 * kThreads], stt);
+    dst[4] = make_float4(sth, sph, 1.f / ivg, dist_abs);
+    if (save_all && args.rng_tag_x) {
+        args.rng_tag_x[3 * static_cast<size_t>(slot)] = tag_create;
+        args.rng_tag_x[3 * static_cast<size_t>(slot) + 1] = tag_pop;
+        args.rng_tag_x[3 * static_cast<size_t>(slot) + 2] = tag_resume;
+        args.rng_tag_a[2 * static_cast<size_t>(slot)] = rng_a;
+        args.rng_tag_a[2 * static_cast<size_t>(slot) + 1] = interrupt_at;
+    }
+}
+
 template <bool TILT, bool ANISO, bool SAVE_ALL>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 propagate_persistent(const __grid_constant__ DevScene scene, const __grid_constant__ LaunchArgs args, const __grid_constant__ SmemLayout lay)
@@ -261,6 +394,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     sp.string_set = smem + lay.off_string_set;
     sp.layer_to_dom = reinterpret_cast<uint16_t *>(smem + lay.off_layer_to_dom);
     sp.cells = reinterpret_cast<uint16_t *>(smem + lay.off_cells);
+    sp.near_d1 = smem + lay.off_near;
     sp.start = reinterpret_cast<float *>(smem + lay.off_start);
     sp.spare = reinterpret_cast<float *>(smem + lay.off_spare);
     sp.warp_step = reinterpret_cast<uint32_t *>(smem + lay.off_warp_step);
@@ -268,6 +402,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const unsigned lane_bit = 1u << lane;
 
     // ---- stage the hot tables into shared memory (coalesced reads, once per CTA)
     for (int i = tid; i < m.num_layers; i += kThreads)
@@ -286,6 +421,9 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             const int n = geo.grids[gI].num_x * geo.grids[gI].num_y;
             for (int i = tid; i < n; i += kThreads) sp.cells[lay.cell_offset[gI] + i] = __ldg(geo.grids[gI].cell_to_string + i);
         }
+        const int near_words = (geo.near_nx * geo.near_ny + 3) / 4;
+        for (int i = tid; i < near_words; i += kThreads)
+            reinterpret_cast<uint32_t *>(sp.near_d1)[i] = __ldg(reinterpret_cast<const uint32_t *>(geo.near_d1) + i);
     }
     __syncthreads();
 
@@ -296,24 +434,28 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     Mwc rng{args.rng_x[gthread], args.rng_a[gthread]};
 
-    // warp-uniform work state
+    // warp-uniform state
     uint32_t w_step_index = 0xffffffffu;
-    uint32_t w_left = 0;       // photons of the warp's step not yet handed to a lane
-    bool w_more = true;        // the global queue may still have steps
+    uint32_t w_left = 0;         // photons of the warp's step not yet handed to a lane
+    bool w_more = true;          // the global queue may still have steps
     V3 w_axis{0.f, 0.f, 1.f};
+    unsigned spare_mask = 0;     // lanes whose mailbox holds a photon
 
     // lane state
-    bool alive = false, has_spare = false;
-    int cur = 0;               // which start buffer holds the photon in flight
+    bool alive = false;
+    int cur = 0;                 // which start buffer holds the photon in flight
     V3 pos{0.f, 0.f, 0.f}, dir{0.f, 0.f, 1.f};
     float abs_left = 0.f, path = 0.f;
     float f_scat = 0.f, f_dust = 0.f, f_pure = 0.f;
     uint32_t scatters = 0;
     int layer = 0;
     unsigned long long n_created = 0, n_segments = 0;
-    // RNG states for single-photon replay by a checker: before the spare's creation, and of the
-    // photon in flight before its creation / at the moment it was popped
-    uint64_t spare_tag_create = 0, cur_tag_create = 0, cur_tag_pop = 0;
+    // RNG bookkeeping for single-photon replay by a checker (save-all variants only; dead code
+    // otherwise).  A lane's stream serves, in this order: creation of a photon (x_create), later
+    // its propagation from x_pop, interrupted at most once -- after `interrupt_at` scatters -- by
+    // the creation of the lane's next spare, after which it resumes from x_resume.
+    uint64_t spare_tag_create = 0, cur_tag_create = 0, cur_tag_pop = 0, cur_tag_resume = 0;
+    uint32_t cur_interrupt_at = 0xffffffffu;
 
     const float inv_h = m.inv_h;
     const float inv_fsl = (m.f_sl > 0.f) ? 1.f / m.f_sl : 0.f;
@@ -321,103 +463,113 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     const float inv_2g = 1.f / (2.f * m.g);
 
     for (;;) {
-        // ------------------------------------------------------------------ refill (converged)
-        const unsigned empty_mask = __ballot_sync(0xffffffffu, !has_spare);
-        const bool starving = !__any_sync(0xffffffffu, alive || has_spare);
-        if ((w_more || w_left > 0) && (__popc(empty_mask) >= kRefillThreshold || starving)) {
-            bool need = !has_spare;
-            for (;;) {
-                const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-                if (need_mask == 0) break;
-                if (w_left == 0) {
-                    if (!w_more) break;
-                    // fetch the next non-empty step for this warp
-                    uint32_t idx = 0;
-                    if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
-                    idx = __shfl_sync(0xffffffffu, idx, 0);
-                    if (idx >= args.num_steps) { w_more = false; break; }
-                    __syncwarp();
-                    if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
-                    __syncwarp();
-                    w_step_index = idx;
-                    w_left = wstep[8];
-                    float st, ct, sph, cph;
-                    __sincosf(__uint_as_float(wstep[4]), &st, &ct);
-                    __sincosf(__uint_as_float(wstep[5]), &sph, &cph);
-                    w_axis.x = st * cph; w_axis.y = st * sph; w_axis.z = ct;
-                    if (w_left == 0) continue; // dummy step (quirk 11)
-                }
-                const int rank = __popc(need_mask & ((1u << lane) - 1u));
-                const bool take = need && (static_cast<uint32_t>(rank) < w_left);
-                if (take) {
-                    // R3: createPhotonFromTrack (propagation_kernel.c.cl:132-184)
-                    const uint64_t x_before = rng.x;
-                    const float s_x = __uint_as_float(wstep[0]), s_y = __uint_as_float(wstep[1]), s_z = __uint_as_float(wstep[2]);
-                    const float s_t = __uint_as_float(wstep[3]), s_len = __uint_as_float(wstep[6]), s_beta = __uint_as_float(wstep[7]);
-                    const uint32_t source = (wstep[11] & 0xffu);
-                    const float shift = s_len * rng.co();
-                    V3 d = w_axis;
-                    float wlen;
-                    if (scene.num_generators <= 1 || source == 0) {
-                        wlen = draw_wavelength(scene.generators[0], rng);
-                        const float cos_c = fminf(1.f, mufu_rcp(s_beta * phase_index(m, wlen)));
-                        const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
-                        rotate_by(cos_c, sin_c, d, rng.co());
-                    } else {
-                        wlen = (source < static_cast<uint32_t>(scene.num_generators)) ? draw_wavelength(scene.generators[source], rng) : 0.f;
+        // One vote per iteration; everything else on the control path runs only when a lane is dead.
+        unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+        if (alive_mask != 0xffffffffu) {
+            // ---------------------------------------------------------- refill (converged)
+            const bool work = w_more || w_left > 0;
+            if (work && (__popc(~spare_mask) >= kRefillThreshold || (alive_mask | spare_mask) == 0u)) {
+                bool need = !(spare_mask & lane_bit);
+                for (;;) {
+                    const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+                    if (need_mask == 0) break;
+                    if (w_left == 0) {
+                        if (!w_more) break;
+                        // next step for this warp
+                        uint32_t idx = 0;
+                        if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
+                        idx = __shfl_sync(0xffffffffu, idx, 0);
+                        if (idx >= args.num_steps) { w_more = false; break; }
+                        __syncwarp();
+                        if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
+                        __syncwarp();
+                        w_step_index = idx;
+                        w_left = wstep[8];
+                        float st, ct, sph, cph;
+                        __sincosf(__uint_as_float(wstep[4]), &st, &ct);
+                        __sincosf(__uint_as_float(wstep[5]), &sph, &cph);
+                        w_axis.x = st * cph; w_axis.y = st * sph; w_axis.z = ct;
+                        if (w_left == 0) continue; // dummy step (quirk 11)
                     }
-                    const float life = scene.fixed_abs ? scene.fixed_abs_lens : -fast_ln(rng.oc());
-                    float *st = start0 + (cur ^ (alive ? 1 : 0)) * (kStartWords * kThreads);
-                    st[0 * kThreads] = s_x + w_axis.x * shift;
-                    st[1 * kThreads] = s_y + w_axis.y * shift;
-                    st[2 * kThreads] = s_z + w_axis.z * shift;
-                    st[3 * kThreads] = s_t + shift * mufu_rcp(kSpeedOfLight * s_beta);
-                    st[4 * kThreads] = d.x;
-                    st[5 * kThreads] = d.y;
-                    st[6 * kThreads] = d.z;
-                    st[7 * kThreads] = wlen;
-                    st[8 * kThreads] = life;
-                    st[9 * kThreads] = __uint_as_float(w_step_index);
-                    // wavelength-only factors of R4 (…_Optimizers.cxx:123-250), once per photon
-                    const float nm = wlen * 1e9f;
-                    spare[0 * kThreads] = fast_pow(wlen * m.inv_ref_wlen, -m.alpha);      // 1/scatLen = b400 * this
-                    spare[1 * kThreads] = fast_pow(nm, -m.kappa);                        // dust term factor
-                    spare[2 * kThreads] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f); // pure-ice term
-                    has_spare = true;
-                    need = false;
-                    spare_tag_create = x_before;
-                    ++n_created;
+                    const int rank = __popc(need_mask & (lane_bit - 1u));
+                    const bool take = need && (static_cast<uint32_t>(rank) < w_left);
+                    if (take) {
+                        // R3: createPhotonFromTrack (propagation_kernel.c.cl:132-184)
+                        const uint64_t x_before = rng.x;
+                        const float s_x = __uint_as_float(wstep[0]), s_y = __uint_as_float(wstep[1]), s_z = __uint_as_float(wstep[2]);
+                        const float s_t = __uint_as_float(wstep[3]), s_len = __uint_as_float(wstep[6]), s_beta = __uint_as_float(wstep[7]);
+                        const uint32_t source = (wstep[11] & 0xffu);
+                        const float shift = s_len * rng.co();
+                        V3 d = w_axis;
+                        float wlen;
+                        if (scene.num_generators <= 1 || source == 0) {
+                            wlen = draw_wavelength(scene.generators[0], rng);
+                            const float cos_c = fminf(1.f, mufu_rcp(s_beta * phase_index(m, wlen)));
+                            const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
+                            rotate_by(cos_c, sin_c, d, rng.co());
+                        } else {
+                            wlen = (source < static_cast<uint32_t>(scene.num_generators)) ? draw_wavelength(scene.generators[source], rng) : 0.f;
+                        }
+                        const float life = scene.fixed_abs ? scene.fixed_abs_lens : -fast_ln(rng.oc());
+                        // the spare goes to the buffer that is not in flight
+                        float *st = start0 + (cur ^ (alive ? 1 : 0)) * (kStartWords * kThreads);
+                        st[0 * kThreads] = s_x + w_axis.x * shift;
+                        st[1 * kThreads] = s_y + w_axis.y * shift;
+                        st[2 * kThreads] = s_z + w_axis.z * shift;
+                        st[3 * kThreads] = s_t + shift * mufu_rcp(kSpeedOfLight * s_beta);
+                        st[4 * kThreads] = d.x;
+                        st[5 * kThreads] = d.y;
+                        st[6 * kThreads] = d.z;
+                        st[7 * kThreads] = wlen;
+                        st[8 * kThreads] = life;
+                        st[9 * kThreads] = __uint_as_float(w_step_index);
+                        // wavelength-only factors of R4 (…_Optimizers.cxx:123-250), once per photon
+                        const float nm = wlen * 1e9f;
+                        spare[0 * kThreads] = fast_pow(wlen * m.inv_ref_wlen, -m.alpha);                // 1/scatLen = b400 * this
+                        spare[1 * kThreads] = fast_pow(nm, -m.kappa);                                  // dust term factor
+                        spare[2 * kThreads] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
+                        need = false;
+                        if (SAVE_ALL) {
+                            spare_tag_create = x_before;
+                            if (alive) {
+                                cur_interrupt_at = scatters;
+                                cur_tag_resume = rng.x;
+                            }
+                        }
+                        ++n_created;
+                    }
+                    spare_mask |= __ballot_sync(0xffffffffu, take);
+                    const uint32_t wanted = __popc(need_mask);
+                    w_left -= min(wanted, w_left);
                 }
-                const uint32_t wanted = __popc(need_mask);
-                w_left -= min(wanted, w_left);
+            }
+
+            // ---------------------------------------------------------- pop
+            const unsigned popping = ~alive_mask & spare_mask;
+            if (popping & lane_bit) {
+                const float *st = start0 + cur * (kStartWords * kThreads);
+                pos.x = st[0 * kThreads]; pos.y = st[1 * kThreads]; pos.z = st[2 * kThreads];
+                dir.x = st[4 * kThreads]; dir.y = st[5 * kThreads]; dir.z = st[6 * kThreads];
+                abs_left = st[8 * kThreads];
+                f_scat = spare[0 * kThreads]; f_dust = spare[1 * kThreads]; f_pure = spare[2 * kThreads];
+                path = 0.f;
+                scatters = 0;
+                layer = min(max(__float2int_rz((pos.z - m.z0) * inv_h), 0), m.num_layers - 1);
+                alive = true;
+                if (SAVE_ALL) {
+                    cur_tag_create = spare_tag_create;
+                    cur_tag_pop = rng.x;
+                    cur_interrupt_at = 0xffffffffu;
+                }
+            }
+            spare_mask &= ~popping;
+            alive_mask |= popping;
+            if (alive_mask == 0u) {
+                if (!w_more && w_left == 0) break; // nothing in flight, nothing spare, nothing to fetch
+                continue;
             }
         }
 
-        // ------------------------------------------------------------------ pop
-        if (!alive && has_spare) {
-            // the spare was written to the buffer that is not in flight; when dead, that is `cur`
-            const float *st = start0 + cur * (kStartWords * kThreads);
-            pos.x = st[0 * kThreads]; pos.y = st[1 * kThreads]; pos.z = st[2 * kThreads];
-            dir.x = st[4 * kThreads]; dir.y = st[5 * kThreads]; dir.z = st[6 * kThreads];
-            abs_left = st[8 * kThreads];
-            f_scat = spare[0 * kThreads]; f_dust = spare[1 * kThreads]; f_pure = spare[2 * kThreads];
-            path = 0.f;
-            scatters = 0;
-            layer = min(max(__float2int_rz((pos.z - m.z0) * inv_h), 0), m.num_layers - 1);
-            alive = true;
-            has_spare = false;
-            cur_tag_create = spare_tag_create;
-            cur_tag_pop = rng.x;
-        }
-
-        if (!__any_sync(0xffffffffu, alive)) {
-            if (!w_more && w_left == 0 && !__any_sync(0xffffffffu, has_spare)) break;
-            continue;
-        }
-
-        bool emit = false;
-        float emit_dist_abs = 0.f;
-        int hit_string = 0, hit_dom = 0;
         if (alive) {
             // -------------------------------------------------------------- R5: segment length
             float z_eff = pos.z;
@@ -489,72 +641,35 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             ++n_segments;
 
             // -------------------------------------------------------------- R6: DOM collision
-            bool hit = false;
+            Collision col{travel, 0, 0, false};
             if (!SAVE_ALL) {
-                const float dir_xy2 = dir.x * dir.x + dir.y * dir.y;
-                if (dir_xy2 > 0.f) {
-                    const float inv_xy2 = mufu_rcp(dir_xy2);
-                    const float r_cyl2 = geo.string_max_radius * geo.string_max_radius;
-                    const float r_om2 = geo.om_radius * geo.om_radius;
-                    const float inv_pancake = scene.pancake ? 1.f / scene.pancake_factor : 1.f;
-                    for (int gI = 0; gI < geo.num_grids; ++gI) {
-                        const DevCellGrid &cg = geo.grids[gI];
-                        const float ex = pos.x + dir.x * travel, ey = pos.y + dir.y * travel;
-                        int x0 = __float2int_rz((pos.x - cg.start_x) * cg.inv_width_x);
-                        int y0 = __float2int_rz((pos.y - cg.start_y) * cg.inv_width_y);
-                        int x1 = __float2int_rz((ex - cg.start_x) * cg.inv_width_x);
-                        int y1 = __float2int_rz((ey - cg.start_y) * cg.inv_width_y);
-                        const int xa = min(max(min(x0, x1), 0), cg.num_x - 1), xb = min(max(max(x0, x1), 0), cg.num_x - 1);
-                        const int ya = min(max(min(y0, y1), 0), cg.num_y - 1), yb = min(max(max(y0, y1), 0), cg.num_y - 1);
-                        const uint16_t *cells = sp.cells + lay.cell_offset[gI];
-                        for (int cy = ya; cy <= yb; ++cy) {
-                            for (int cx = xa; cx <= xb; ++cx) {
-                                const int s = cells[cy * cg.num_x + cx];
-                                if (s == 0xFFFF) continue;
-                                // string cylinder, global max radius (quirk 7), then vertical extent
-                                const float4 sv = sp.strings[s];
-                                const float cross = (pos.x - sv.x) * dir.y - (pos.y - sv.y) * dir.x;
-                                if (cross * cross * inv_xy2 > r_cyl2) continue;
-                                if ((dz > 0.f) && (pos.z > sv.z)) continue;
-                                if ((dz < 0.f) && (pos.z < sv.w)) continue;
-                                const float4 set = sp.sets[sp.string_set[s]];
-                                const int nl = static_cast<int>(set.z);
-                                int l0 = __float2int_rz((pos.z - set.x) * set.y);
-                                int l1 = __float2int_rz((pos.z + dz * travel - set.x) * set.y);
-                                const int la = min(max(min(l0, l1), 0), nl - 1), lb = min(max(max(l0, l1), 0), nl - 1);
-                                const uint16_t *row = sp.layer_to_dom + static_cast<int>(set.w);
-                                for (int l = la; l <= lb; ++l) {
-                                    const int dom = row[l];
-                                    if (dom == 0xFFFF) continue;
-                                    float qx, qy, qz;
-                                    dom_centre(geo, s, dom, qx, qy, qz);
-                                    const float rx = qx - pos.x, ry = qy - pos.y, rz = qz - pos.z;
-                                    const float along = rx * dir.x + ry * dir.y + rz * dir.z;
-                                    float disc = along * along - (rx * rx + ry * ry + rz * rz) + r_om2;
-                                    if (disc < 0.f) continue;
-                                    disc = mufu_sqrt(disc) * inv_pancake;
-                                    const float entry = along - disc;
-                                    // entry < 0 with exit >= 0: started inside, let it leave (quirk 9)
-                                    if (entry < 0.f) continue;
-                                    if (entry < travel) {
-                                        travel = entry;
-                                        hit = true;
-                                        hit_string = s;
-                                        hit_dom = dom;
-                                    }
-                                }
-                            }
+                // distance-field early out: can this segment reach any string at all?
+                const int px = min(max(__float2int_rz((pos.x - geo.near_x0) * geo.near_inv_pixel), 0), geo.near_nx - 1);
+                const int py = min(max(__float2int_rz((pos.y - geo.near_y0) * geo.near_inv_pixel), 0), geo.near_ny - 1);
+                const int pixel = py * geo.near_nx + px;
+                const float reach = travel + geo.string_max_radius;
+                if (reach >= static_cast<float>(sp.near_d1[pixel])) {
+                    const float dir_xy2 = dir.x * dir.x + dir.y * dir.y;
+                    if (dir_xy2 > 0.f) {
+                        const float inv_xy2 = mufu_rcp(dir_xy2);
+                        const uint32_t info = __ldg(geo.near_info + pixel);
+                        if (reach < static_cast<float>((info >> 16) & 0xffu)) {
+                            test_string(sp, geo, static_cast<int>(info & 0xffffu), pos, dir, inv_xy2, scene.inv_pancake_factor, col);
+                        } else {
+                            cell_walk(sp, geo, lay, pos, dir, inv_xy2, scene.inv_pancake_factor, col);
                         }
                     }
                 }
             }
-
-            if (hit) {
+            bool emit = false;
+            float emit_dist_abs = 0.f;
+            if (col.hit) {
                 // distInAbsLens is taken for the unshortened segment (propagation_kernel.c.cl:718)
                 emit = true;
                 emit_dist_abs = life_of_current(start0, cur) - abs_left;
                 abs_left = 0.f;
             }
+            travel = col.travel;
 
             // -------------------------------------------------------------- advance
             pos.x += dir.x * travel;
@@ -564,14 +679,17 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
 
             if (abs_left < kEpsilon) {
                 alive = false;
-                cur ^= 1; // the spare (if any) sits in the other buffer; the dead photon's start record is in cur^1
                 if (SAVE_ALL) {
                     // propagation_kernel.c.cl:800-826
                     if (rng.co() < scene.prescale) {
                         emit = true;
-                        emit_dist_abs = life_of_current(start0, cur ^ 1);
+                        emit_dist_abs = life_of_current(start0, cur);
                     }
                 }
+                if (emit)
+                    emit_record(scene, args, start0 + cur * (kStartWords * kThreads), pos, dir, path, scatters, col.string, col.dom,
+                                emit_dist_abs, SAVE_ALL, cur_tag_create, cur_tag_pop, cur_tag_resume, cur_interrupt_at, rng.a);
+                cur ^= 1; // the spare (if any) sits in the other buffer
             } else {
                 // ---------------------------------------------------------- R9 + R8: scatter
                 if (ANISO) apply_matrix(m.pre, dir);
@@ -596,60 +714,6 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                 rotate_by(cs, sn, dir, rng.co());
                 if (ANISO) apply_matrix(m.post, dir);
                 ++scatters;
-            }
-        }
-
-        // ------------------------------------------------------------------ R10: hit output (converged)
-        // A photon that is recorded has just died: `pos` is the point of detection / absorption,
-        // `path` the full path, its start record sits in buffer cur^1.
-        const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-        if (emit_mask) {
-            // warp-aggregated reservation: one atomic per warp and iteration
-            const int leader = __ffs(emit_mask) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(args.hit_counter, static_cast<uint32_t>(__popc(emit_mask)));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (emit) {
-                const uint32_t slot = base + __popc(emit_mask & ((1u << lane) - 1u));
-                if (slot < args.max_hits) {
-                    const float *st = start0 + (cur ^ 1) * (kStartWords * kThreads);
-                    const float stt = st[3 * kThreads], wlen = st[7 * kThreads];
-                    const uint32_t step_index = __float_as_uint(st[9 * kThreads]);
-                    const clsimcu_step *step = static_cast<const clsimcu_step *>(args.steps) + step_index;
-                    float qx = 0.f, qy = 0.f, qz = 0.f;
-                    uint32_t ids = 0;
-                    if (!SAVE_ALL) {
-                        dom_centre(geo, hit_string, hit_dom, qx, qy, qz);
-                        if (scene.pancake) {
-                            // undo the pancake: move the DOM centre along the component of (pos-dom)
-                            // perpendicular to the direction (propagation_kernel.c.cl:340-355); that
-                            // component is the same anywhere along the ray
-                            const float px = pos.x - qx, py = pos.y - qy, pz = pos.z - qz;
-                            const float along = px * dir.x + py * dir.y + pz * dir.z;
-                            const float k = (scene.pancake_factor - 1.f) / scene.pancake_factor;
-                            qx += k * (px - along * dir.x); qy += k * (py - along * dir.y); qz += k * (pz - along * dir.z);
-                        }
-                        const int16_t sid = __ldg(geo.string_index_to_id + hit_string);
-                        const uint16_t oid = __ldg(geo.dom_ids + __ldg(geo.dom_id_offset + hit_string) + hit_dom);
-                        ids = static_cast<uint32_t>(static_cast<uint16_t>(sid)) | (static_cast<uint32_t>(oid) << 16);
-                    }
-                    const float ivg = inv_group_velocity(m, wlen);
-                    float th, ph, sth, sph;
-                    to_spherical(dir.x, dir.y, dir.z, th, ph);
-                    to_spherical(st[4 * kThreads], st[5 * kThreads], st[6 * kThreads], sth, sph);
-                    float4 *dst = reinterpret_cast<float4 *>(static_cast<clsimcu_photon *>(args.photons) + slot);
-                    dst[0] = make_float4(pos.x - qx, pos.y - qy, pos.z - qz, stt + path * ivg);
-                    dst[1] = make_float4(th, ph, wlen, path);
-                    dst[2] = make_float4(__uint_as_float(scatters), __ldg(&step->weight) / bias_at(scene.bias, wlen),
-                                         __uint_as_float(__ldg(&step->identifier)), __uint_as_float(ids));
-                    dst[3] = make_float4(st[0 * kThreads], st[1 * kThreads], st[2 * kThreads], stt);
-                    dst[4] = make_float4(sth, sph, 1.f / ivg, emit_dist_abs);
-                    if (args.rng_tag_x) {
-                        args.rng_tag_x[2 * static_cast<size_t>(slot)] = cur_tag_create;
-                        args.rng_tag_x[2 * static_cast<size_t>(slot) + 1] = cur_tag_pop;
-                        args.rng_tag_a[slot] = rng.a;
-                    }
-                }
             }
         }
     }

@@ -1174,7 +1174,8 @@ struct WorkItemStats {
 // One work-item of propKernel (propagation_kernel.c.cl:406-913).  max_photons limits the
 // photons taken from the step (single-photon replay uses 1).
 void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, HitSink &sink, WorkItemStats &st,
-                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr)
+                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr,
+                   uint32_t interruptAtScatters = 0xffffffffu, uint64_t xResume = 0)
 {
     const Medium &m = sc.med;
     Vec4 stepDir;
@@ -1211,6 +1212,10 @@ void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, Hi
             if (traj) traj->record(ph, abs_lens_left);
         }
 
+        if (xAfterCreation && ph.numScatters == interruptAtScatters) {
+            rng.x = xResume; // replay: the stream was used for something else at this point
+            interruptAtScatters = 0xffffffffu;
+        }
         float distancePropagated;
         {
             float effective_z;
@@ -1530,6 +1535,7 @@ int oracle_propagate_single_photon(const oracle_scene *scene, const oracle_step 
 }
 
 int oracle_propagate_single_photon_split(const oracle_scene *scene, const oracle_step *step, uint64_t x_create, uint64_t x_propagate,
+                                         uint32_t interrupt_at_scatters, uint64_t x_resume,
                                          uint32_t a, oracle_photon *out, float *traj, int max_points, int *num_points)
 {
     Rng rng{x_create, a, 0};
@@ -1538,7 +1544,7 @@ int oracle_propagate_single_photon_split(const oracle_scene *scene, const oracle
     if (scene->history > 0) { sink.useLocal = true; }
     WorkItemStats st;
     TrajSink ts{traj, max_points, 0};
-    run_work_item(*scene, *step, rng, sink, st, 1, &ts, &x_propagate);
+    run_work_item(*scene, *step, rng, sink, st, 1, &ts, &x_propagate, interrupt_at_scatters, x_resume);
     if (num_points) *num_points = ts.n;
     if (sink.count > 0 && out) *out = sink.useLocal ? sink.local[0] : tmp[0];
     return sink.count > 0 ? 1 : 0;
