@@ -13,7 +13,8 @@ import numpy as np
 from .description import PHOTON_DTYPE, STEP_DTYPE, ConfigStruct, ResultStruct, build_config
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclsimcuda.so")
+# CLSIMCU_LIB selects another build of the same library (tools/build_variants.py, A/B runs)
+LIB_PATH = os.environ.get("CLSIMCU_LIB") or os.path.join(_HERE, "libclsimcuda.so")
 _lib = None
 
 # every entry point declared in include/clsimcuda.h
@@ -198,10 +199,10 @@ class Engine(object):
         return out
 
     def download_resident_rng_tags(self, k):
-        x = np.zeros(3 * k, dtype=np.uint64)
+        x = np.zeros(2 * k, dtype=np.uint64)
         a = np.zeros(2 * k, dtype=np.uint32)
         _check(lib().clsimcu_download_resident_rng_tags(self._h, x.ctypes.data, a.ctypes.data, k))
-        return x.reshape(k, 3), a.reshape(k, 2)
+        return x.reshape(k, 2), a.reshape(k, 2)  # per record: (x_create, x_propagate), (a_create, a_propagate)
 
     def rng_get(self, n):
         x = np.zeros(n, dtype=np.uint64)

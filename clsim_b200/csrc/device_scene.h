@@ -31,6 +31,7 @@ struct DevMedium {
     float n_phase[5], n_group[5], c_light;
     int scat_kind;
     float f_sl, one_minus_f_sl, g, g2, sl_beta;
+    float inv_f_sl, inv_one_minus_f_sl, inv_2g; // fast kernel: reciprocals (0 where undefined)
     int tilt_nd, tilt_nz;
     float tilt_z0, tilt_dz, tilt_lnx, tilt_lny;
     int anisotropy, pre_renorm, post_renorm;
@@ -61,18 +62,17 @@ struct DevGeometry {
     const float *tmpl_z;
     const uint32_t *string_tmpl_start;
     const float *string_mean_x, *string_mean_y;
-    // Fast kernel only: conservative distance field over the xy plane.  near_d1[pixel] is a lower
-    // bound (whole metres, capped at 255) of the distance from ANY point of the pixel to the
-    // nearest string axis; a segment of length L can only touch a DOM if L + string_max_radius
-    // reaches that far, so most segments skip the collision test after one byte load.
-    // near_info[pixel] = nearest string index (low 16 bits) | lower bound of the distance to every
-    // OTHER string (bits 16-23): when the segment cannot reach that either, only one string has to
-    // be tested; otherwise the reference's cell walk is used.  Points outside the table clamp to
-    // the border pixels (the bounds stay valid: projection onto the table rectangle is
+    // Fast kernel only: pixel map over the xy plane.  near_info[pixel] = index of the string
+    // nearest to the pixel centre (low 16 bits) | the RANGE of the pixel, stored as the upper 16
+    // bits of an fp32 (rounded down): a photon anywhere in the pixel can fly that far before any
+    // OTHER string can come within string_max_radius of it.  The fast kernel cuts flights at that
+    // range, so a segment only ever has to be tested against the one named string (exactly, from
+    // the photon's own position).  Range 0 marks pixels where the strings are too dense for the
+    // pixel size: there every segment takes the reference's cell walk.  Points outside the map
+    // clamp to the border pixels (the bound stays valid: projection onto the map rectangle is
     // non-expansive and every string lies inside it).
     int near_nx, near_ny;
     float near_x0, near_y0, near_inv_pixel;
-    const uint8_t *near_d1;
     const uint32_t *near_info;
     // index -> ID rewrite on the device (…ConverterOpenCL.cxx:1565-1602 does it on the host)
     const int16_t *string_index_to_id;
@@ -102,7 +102,9 @@ struct LaunchArgs {
     uint32_t *work_counter;    // fast kernel: next step to hand out
     uint64_t *rng_x;           // RNG streams used by this launch
     uint32_t *rng_a;
-    uint64_t *rng_tag_x;       // optional (save-all debugging): RNG state at photon creation
+    const struct DevScene *scene_dev; // the scene again, in global memory (out-of-line device functions read it there)
+    uint32_t rng_creation_offset;     // fast kernel: thread t creates photons from stream rng_creation_offset + t
+    uint64_t *rng_tag_x;       // optional (save-all replay): per record, creation and propagation RNG states
     uint32_t *rng_tag_a;
     int count_stats;
 };
@@ -111,6 +113,7 @@ struct LaunchArgs {
 int launch_reference_kernel(const DevScene &scene, const LaunchArgs &args, void *stream);
 int launch_fast_kernel(const DevScene &scene, const LaunchArgs &args, int grid_blocks, void *stream);
 bool fast_kernel_supports(const DevScene &scene, const char **why);
+bool fast_kernel_smem_is_the_problem(const DevScene &scene);
 void fast_kernel_geometry(int device, int *grid_blocks, int *threads_per_block);
 
 } // namespace clsimcu

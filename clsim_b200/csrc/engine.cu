@@ -162,6 +162,7 @@ struct clsimcu_engine {
     SceneTables tables;
     DevScene scene;
     uint8_t *d_arena = nullptr;
+    DevScene *d_scene = nullptr;   // copy of `scene` in global memory for out-of-line device code
     uint64_t *d_rng_x = nullptr;
     uint32_t *d_rng_a = nullptr;
     size_t rng_n = 0;
@@ -209,7 +210,7 @@ struct clsimcu_engine {
 namespace clsimcu {
 namespace {
 
-void upload_tables(clsimcu_engine &e)
+void upload_tables(clsimcu_engine &e, int near_pixel_budget)
 {
     const SceneTables &t = e.tables;
     Arena arena;
@@ -227,6 +228,9 @@ void upload_tables(clsimcu_engine &e)
     dm.c_light = m.c_light;
     dm.scat_kind = m.scat_kind;
     dm.f_sl = m.f_sl; dm.one_minus_f_sl = m.one_minus_f_sl; dm.g = m.g; dm.g2 = m.g2; dm.sl_beta = m.sl_beta;
+    dm.inv_f_sl = (m.f_sl > 0.f) ? 1.f / m.f_sl : 0.f;
+    dm.inv_one_minus_f_sl = (m.one_minus_f_sl > 0.f) ? 1.f / m.one_minus_f_sl : 0.f;
+    dm.inv_2g = (m.g != 0.f) ? 1.f / (2.f * m.g) : 0.f;
     dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
     dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
     dm.anisotropy = m.anisotropy; dm.pre_renorm = m.pre_renorm; dm.post_renorm = m.post_renorm;
@@ -265,7 +269,7 @@ void upload_tables(clsimcu_engine &e)
     size_t o_grid[kMaxSubdetectors] = {0};
     size_t o_sx = 0, o_sy = 0, o_smin = 0, o_smax = 0, o_sset = 0, o_lcount = 0, o_lstart = 0, o_lheight = 0, o_l2d = 0;
     size_t o_tdx = 0, o_tdy = 0, o_tz = 0, o_tstart = 0, o_mx = 0, o_my = 0, o_sid = 0, o_doff = 0, o_dids = 0;
-    size_t o_near_d1 = 0, o_near_info = 0;
+    size_t o_near_info = 0;
     if (t.has_geometry) {
         dg.num_strings = g.num_strings; dg.num_sets = g.num_sets; dg.max_layers = g.max_layers;
         dg.num_grids = static_cast<int>(g.grids.size());
@@ -306,25 +310,30 @@ void upload_tables(clsimcu_engine &e)
         }
         o_sid = arena.add(sid); o_doff = arena.add(doff); o_dids = arena.add(dids);
 
-        // distance field for the fast kernel (see device_scene.h)
+        // xy pixel map for the fast kernel (see device_scene.h); built for the pixel budget the
+        // caller found to fit into shared memory
         {
-            const float margin = 250.f;
             float xlo = g.string_x[0], xhi = g.string_x[0], ylo = g.string_y[0], yhi = g.string_y[0];
             for (int i = 0; i < g.num_strings; ++i) {
                 xlo = std::min(xlo, g.string_x[i]); xhi = std::max(xhi, g.string_x[i]);
                 ylo = std::min(ylo, g.string_y[i]); yhi = std::max(yhi, g.string_y[i]);
             }
-            // pixel size such that the byte table stays around 12 KB (it is staged in shared memory)
-            const float area = (xhi - xlo + 2 * margin) * (yhi - ylo + 2 * margin);
-            const float pixel = std::max(8.f, std::sqrt(area / 12000.f));
-            dg.near_x0 = xlo - margin;
-            dg.near_y0 = ylo - margin;
+            // one pixel of margin is enough: a point outside the map is farther from every string
+            // than its projection onto the map, so the border pixels' bounds hold for it
+            float pixel = 4.f;
+            for (;;) {
+                const double w = (xhi - xlo) + 2.0 * pixel, h = (yhi - ylo) + 2.0 * pixel;
+                if (std::ceil(w / pixel) * std::ceil(h / pixel) <= static_cast<double>(near_pixel_budget)) break;
+                pixel *= 1.05f;
+            }
+            dg.near_x0 = xlo - pixel;
+            dg.near_y0 = ylo - pixel;
             dg.near_inv_pixel = 1.f / pixel;
-            dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * margin) / pixel));
-            dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * margin) / pixel));
-            const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-3; // + slack for fp32 pixel assignment
-            std::vector<uint8_t> d1(static_cast<size_t>(dg.near_nx) * dg.near_ny);
-            std::vector<uint32_t> info(d1.size());
+            dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * pixel) / pixel));
+            dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * pixel) / pixel));
+            const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-2; // + slack for fp32 pixel assignment
+            const double min_range = 3.0; // below this the map cannot limit flights sensibly: cell walk
+            std::vector<uint32_t> info(static_cast<size_t>(dg.near_nx) * dg.near_ny);
             for (int iy = 0; iy < dg.near_ny; ++iy) {
                 for (int ix = 0; ix < dg.near_nx; ++ix) {
                     const double cx = dg.near_x0 + (ix + 0.5) * pixel, cy = dg.near_y0 + (iy + 0.5) * pixel;
@@ -335,13 +344,17 @@ void upload_tables(clsimcu_engine &e)
                         if (d < best) { second = best; best = d; who = k; }
                         else if (d < second) second = d;
                     }
-                    const double lb1 = std::max(0.0, best - half_diag), lb2 = std::max(0.0, second - half_diag);
-                    d1[static_cast<size_t>(iy) * dg.near_nx + ix] = static_cast<uint8_t>(std::min(255.0, std::floor(lb1)));
-                    info[static_cast<size_t>(iy) * dg.near_nx + ix] =
-                        static_cast<uint32_t>(who) | (static_cast<uint32_t>(std::min(255.0, std::floor(lb2))) << 16);
+                    // how far a photon anywhere in this pixel may fly before a string other than
+                    // `who` can come within the collision radius
+                    double range = std::min(second, 1e9) - half_diag - g.string_max_radius - 1e-2;
+                    if (range < min_range) range = 0.0;
+                    const float rf = static_cast<float>(range);
+                    uint32_t bits;
+                    std::memcpy(&bits, &rf, 4);
+                    bits &= 0xffff0000u; // truncation of a positive float rounds down: the bound stays a lower bound
+                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = static_cast<uint32_t>(who) | bits;
                 }
             }
-            o_near_d1 = arena.add(d1);
             o_near_info = arena.add(info);
         }
     }
@@ -351,6 +364,8 @@ void upload_tables(clsimcu_engine &e)
     s.prescale = t.prescale; s.fixed_abs_lens = t.fixed_abs_lens; s.pancake_factor = t.pancake_factor;
     s.inv_pancake_factor = t.pancake ? 1.f / t.pancake_factor : 1.f;
 
+    if (e.d_arena) { cudaFree(e.d_arena); e.d_arena = nullptr; }
+    if (e.d_scene) { cudaFree(e.d_scene); e.d_scene = nullptr; }
     CUDA_OK(cudaMalloc(&e.d_arena, arena.bytes().size()));
     CUDA_OK(cudaMemcpy(e.d_arena, arena.bytes().data(), arena.bytes().size(), cudaMemcpyHostToDevice));
     const uint8_t *b = e.d_arena;
@@ -377,9 +392,10 @@ void upload_tables(clsimcu_engine &e)
         dg.string_index_to_id = at<int16_t>(b, o_sid);
         dg.dom_id_offset = at<uint32_t>(b, o_doff);
         dg.dom_ids = at<uint16_t>(b, o_dids);
-        dg.near_d1 = at<uint8_t>(b, o_near_d1);
         dg.near_info = at<uint32_t>(b, o_near_info);
     }
+    CUDA_OK(cudaMalloc(&e.d_scene, sizeof(DevScene)));
+    CUDA_OK(cudaMemcpy(e.d_scene, &s, sizeof(DevScene), cudaMemcpyHostToDevice));
 }
 
 std::string prime_cache_path()
@@ -438,6 +454,9 @@ void submit_loop(clsimcu_engine *e)
                 a.rng_x = e->d_rng_x;
                 a.rng_a = e->d_rng_a;
                 a.count_stats = 0;
+                a.scene_dev = e->d_scene;
+            a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
+                a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
                 launch(*e, a, e->compute);
                 CUDA_OK(cudaEventRecord(s.k_stop, e->compute));
             }
@@ -526,7 +545,7 @@ void free_engine(clsimcu_engine *e)
         if (s.counted) cudaEventDestroy(s.counted);
         if (s.xfer) cudaStreamDestroy(s.xfer);
     }
-    cudaFree(e->d_arena); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
+    cudaFree(e->d_arena); cudaFree(e->d_scene); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
     cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
     cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush);
     cudaFreeHost(e->h_res_counters); cudaFreeHost(e->h_res_stats);
@@ -582,16 +601,25 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
         e->max_hits = std::min<size_t>(e->max_items * per_item, 0xffffffffull);
         if (!e->save_all && e->max_hits < 1000) e->max_hits = 1000;
 
-        upload_tables(*e);
         if (e->kernel_mode == CLSIMCU_KERNEL_FAST) {
+            // the pixel map of the collision test takes whatever shared memory the other tables leave
             const char *why = nullptr;
-            if (!fast_kernel_supports(e->scene, &why))
-                throw std::runtime_error(std::string("the fast kernel does not support this configuration (") + why + "); use CLSIMCU_KERNEL_REFERENCE");
+            int budget = 8192;
+            for (;;) {
+                upload_tables(*e, budget);
+                if (fast_kernel_supports(e->scene, &why)) break;
+                if (budget <= 512 || !fast_kernel_smem_is_the_problem(e->scene))
+                    throw std::runtime_error(std::string("the fast kernel does not support this configuration (") + why + "); use CLSIMCU_KERNEL_REFERENCE");
+                budget /= 2;
+            }
             fast_kernel_geometry(e->device, &e->fast_blocks, &e->fast_threads);
+        } else {
+            upload_tables(*e, 4096);
         }
 
         // RNG streams: one per work item (reference order) or one per resident thread (fast)
-        size_t need = (e->kernel_mode == CLSIMCU_KERNEL_REFERENCE) ? e->max_items : static_cast<size_t>(e->fast_blocks) * e->fast_threads;
+        // (fast: two per resident thread, one for photon creation and one for propagation)
+        size_t need = (e->kernel_mode == CLSIMCU_KERNEL_REFERENCE) ? e->max_items : 2 * static_cast<size_t>(e->fast_blocks) * e->fast_threads;
         e->rng_n = config->rng_n ? static_cast<size_t>(config->rng_n) : need;
         if (e->rng_n < need)
             throw std::runtime_error("rng_n (" + std::to_string(e->rng_n) + ") is smaller than the number of RNG streams this configuration needs (" + std::to_string(need) + ")");
@@ -778,7 +806,7 @@ int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t
             CUDA_OK(cudaHostAlloc(&e->h_res_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
             CUDA_OK(cudaMalloc(&e->d_l2_flush, kL2FlushBytes));
             if (e->save_all) {
-                CUDA_OK(cudaMalloc(&e->d_tag_x, 3 * e->res_cap * sizeof(uint64_t)));
+                CUDA_OK(cudaMalloc(&e->d_tag_x, 2 * e->res_cap * sizeof(uint64_t)));
                 CUDA_OK(cudaMalloc(&e->d_tag_a, 2 * e->res_cap * sizeof(uint32_t)));
             }
         }
@@ -824,6 +852,8 @@ int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint6
             a.rng_tag_x = e->d_tag_x;
             a.rng_tag_a = e->d_tag_a;
             a.count_stats = 1;
+            a.scene_dev = e->d_scene;
+            a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
             CUDA_OK(cudaEventRecord(ev[2 * r], e->compute));
             launch(*e, a, e->compute);
             CUDA_OK(cudaEventRecord(ev[2 * r + 1], e->compute));
@@ -873,7 +903,7 @@ int clsimcu_download_resident_rng_tags(clsimcu_engine *e, uint64_t *x, uint32_t 
         CUDA_OK(cudaSetDevice(e->device));
         const size_t k = std::min(std::min<size_t>(e->res_last_hits, e->res_cap), cap);
         if (k > 0) {
-            CUDA_OK(cudaMemcpy(x, e->d_tag_x, 3 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(x, e->d_tag_x, 2 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
             CUDA_OK(cudaMemcpy(a, e->d_tag_a, 2 * k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         }
     } catch (const std::exception &ex) {

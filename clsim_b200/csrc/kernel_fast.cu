@@ -2,21 +2,38 @@
 //
 // Design (B200-first, not the reference's one-work-item-per-step loop):
 //
-//  * Persistent CTAs (a multiple of the SM count), 8 warps each.  A WARP owns a step at a time
-//    and pulls the next one from a global work counter, so step bunches of any size balance
-//    across the 148 SMs and there is no per-step tail.
-//  * One photon per LANE, one MWC stream per lane (multipliers from the safe-prime table).
-//  * Per-lane MAILBOX in shared memory: photon creation (wavelength table search, Cherenkov cone,
-//    the wavelength-only transcendental factors of the ice model, lifetime) is done for many
-//    lanes at once, ahead of time, whenever >= kRefillThreshold lanes have used up their spare
-//    photon.  A lane whose photon dies pops its spare with a dozen shared-memory loads and
-//    keeps going; the expensive creation code never runs for one or two lanes only.  The
-//    start-of-flight record needed for a hit stays in shared memory, not in registers.
+//  * Persistent CTAs (a multiple of the SM count).  A WARP owns a step at a time and pulls the
+//    next one from a global work counter, so step bunches of any size balance across the 148 SMs
+//    and there is no per-step tail.
+//  * One photon per LANE.  The kernel alternates between two phases per warp:
+//      FAST  -- a straight-line loop with the photon state in registers: every iteration moves
+//               each live photon to its next EVENT (scatter, absorption, ice-layer boundary, or
+//               the range limit of the collision map).  No calls, no rare paths, no spills.
+//               Lanes whose photon ended, or whose segment might touch a DOM, go idle; the
+//               loop runs until kIdleLimit lanes are idle.
+//      SLOW  -- out of line, lane state parked in shared memory: the few segments that may touch
+//               a DOM get the reference's full collision test and hits are written out; idle
+//               lanes take their next photon from the warp's QUEUE; an empty queue is refilled
+//               by all 32 lanes at once (photon creation: wavelength table search, Cherenkov
+//               cone, the wavelength-only transcendental factors of the ice model, lifetime).
+//    Batching the rare work this way keeps its cost per photon small and, more importantly,
+//    keeps it from diverging the hot loop on almost every iteration.
+//  * Two MWC streams per lane (multipliers from the safe-prime table): one drives creation, one
+//    drives propagation, so a photon's propagation draws are contiguous in its stream and any
+//    photon can be replayed by a checker from two recorded states.
+//  * Flights are cut at ice-layer boundaries, so the reference's data-dependent walk over layers
+//    (propagation_kernel.c.cl:647-662) becomes straight-line code; the budgets (scattering /
+//    absorption lengths left) are carried in registers.  Same distances up to fp32 rounding.
 //  * The wavelength dependence of the ice (powr/exp of R4) is hoisted to once per photon: per
-//    segment and per layer crossed only two FMAs on per-layer coefficients remain, which live
-//    in shared memory as one float4 per layer together with the cell grid and string tables.
-//  * One reciprocal per segment in the common same-layer case; SL and HG scattering angles are
-//    both evaluated and selected (no divergent branch); fast approximate MUFU intrinsics.
+//    iteration only two FMAs on per-layer coefficients remain, which live in shared memory as one
+//    float4 per layer together with the collision tables.
+//  * DOM collision: an xy pixel map in shared memory names the string nearest to the photon and
+//    how far the photon may fly before any other string comes into range (flights are cut there
+//    too).  A 2-D segment/cylinder test against that one string rules out > 99.9 % of the
+//    segments in ~25 instructions; the rest run the reference's string / cell walk in the slow
+//    phase.
+//  * One reciprocal per iteration; SL and HG scattering angles are both evaluated and selected
+//    (no divergent branch); fast approximate MUFU intrinsics.
 //  * Hits: warp-aggregated atomic reservation, five 16-byte stores per record, string/DOM IDs
 //    and the wavelength-bias weight applied on the device.
 //
@@ -25,7 +42,7 @@
 // Physics restated from resources/kernels/propagation_kernel.c.cl and
 // sparse_collision_kernel.c.cl (citations at each block); the arithmetic is re-formulated, so
 // agreement with the reference is statistical (per-DOM counts, time and angle distributions)
-// and per photon within fp32 tolerance when a photon is replayed from its recorded RNG state.
+// and per photon within fp32 tolerance when a photon is replayed from its recorded RNG states.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -36,16 +53,41 @@
 namespace clsimcu {
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef CLSIMCU_THREADS
+#define CLSIMCU_THREADS 256
+#endif
+#ifndef CLSIMCU_BLOCKS_PER_SM
+#define CLSIMCU_BLOCKS_PER_SM 3
+#endif
+#ifndef CLSIMCU_IDLE_LIMIT
+#define CLSIMCU_IDLE_LIMIT 8
+#endif
+constexpr int kThreads = CLSIMCU_THREADS;
 constexpr int kWarpsPerBlock = kThreads / 32;
-constexpr int kBlocksPerSM = 4;
-constexpr int kRefillThreshold = 14; // lanes with an empty mailbox that trigger a creation pass
+constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
+constexpr int kIdleLimit = CLSIMCU_IDLE_LIMIT; // idle lanes that end a fast phase
 constexpr float kSpeedOfLight = 0.299792458f;
 constexpr float kPi = 3.14159265359f;
 constexpr float kEpsilon = 0.00001f;
 constexpr float kLn2 = 0.69314718056f;
+constexpr uint32_t kSmemBudget = 227u * 1024u;
+
+// start-of-flight record (what a hit needs besides the running state)
 constexpr int kStartWords = 10; // x y z t dx dy dz wlen abs_initial step_index
-constexpr int kSpareWords = 3;  // scattering factor, dust factor, pure-ice absorption
+// queue slot: start record + the three wavelength-only ice factors + replay tags
+constexpr int kQueueWords = 16; // [10] scattering factor [11] dust factor [12] pure-ice absorption [13,14] x_create [15] a_create
+// per-lane running state, parked in shared memory between fast phases
+enum StateWord {
+    kPx = 0, kPy, kPz, kDx, kDy, kDz, kAbsLeft, kScaLeft, kPath, kFScat, kFDust, kFPure, kScatters, kLayer, kStatus, kRngLo, kRngHi,
+    kZEff, kInvAniso, kStateWords
+};
+// per-lane replay tags of the photon in flight (save-all variants only)
+constexpr int kTagWords = 5; // x_create lo, hi, a_create, x_pop lo, hi
+// per-warp control block
+enum WarpCtl { kWLeft = 0, kWStepIndex, kWMore, kWQueued, kWCreated, kWarpCtlWords = 8 };
+constexpr int kWarpStepWords = 16; // the warp's step record (12 words) + its direction (3)
+
+enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3 };
 
 // ---- approximate MUFU wrappers ---------------------------------------------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -73,7 +115,26 @@ struct Mwc {
     }
 };
 
+__device__ __forceinline__ uint64_t pack64(float lo, float hi)
+{
+    return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
+}
+
 // Shared-memory plan, carved out of the dynamic allocation.
+struct SmemLayout {
+    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near;
+    uint32_t off_state, off_cstart, off_queue, off_nseg, off_tags, off_warp_step, off_warp_ctl;
+    uint32_t cell_offset[kMaxSubdetectors];
+    uint32_t total;
+};
+
+// First bytes of the dynamic shared memory: the layout and the launch arguments, so that
+// out-of-line device functions find everything from the shared-memory base alone.
+struct SmemHeader {
+    SmemLayout lay;
+    LaunchArgs args;
+};
+
 struct SmemPlan {
     float4 *layers;          // [num_layers] (b400, D*aDust+E, 1+0.01*dTau, 0)
     float4 *strings;         // [num_strings] (x, y, zmax+R, zmin-R)
@@ -81,16 +142,7 @@ struct SmemPlan {
     uint8_t *string_set;     // [num_strings]
     uint16_t *layer_to_dom;  // [layer_table_size]
     uint16_t *cells;         // concatenated grids
-    uint8_t *near_d1;        // distance field, one byte per pixel
-    float *start;            // [2][kStartWords][kThreads]
-    float *spare;            // [kSpareWords][kThreads]
-    uint32_t *warp_step;     // [kWarpsPerBlock][12]
-};
-
-struct SmemLayout {
-    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_start, off_spare, off_warp_step;
-    uint32_t cell_offset[kMaxSubdetectors];
-    uint32_t total;
+    uint32_t *near;          // xy pixel map, see device_scene.h
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -98,7 +150,7 @@ __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15
 __host__ SmemLayout plan_smem(const DevScene &s)
 {
     SmemLayout L{};
-    uint32_t at = 0;
+    uint32_t at = align16(sizeof(SmemHeader));
     L.off_layers = at; at = align16(at + s.medium.num_layers * 16);
     L.off_strings = at; at = align16(at + s.geo.num_strings * 16);
     L.off_sets = at; at = align16(at + s.geo.num_sets * 16);
@@ -111,12 +163,36 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         cells += s.geo.grids[i].num_x * s.geo.grids[i].num_y;
     }
     at = align16(at + cells * 2);
-    L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny + 4);
-    L.off_start = at; at = align16(at + 2 * kStartWords * kThreads * 4);
-    L.off_spare = at; at = align16(at + kSpareWords * kThreads * 4);
-    L.off_warp_step = at; at = align16(at + kWarpsPerBlock * 12 * 4);
+    L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
+    L.off_state = at; at = align16(at + kStateWords * kThreads * 4);
+    L.off_cstart = at; at = align16(at + kStartWords * kThreads * 4);
+    L.off_queue = at; at = align16(at + kWarpsPerBlock * kQueueWords * 32 * 4);
+    L.off_nseg = at; at = align16(at + kThreads * 4);
+    L.off_tags = at; at = align16(at + (s.save_all ? kTagWords * kThreads * 4 : 0));
+    L.off_warp_step = at; at = align16(at + kWarpsPerBlock * kWarpStepWords * 4);
+    L.off_warp_ctl = at; at = align16(at + kWarpsPerBlock * kWarpCtlWords * 4);
     L.total = at;
     return L;
+}
+
+__device__ __forceinline__ uint8_t *smem_base()
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    return smem;
+}
+
+__device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
+{
+    uint8_t *smem = smem_base();
+    SmemPlan sp;
+    sp.layers = reinterpret_cast<float4 *>(smem + lay.off_layers);
+    sp.strings = reinterpret_cast<float4 *>(smem + lay.off_strings);
+    sp.sets = reinterpret_cast<float4 *>(smem + lay.off_sets);
+    sp.string_set = smem + lay.off_string_set;
+    sp.layer_to_dom = reinterpret_cast<uint16_t *>(smem + lay.off_layer_to_dom);
+    sp.cells = reinterpret_cast<uint16_t *>(smem + lay.off_cells);
+    sp.near = reinterpret_cast<uint32_t *>(smem + lay.off_near);
+    return sp;
 }
 
 struct V3 {
@@ -142,7 +218,9 @@ __device__ __forceinline__ void rotate_by(float cosa, float sina, V3 &d, float r
         ny = sina * sinb;
         nz = (d.z > 0.f) ? cosa : ((d.z < 0.f) ? -cosa : cosa * d.z);
     }
-    const float inv = mufu_rsqrt(nx * nx + ny * ny + nz * nz);
+    // the rotation preserves the length up to rounding, so one Newton step of 1/sqrt about 1 is
+    // exact to fp32 here and keeps the special-function unit free
+    const float inv = fmaf(nx * nx + ny * ny + nz * nz, -0.5f, 1.5f);
     d.x = nx * inv; d.y = ny * inv; d.z = nz * inv;
 }
 
@@ -249,9 +327,10 @@ __device__ __forceinline__ void apply_matrix(const float *M, V3 &d)
     d.x = nx * inv; d.y = ny * inv; d.z = nz * inv;
 }
 
-__device__ __forceinline__ float life_of_current(const float *start0, int buffer)
+__device__ __forceinline__ float safe_inv_dz(float dz)
 {
-    return start0[buffer * (kStartWords * kThreads) + 8 * kThreads];
+    // the reference treats |dz| < 1e-5 as "stays in its layer" (propagation_kernel.c.cl:669)
+    return (fabsf(dz) < kEpsilon) ? ((dz < 0.f) ? -1e30f : 1e30f) : mufu_rcp(dz);
 }
 
 // ---- R6: DOM collision, restated for SIMT -----------------------------------------------------
@@ -300,12 +379,23 @@ __device__ __forceinline__ void test_string(const SmemPlan &sp, const DevGeometr
     }
 }
 
-// Cell level, the reference's walk over the xy cells covered by the segment
-// (sparse_collision_kernel.c.cl:194-303, 305-460).  Only taken when the distance field cannot
-// narrow the candidates down to one string, so it is kept out of line.
-__device__ __noinline__ void cell_walk(const SmemPlan sp, const DevGeometry &geo, const SmemLayout &lay, V3 pos, V3 dir, float inv_xy2,
-                                       float inv_pancake, Collision &c)
+// The collision test proper, for the few segments the pixel map cannot rule out.  `who` >= 0:
+// only that string can be reached (string level of the reference); `who` < 0: the reference's
+// walk over the xy cells covered by the segment (sparse_collision_kernel.c.cl:194-303, 305-460).
+__device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos, V3 dir, float travel)
 {
+    const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
+    const SmemPlan sp = table_plan(lay);
+    const DevGeometry &geo = scene->geo;
+    Collision c{travel, 0, 0, false};
+    const float dir_xy2 = dir.x * dir.x + dir.y * dir.y;
+    if (!(dir_xy2 > 0.f)) return c; // sparse_collision_kernel.c.cl:511-512
+    const float inv_xy2 = mufu_rcp(dir_xy2);
+    const float inv_pancake = scene->inv_pancake_factor;
+    if (who >= 0) {
+        test_string(sp, geo, who, pos, dir, inv_xy2, inv_pancake, c);
+        return c;
+    }
     for (int gI = 0; gI < geo.num_grids; ++gI) {
         const DevCellGrid &cg = geo.grids[gI];
         const float ex = pos.x + dir.x * c.travel, ey = pos.y + dir.y * c.travel;
@@ -321,16 +411,19 @@ __device__ __noinline__ void cell_walk(const SmemPlan sp, const DevGeometry &geo
             }
         }
     }
+    return c;
 }
 
 // ---- R10: hit output ----------------------------------------------------------------------------
 // Called by the lanes whose photon was just detected (or absorbed, in save-all mode): `pos` is
-// the end point, `path` the full path length.  Reservation is aggregated over the lanes that
-// arrive together; the record leaves as five 16-byte stores.
-__device__ __noinline__ void emit_record(const DevScene &scene, const LaunchArgs &args, const float *st, V3 pos, V3 dir, float path,
-                                         uint32_t scatters, int hit_string, int hit_dom, float dist_abs, bool save_all,
-                                         uint64_t tag_create, uint64_t tag_pop, uint64_t tag_resume, uint32_t interrupt_at, uint32_t rng_a)
+// the end point, `path` the full path length, `st` the lane's start-of-flight record.
+// Reservation is aggregated over the lanes that arrive together; the record leaves as five
+// 16-byte stores.
+__device__ __noinline__ void emit_record(const DevScene *scene_dev, const float *st, V3 pos, V3 dir, float path, uint32_t scatters,
+                                         int hit_string, int hit_dom, float dist_abs, bool save_all, const uint32_t *tags, uint32_t rng_a)
 {
+    const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
+    const DevScene &scene = *scene_dev;
     const unsigned peers = __activemask();
     const int lane = threadIdx.x & 31;
     const int leader = __ffs(peers) - 1;
@@ -371,38 +464,443 @@ __device__ __noinline__ void emit_record(const DevScene &scene, const LaunchArgs
                          __uint_as_float(__ldg(&step->identifier)), __uint_as_float(ids));
     dst[3] = make_float4(st[0 * kThreads], st[1 * kThreads], st[2 * kThreads], stt);
     dst[4] = make_float4(sth, sph, 1.f / ivg, dist_abs);
-    if (save_all && args.rng_tag_x) {
-        args.rng_tag_x[3 * static_cast<size_t>(slot)] = tag_create;
-        args.rng_tag_x[3 * static_cast<size_t>(slot) + 1] = tag_pop;
-        args.rng_tag_x[3 * static_cast<size_t>(slot) + 2] = tag_resume;
-        args.rng_tag_a[2 * static_cast<size_t>(slot)] = rng_a;
-        args.rng_tag_a[2 * static_cast<size_t>(slot) + 1] = interrupt_at;
+    if (save_all && args.rng_tag_x && tags) {
+        args.rng_tag_x[2 * static_cast<size_t>(slot)] = static_cast<uint64_t>(tags[0 * kThreads]) | (static_cast<uint64_t>(tags[1 * kThreads]) << 32);
+        args.rng_tag_x[2 * static_cast<size_t>(slot) + 1] = static_cast<uint64_t>(tags[3 * kThreads]) | (static_cast<uint64_t>(tags[4 * kThreads]) << 32);
+        args.rng_tag_a[2 * static_cast<size_t>(slot)] = tags[2 * kThreads];
+        args.rng_tag_a[2 * static_cast<size_t>(slot) + 1] = rng_a;
     }
+}
+
+// R3: createPhotonFromTrack (propagation_kernel.c.cl:132-184) plus the wavelength-only factors of
+// the ice model (R4, …_Optimizers.cxx:123-250), written to queue slot `slot` (word stride 32).
+// The scene is read from its copy in global memory (uniform addresses).  Returns the advanced
+// state of the creation stream.
+__device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float *slot, uint64_t rng_x, uint32_t rng_a,
+                                               uint32_t step_index)
+{
+    const DevMedium &m = scene->medium;
+    Mwc rng{rng_x, rng_a};
+    const float s_x = __uint_as_float(wstep[0]), s_y = __uint_as_float(wstep[1]), s_z = __uint_as_float(wstep[2]);
+    const float s_t = __uint_as_float(wstep[3]), s_len = __uint_as_float(wstep[6]), s_beta = __uint_as_float(wstep[7]);
+    const uint32_t source = (wstep[11] & 0xffu);
+    const V3 axis{__uint_as_float(wstep[12]), __uint_as_float(wstep[13]), __uint_as_float(wstep[14])};
+    const float shift = s_len * rng.co();
+    V3 d = axis;
+    float wlen;
+    if (scene->num_generators <= 1 || source == 0) {
+        wlen = draw_wavelength(scene->generators[0], rng);
+        const float cos_c = fminf(1.f, mufu_rcp(s_beta * phase_index(m, wlen)));
+        const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
+        rotate_by(cos_c, sin_c, d, rng.co());
+    } else {
+        wlen = (source < static_cast<uint32_t>(scene->num_generators)) ? draw_wavelength(scene->generators[source], rng) : 0.f;
+    }
+    const float life = scene->fixed_abs ? scene->fixed_abs_lens : -fast_ln(rng.oc());
+    slot[0 * 32] = s_x + axis.x * shift;
+    slot[1 * 32] = s_y + axis.y * shift;
+    slot[2 * 32] = s_z + axis.z * shift;
+    slot[3 * 32] = s_t + shift * mufu_rcp(kSpeedOfLight * s_beta);
+    slot[4 * 32] = d.x;
+    slot[5 * 32] = d.y;
+    slot[6 * 32] = d.z;
+    slot[7 * 32] = wlen;
+    slot[8 * 32] = life;
+    slot[9 * 32] = __uint_as_float(step_index);
+    const float nm = wlen * 1e9f;
+    slot[10 * 32] = fast_pow(wlen * m.inv_ref_wlen, -m.alpha);                // 1/scatLen = b400 * this
+    slot[11 * 32] = fast_pow(nm, -m.kappa);                                  // dust term factor
+    slot[12 * 32] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
+    slot[13 * 32] = __uint_as_float(static_cast<uint32_t>(rng_x));
+    slot[14 * 32] = __uint_as_float(static_cast<uint32_t>(rng_x >> 32));
+    slot[15 * 32] = __uint_as_float(rng_a);
+    return rng.x;
+}
+
+// The rest of a flight that was cut short by a DOM: the reference reports distInAbsLens for the
+// UNSHORTENED segment (propagation_kernel.c.cl:718), i.e. the absorption budget left where the
+// flight would have ended.  Only hit photons whose flight was not going to end in this layer
+// come here, so the loop the main path avoids is acceptable.
+__device__ __noinline__ float abs_left_at_end_of_flight(const float4 *layers, float z0, float h, int num_layers, int layer, float z,
+                                                        float dz, float inv_dz, float sca_left, float abs_left, float f_scat,
+                                                        float f_dust, float f_pure)
+{
+    const bool up = !(dz < 0.f);
+    for (;;) {
+        const float4 c = layers[layer];
+        const float b = c.x * f_scat, a = c.y * f_dust + c.z * f_pure;
+        const float zb = z0 + h * static_cast<float>(layer + (up ? 1 : 0));
+        const float d_b = fmaxf((zb - z) * inv_dz, 0.f);
+        const bool can_cross = up ? (layer < num_layers - 1) : (layer > 0);
+        const bool absorbed = abs_left * b < sca_left * a;
+        const float d_sa = (absorbed ? abs_left : sca_left) * mufu_rcp(absorbed ? a : b);
+        if (!(can_cross && d_b < d_sa)) return absorbed ? 0.f : abs_left - d_sa * a;
+        sca_left = fmaxf(sca_left - d_b * b, 1e-30f);
+        abs_left -= d_b * a;
+        z = zb;
+        layer += up ? 1 : -1;
+    }
+}
+
+// ---- the photon in flight ---------------------------------------------------------------------
+struct Lane {
+    V3 pos, dir;
+    float inv_dz;                     // 1/dir.z (guarded), refreshed whenever the direction changes
+    float abs_left, sca_left, path;   // sca_left == 0 marks "draw a new flight"
+    float f_scat, f_dust, f_pure;
+    float z_eff;                      // TILT only: z in the untilted layer frame, carried along the flight
+    float inv_aniso;                  // ANISO only: abs_left is held scaled by 1/inv_aniso during a flight
+    uint32_t scatters;
+    int layer;
+    uint32_t status;
+    uint64_t rng_x;
+};
+
+template <bool TILT, bool ANISO> __device__ __forceinline__ void load_lane(Lane &L, const float *st)
+{
+    L.pos.x = st[kPx * kThreads]; L.pos.y = st[kPy * kThreads]; L.pos.z = st[kPz * kThreads];
+    L.dir.x = st[kDx * kThreads]; L.dir.y = st[kDy * kThreads]; L.dir.z = st[kDz * kThreads];
+    L.inv_dz = safe_inv_dz(L.dir.z);
+    L.abs_left = st[kAbsLeft * kThreads]; L.sca_left = st[kScaLeft * kThreads]; L.path = st[kPath * kThreads];
+    L.f_scat = st[kFScat * kThreads]; L.f_dust = st[kFDust * kThreads]; L.f_pure = st[kFPure * kThreads];
+    L.scatters = __float_as_uint(st[kScatters * kThreads]);
+    L.layer = __float_as_int(st[kLayer * kThreads]);
+    L.status = __float_as_uint(st[kStatus * kThreads]);
+    L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
+    L.z_eff = TILT ? st[kZEff * kThreads] : 0.f;
+    L.inv_aniso = ANISO ? st[kInvAniso * kThreads] : 1.f;
+}
+
+template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(const Lane &L, float *st)
+{
+    st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
+    st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
+    st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = L.sca_left; st[kPath * kThreads] = L.path;
+    st[kScatters * kThreads] = __uint_as_float(L.scatters);
+    st[kLayer * kThreads] = __int_as_float(L.layer);
+    st[kStatus * kThreads] = __uint_as_float(L.status);
+    st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x));
+    st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x >> 32));
+    if (TILT) st[kZEff * kThreads] = L.z_eff;
+    if (ANISO) st[kInvAniso * kThreads] = L.inv_aniso;
+}
+
+// One iteration: move the photon to its next event.  RESOLVE = false is the hot loop: a segment
+// that might touch a DOM parks the lane (status kFrozen) with nothing but the scattering-length
+// draw applied.  RESOLVE = true (slow phase) runs the same arithmetic again for such a lane,
+// this time with the full collision test and the hit output.  `scene_dev`/`cstart` are only
+// used by RESOLVE.
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool RESOLVE>
+__device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
+                                               const float4 *strings, const uint32_t *near, uint32_t rng_a, const float *cstart)
+{
+    const DevMedium &m = scene.medium;
+    const DevGeometry &geo = scene.geo;
+    Mwc rng{L.rng_x, rng_a};
+    const int top_layer = m.num_layers - 1;
+
+    // ------------------------------------------------------------------ R5: next event of the flight
+    if (L.sca_left <= 0.f) {
+        // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
+        if (TILT) {
+            L.z_eff = L.pos.z - tilt_shift(m, L.pos.x, L.pos.y, L.pos.z);
+            L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), top_layer);
+        }
+        if (ANISO) {
+            // R4b: 1/f = (B2-nB)*An/2 (I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx:92-134)
+            const float n0 = m.azx * L.dir.x + m.azy * L.dir.y, n1 = m.neg_azy * L.dir.x + m.azx * L.dir.y;
+            const float s0 = n0 * n0, s1 = n1 * n1, s2 = L.dir.z * L.dir.z;
+            const float nB = s0 * m.rl[0] + s1 * m.rl[1] + s2 * m.rl[2];
+            const float An = s0 * m.l[0] + s1 * m.l[1] + s2 * m.l[2];
+            L.inv_aniso = (m.B2 - nB) * An * 0.5f;
+            L.abs_left *= mufu_rcp(L.inv_aniso);
+        }
+        L.sca_left = -fast_ln(rng.oc());
+        L.rng_x = rng.x;
+    }
+    const float4 c = layers[L.layer];
+    const float b = c.x * L.f_scat;                          // 1/scattering length
+    const float a = fmaf(c.y, L.f_dust, c.z * L.f_pure);     // 1/absorption length
+    const bool up = !(L.dir.z < 0.f);
+    const float zb = fmaf(m.h, static_cast<float>(L.layer + (up ? 1 : 0)), m.z0);
+    const float zc = TILT ? L.z_eff : L.pos.z;
+    const float d_b = fmaxf((zb - zc) * L.inv_dz, 0.f);
+    const bool can_cross = up ? (L.layer < top_layer) : (L.layer > 0);
+    const bool absorbed = L.abs_left * b < L.sca_left * a;   // d_absorb < d_scatter inside this layer
+    const float d_sa = (absorbed ? L.abs_left : L.sca_left) * mufu_rcp(absorbed ? a : b);
+
+    // ------------------------------------------------------------------ R6: DOM collision, cheap part
+    // pixel map: nearest string and the range within which no other string can be touched
+    int who = -1;
+    float cap = __int_as_float(0x7f800000);
+    float ox = 0.f, oy = 0.f;
+    bool walk = false;
+    if (!SAVE_ALL) {
+        const int px = min(max(__float2int_rz((L.pos.x - geo.near_x0) * geo.near_inv_pixel), 0), geo.near_nx - 1);
+        const int py = min(max(__float2int_rz((L.pos.y - geo.near_y0) * geo.near_inv_pixel), 0), geo.near_ny - 1);
+        const uint32_t cell = near[py * geo.near_nx + px];
+        who = static_cast<int>(cell & 0xffffu);
+        const float range = __uint_as_float(cell & 0xffff0000u);
+        walk = !(range > 0.f);          // strings too dense here for the map: no range limit, cell walk instead
+        if (!walk) cap = range;
+        const float2 sxy = *reinterpret_cast<const float2 *>(strings + who);
+        ox = sxy.x - L.pos.x;
+        oy = sxy.y - L.pos.y;
+    }
+    const float d_geo = can_cross ? fminf(d_b, cap) : cap;
+    const bool limited = d_geo < d_sa;                       // the flight goes on after this iteration
+    const bool cross = limited && can_cross && (d_b <= cap);
+    float travel = limited ? d_geo : d_sa;
+    const float rem_abs = fmaf(-travel, a, L.abs_left);
+    const float rem_sca = fmaxf(fmaf(-travel, b, L.sca_left), 1e-30f);
+
+    Collision col{travel, 0, 0, false};
+    if (!SAVE_ALL) {
+        // 2-D segment / cylinder test against the one string in range
+        const float R = geo.string_max_radius;
+        const float o2 = ox * ox + oy * oy;
+        const float t = ox * L.dir.x + oy * L.dir.y;
+        const float dxy2 = L.dir.x * L.dir.x + L.dir.y * L.dir.y;
+        const float reach = travel + R;
+        const float out2 = o2 - R * R;                       // > 0: the photon starts outside the cylinder
+        const bool miss = (o2 > reach * reach) || ((t <= 0.f) && (out2 > 0.f)) || (out2 * dxy2 > t * t);
+        if (!miss || walk) {
+            if (!RESOLVE) {
+                L.status = kFrozen;
+                return;
+            }
+            col = collide(scene_dev, walk ? -1 : who, L.pos, L.dir, travel);
+        }
+    }
+    bool emit = false;
+    float emit_dist_abs = 0.f;
+    if (RESOLVE && col.hit) {
+        // distInAbsLens is taken for the unshortened flight (propagation_kernel.c.cl:718)
+        float at_end = absorbed ? 0.f : rem_abs;
+        if (limited)
+            at_end = abs_left_at_end_of_flight(layers, m.z0, m.h, m.num_layers, cross ? L.layer + (up ? 1 : -1) : L.layer,
+                                               cross ? zb : fmaf(L.dir.z, travel, zc), L.dir.z, L.inv_dz, rem_sca, rem_abs, L.f_scat,
+                                               L.f_dust, L.f_pure);
+        if (ANISO) at_end *= L.inv_aniso;
+        emit = true;
+        emit_dist_abs = cstart[8 * kThreads] - at_end;
+        travel = col.travel;
+    }
+
+    // ------------------------------------------------------------------ advance
+    L.pos.x = fmaf(L.dir.x, travel, L.pos.x);
+    L.pos.y = fmaf(L.dir.y, travel, L.pos.y);
+    L.pos.z = fmaf(L.dir.z, travel, L.pos.z);
+    L.path += travel;
+
+    bool dead = RESOLVE && col.hit;
+    if (!limited) {
+        L.abs_left = absorbed ? 0.f : rem_abs;
+        if (ANISO) L.abs_left *= L.inv_aniso;
+        dead = dead || (L.abs_left < kEpsilon);
+    }
+    if (dead) {
+        L.status = SAVE_ALL ? kDying : kDead;
+        if (RESOLVE && emit)
+            emit_record(scene_dev, cstart, L.pos, L.dir, L.path, L.scatters, col.string, col.dom, emit_dist_abs, false, nullptr, rng_a);
+    } else if (limited) {
+        // the flight goes on (in the neighbouring layer, or past the range limit of the collision
+        // map) with what is left of both budgets
+        if (cross) L.layer += up ? 1 : -1;
+        L.abs_left = rem_abs;
+        L.sca_left = rem_sca;
+        if (TILT) L.z_eff = cross ? zb : fmaf(L.dir.z, travel, L.z_eff);
+    } else {
+        // -------------------------------------------------------------- R9 + R8: scatter
+        if (ANISO) apply_matrix(m.pre, L.dir);
+        const float rr = rng.co();
+        float cs;
+        if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
+            // both samplers are evaluated and one is selected: no divergent branch
+            const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
+            const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
+            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+            const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
+            cs = (rr < m.f_sl) ? cos_sl : cos_hg;
+        } else if (m.scat_kind == CLSIMCU_SCAT_HG) {
+            const float s = 2.f * rr - 1.f;
+            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+            cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
+        } else {
+            cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
+        }
+        cs = fminf(fmaxf(cs, -1.f), 1.f);
+        const float sn = mufu_sqrt(1.f - cs * cs);
+        rotate_by(cs, sn, L.dir, rng.co());
+        if (ANISO) apply_matrix(m.post, L.dir);
+        L.inv_dz = safe_inv_dz(L.dir.z);
+        L.sca_left = 0.f;
+        ++L.scatters;
+        L.rng_x = rng.x;
+    }
+}
+
+// ---- slow phase ------------------------------------------------------------------------------
+// Runs converged, once per warp each time the hot loop has collected kIdleLimit idle lanes.
+// Returns the number of idle lanes that ends the next fast phase, or -1 when the warp is done.
+template <bool TILT, bool ANISO, bool SAVE_ALL> __device__ __noinline__ int slow_phase(const DevScene *scene)
+{
+    uint8_t *smem = smem_base();
+    const SmemHeader *hdr = reinterpret_cast<const SmemHeader *>(smem);
+    const SmemLayout &lay = hdr->lay;
+    const LaunchArgs &args = hdr->args;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const unsigned lane_bit = 1u << lane;
+    float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
+    float *cstart = reinterpret_cast<float *>(smem + lay.off_cstart) + tid;
+    float *queue = reinterpret_cast<float *>(smem + lay.off_queue) + warp * (kQueueWords * 32);
+    uint32_t *nseg = reinterpret_cast<uint32_t *>(smem + lay.off_nseg) + tid;
+    uint32_t *tags = SAVE_ALL ? reinterpret_cast<uint32_t *>(smem + lay.off_tags) + tid : nullptr;
+    uint32_t *wstep = reinterpret_cast<uint32_t *>(smem + lay.off_warp_step) + warp * kWarpStepWords;
+    uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+    const uint32_t gthread = blockIdx.x * kThreads + tid;
+    const uint32_t rng_a = __ldg(args.rng_a + gthread);
+
+    uint32_t w_left = wctl[kWLeft], w_step_index = wctl[kWStepIndex], queued = wctl[kWQueued], w_created = wctl[kWCreated];
+    bool w_more = wctl[kWMore] != 0;
+    __syncwarp();
+    uint32_t status = __float_as_uint(st[kStatus * kThreads]);
+
+    // ---- photons whose next segment may touch a DOM: finish that segment with the full test
+    if (!SAVE_ALL && status == kFrozen) {
+        const SmemPlan sp = table_plan(lay);
+        Lane L;
+        load_lane<TILT, ANISO>(L, st);
+        L.status = kActive;
+        advance_photon<TILT, ANISO, SAVE_ALL, true>(L, *scene, scene, sp.layers, sp.strings, sp.near, rng_a, cstart);
+        store_lane<TILT, ANISO>(L, st);
+        status = L.status;
+    }
+    // ---- save-all: every photon that ended is recorded with probability `prescale`
+    //      (propagation_kernel.c.cl:800-826)
+    if (SAVE_ALL && status == kDying) {
+        Mwc rng{pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]), rng_a};
+        const bool keep = rng.co() < scene->prescale;
+        st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(rng.x));
+        st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(rng.x >> 32));
+        if (keep) {
+            const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
+            const V3 dir{st[kDx * kThreads], st[kDy * kThreads], st[kDz * kThreads]};
+            emit_record(scene, cstart, pos, dir, st[kPath * kThreads], __float_as_uint(st[kScatters * kThreads]), 0, 0, cstart[8 * kThreads],
+                        true, tags, rng_a);
+        }
+        status = kDead;
+    }
+
+    // ---- idle lanes take the next photons of the warp's queue; an empty queue is refilled by
+    //      all lanes at once from the warp's step (and the steps after it)
+    for (;;) {
+        const unsigned dead = __ballot_sync(0xffffffffu, status == kDead);
+        if (dead == 0u) break;
+        if (queued == 0) {
+            if (!(w_more || w_left > 0)) break;
+            Mwc crng{args.rng_x[args.rng_creation_offset + gthread], __ldg(args.rng_a + args.rng_creation_offset + gthread)};
+            bool need = true;
+            for (;;) {
+                const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+                if (need_mask == 0) break;
+                if (w_left == 0) {
+                    if (!w_more) break;
+                    // next step for this warp
+                    uint32_t idx = 0;
+                    if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
+                    idx = __shfl_sync(0xffffffffu, idx, 0);
+                    if (idx >= args.num_steps) { w_more = false; break; }
+                    __syncwarp();
+                    if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
+                    __syncwarp();
+                    w_step_index = idx;
+                    w_left = wstep[8];
+                    if (lane == 0) {
+                        float sth, cth, sph, cph;
+                        __sincosf(__uint_as_float(wstep[4]), &sth, &cth);
+                        __sincosf(__uint_as_float(wstep[5]), &sph, &cph);
+                        wstep[12] = __float_as_uint(sth * cph);
+                        wstep[13] = __float_as_uint(sth * sph);
+                        wstep[14] = __float_as_uint(cth);
+                    }
+                    __syncwarp();
+                    if (w_left == 0) continue; // dummy step (quirk 11)
+                }
+                // the lanes still in need are the upper ones, so the filled slots stay a prefix
+                const int rank = __popc(need_mask & (lane_bit - 1u));
+                const bool take = need && (static_cast<uint32_t>(rank) < w_left);
+                if (take) {
+                    crng.x = create_photon(scene, wstep, queue + lane, crng.x, crng.a, w_step_index);
+                    need = false;
+                }
+                const uint32_t took = __popc(__ballot_sync(0xffffffffu, take));
+                queued += took;
+                w_created += took;
+                w_left -= took;
+            }
+            args.rng_x[args.rng_creation_offset + gthread] = crng.x;
+            __syncwarp();
+            if (queued == 0) break; // nothing left to create
+        }
+        const uint32_t rank = __popc(dead & (lane_bit - 1u));
+        if (status == kDead && rank < queued) {
+            const float *slot = queue + (queued - 1u - rank);
+            // statistics: one flight (reference: segment) per scatter, plus the last one
+            *nseg += __float_as_uint(st[kScatters * kThreads]) + 1u;
+#pragma unroll
+            for (int w = 0; w < kStartWords; ++w) cstart[w * kThreads] = slot[w * 32];
+            const float z = slot[2 * 32];
+            st[kPx * kThreads] = slot[0 * 32]; st[kPy * kThreads] = slot[1 * 32]; st[kPz * kThreads] = z;
+            st[kDx * kThreads] = slot[4 * 32]; st[kDy * kThreads] = slot[5 * 32]; st[kDz * kThreads] = slot[6 * 32];
+            st[kAbsLeft * kThreads] = slot[8 * 32];
+            st[kScaLeft * kThreads] = 0.f;
+            st[kPath * kThreads] = 0.f;
+            st[kFScat * kThreads] = slot[10 * 32]; st[kFDust * kThreads] = slot[11 * 32]; st[kFPure * kThreads] = slot[12 * 32];
+            st[kScatters * kThreads] = __uint_as_float(0u);
+            st[kLayer * kThreads] = __int_as_float(min(max(__float2int_rz((z - scene->medium.z0) * scene->medium.inv_h), 0), scene->medium.num_layers - 1));
+            status = kActive;
+            if (SAVE_ALL) {
+                tags[0 * kThreads] = __float_as_uint(slot[13 * 32]);
+                tags[1 * kThreads] = __float_as_uint(slot[14 * 32]);
+                tags[2 * kThreads] = __float_as_uint(slot[15 * 32]);
+                tags[3 * kThreads] = __float_as_uint(st[kRngLo * kThreads]);
+                tags[4 * kThreads] = __float_as_uint(st[kRngHi * kThreads]);
+            }
+        }
+        queued -= min(static_cast<uint32_t>(__popc(dead)), queued);
+        __syncwarp();
+    }
+    st[kStatus * kThreads] = __uint_as_float(status);
+
+    const int n_idle = __popc(__ballot_sync(0xffffffffu, status != kActive));
+    if (lane == 0) {
+        wctl[kWLeft] = w_left; wctl[kWStepIndex] = w_step_index; wctl[kWMore] = w_more ? 1u : 0u; wctl[kWQueued] = queued;
+        wctl[kWCreated] = w_created;
+    }
+    __syncwarp();
+    if (n_idle == 32) return -1;                    // nothing in flight, nothing queued, nothing to fetch
+    return (n_idle > 0) ? n_idle + 1 : kIdleLimit;  // idle lanes remain only when the work has run out: drain
 }
 
 template <bool TILT, bool ANISO, bool SAVE_ALL>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 propagate_persistent(const __grid_constant__ DevScene scene, const __grid_constant__ LaunchArgs args, const __grid_constant__ SmemLayout lay)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *smem = smem_base();
     const DevMedium &m = scene.medium;
     const DevGeometry &geo = scene.geo;
-    SmemPlan sp;
-    sp.layers = reinterpret_cast<float4 *>(smem + lay.off_layers);
-    sp.strings = reinterpret_cast<float4 *>(smem + lay.off_strings);
-    sp.sets = reinterpret_cast<float4 *>(smem + lay.off_sets);
-    sp.string_set = smem + lay.off_string_set;
-    sp.layer_to_dom = reinterpret_cast<uint16_t *>(smem + lay.off_layer_to_dom);
-    sp.cells = reinterpret_cast<uint16_t *>(smem + lay.off_cells);
-    sp.near_d1 = smem + lay.off_near;
-    sp.start = reinterpret_cast<float *>(smem + lay.off_start);
-    sp.spare = reinterpret_cast<float *>(smem + lay.off_spare);
-    sp.warp_step = reinterpret_cast<uint32_t *>(smem + lay.off_warp_step);
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const unsigned lane_bit = 1u << lane;
+    if (tid == 0) {
+        SmemHeader *hdr = reinterpret_cast<SmemHeader *>(smem);
+        hdr->lay = lay;
+        hdr->args = args;
+    }
+    const SmemPlan sp = table_plan(lay);
 
     // ---- stage the hot tables into shared memory (coalesced reads, once per CTA)
     for (int i = tid; i < m.num_layers; i += kThreads)
@@ -421,313 +919,52 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             const int n = geo.grids[gI].num_x * geo.grids[gI].num_y;
             for (int i = tid; i < n; i += kThreads) sp.cells[lay.cell_offset[gI] + i] = __ldg(geo.grids[gI].cell_to_string + i);
         }
-        const int near_words = (geo.near_nx * geo.near_ny + 3) / 4;
-        for (int i = tid; i < near_words; i += kThreads)
-            reinterpret_cast<uint32_t *>(sp.near_d1)[i] = __ldg(reinterpret_cast<const uint32_t *>(geo.near_d1) + i);
+        for (int i = tid; i < geo.near_nx * geo.near_ny; i += kThreads) sp.near[i] = __ldg(geo.near_info + i);
+    }
+
+    // ---- lane and warp state
+    float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
+    const uint32_t gthread = blockIdx.x * kThreads + tid;
+    const uint32_t rng_a = args.rng_a[gthread];
+    {
+        const uint64_t x = args.rng_x[gthread];
+        st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(x));
+        st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(x >> 32));
+        st[kStatus * kThreads] = __uint_as_float(static_cast<uint32_t>(kDead));
+        st[kScatters * kThreads] = __uint_as_float(0xffffffffu); // no photon yet: counts as 0 flights when replaced
+        reinterpret_cast<uint32_t *>(smem + lay.off_nseg)[tid] = 0u;
+        if (lane == 0) {
+            uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+            wctl[kWLeft] = 0u; wctl[kWStepIndex] = 0xffffffffu; wctl[kWMore] = 1u; wctl[kWQueued] = 0u; wctl[kWCreated] = 0u;
+        }
     }
     __syncthreads();
 
-    float *start0 = sp.start + tid;                          // + word*kThreads (+ kStartWords*kThreads for buffer 1)
-    float *spare = sp.spare + tid;
-    uint32_t *wstep = sp.warp_step + warp * 12;
-
-    const uint32_t gthread = blockIdx.x * kThreads + tid;
-    Mwc rng{args.rng_x[gthread], args.rng_a[gthread]};
-
-    // warp-uniform state
-    uint32_t w_step_index = 0xffffffffu;
-    uint32_t w_left = 0;         // photons of the warp's step not yet handed to a lane
-    bool w_more = true;          // the global queue may still have steps
-    V3 w_axis{0.f, 0.f, 1.f};
-    unsigned spare_mask = 0;     // lanes whose mailbox holds a photon
-
-    // lane state
-    bool alive = false;
-    int cur = 0;                 // which start buffer holds the photon in flight
-    V3 pos{0.f, 0.f, 0.f}, dir{0.f, 0.f, 1.f};
-    float abs_left = 0.f, path = 0.f;
-    float f_scat = 0.f, f_dust = 0.f, f_pure = 0.f;
-    uint32_t scatters = 0;
-    int layer = 0;
-    unsigned long long n_created = 0, n_segments = 0;
-    // RNG bookkeeping for single-photon replay by a checker (save-all variants only; dead code
-    // otherwise).  A lane's stream serves, in this order: creation of a photon (x_create), later
-    // its propagation from x_pop, interrupted at most once -- after `interrupt_at` scatters -- by
-    // the creation of the lane's next spare, after which it resumes from x_resume.
-    uint64_t spare_tag_create = 0, cur_tag_create = 0, cur_tag_pop = 0, cur_tag_resume = 0;
-    uint32_t cur_interrupt_at = 0xffffffffu;
-
-    const float inv_h = m.inv_h;
-    const float inv_fsl = (m.f_sl > 0.f) ? 1.f / m.f_sl : 0.f;
-    const float inv_omf = (m.one_minus_f_sl > 0.f) ? 1.f / m.one_minus_f_sl : 0.f;
-    const float inv_2g = 1.f / (2.f * m.g);
-
     for (;;) {
-        // One vote per iteration; everything else on the control path runs only when a lane is dead.
-        unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
-        if (alive_mask != 0xffffffffu) {
-            // ---------------------------------------------------------- refill (converged)
-            const bool work = w_more || w_left > 0;
-            if (work && (__popc(~spare_mask) >= kRefillThreshold || (alive_mask | spare_mask) == 0u)) {
-                bool need = !(spare_mask & lane_bit);
-                for (;;) {
-                    const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-                    if (need_mask == 0) break;
-                    if (w_left == 0) {
-                        if (!w_more) break;
-                        // next step for this warp
-                        uint32_t idx = 0;
-                        if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
-                        idx = __shfl_sync(0xffffffffu, idx, 0);
-                        if (idx >= args.num_steps) { w_more = false; break; }
-                        __syncwarp();
-                        if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
-                        __syncwarp();
-                        w_step_index = idx;
-                        w_left = wstep[8];
-                        float st, ct, sph, cph;
-                        __sincosf(__uint_as_float(wstep[4]), &st, &ct);
-                        __sincosf(__uint_as_float(wstep[5]), &sph, &cph);
-                        w_axis.x = st * cph; w_axis.y = st * sph; w_axis.z = ct;
-                        if (w_left == 0) continue; // dummy step (quirk 11)
-                    }
-                    const int rank = __popc(need_mask & (lane_bit - 1u));
-                    const bool take = need && (static_cast<uint32_t>(rank) < w_left);
-                    if (take) {
-                        // R3: createPhotonFromTrack (propagation_kernel.c.cl:132-184)
-                        const uint64_t x_before = rng.x;
-                        const float s_x = __uint_as_float(wstep[0]), s_y = __uint_as_float(wstep[1]), s_z = __uint_as_float(wstep[2]);
-                        const float s_t = __uint_as_float(wstep[3]), s_len = __uint_as_float(wstep[6]), s_beta = __uint_as_float(wstep[7]);
-                        const uint32_t source = (wstep[11] & 0xffu);
-                        const float shift = s_len * rng.co();
-                        V3 d = w_axis;
-                        float wlen;
-                        if (scene.num_generators <= 1 || source == 0) {
-                            wlen = draw_wavelength(scene.generators[0], rng);
-                            const float cos_c = fminf(1.f, mufu_rcp(s_beta * phase_index(m, wlen)));
-                            const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
-                            rotate_by(cos_c, sin_c, d, rng.co());
-                        } else {
-                            wlen = (source < static_cast<uint32_t>(scene.num_generators)) ? draw_wavelength(scene.generators[source], rng) : 0.f;
-                        }
-                        const float life = scene.fixed_abs ? scene.fixed_abs_lens : -fast_ln(rng.oc());
-                        // the spare goes to the buffer that is not in flight
-                        float *st = start0 + (cur ^ (alive ? 1 : 0)) * (kStartWords * kThreads);
-                        st[0 * kThreads] = s_x + w_axis.x * shift;
-                        st[1 * kThreads] = s_y + w_axis.y * shift;
-                        st[2 * kThreads] = s_z + w_axis.z * shift;
-                        st[3 * kThreads] = s_t + shift * mufu_rcp(kSpeedOfLight * s_beta);
-                        st[4 * kThreads] = d.x;
-                        st[5 * kThreads] = d.y;
-                        st[6 * kThreads] = d.z;
-                        st[7 * kThreads] = wlen;
-                        st[8 * kThreads] = life;
-                        st[9 * kThreads] = __uint_as_float(w_step_index);
-                        // wavelength-only factors of R4 (…_Optimizers.cxx:123-250), once per photon
-                        const float nm = wlen * 1e9f;
-                        spare[0 * kThreads] = fast_pow(wlen * m.inv_ref_wlen, -m.alpha);                // 1/scatLen = b400 * this
-                        spare[1 * kThreads] = fast_pow(nm, -m.kappa);                                  // dust term factor
-                        spare[2 * kThreads] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
-                        need = false;
-                        if (SAVE_ALL) {
-                            spare_tag_create = x_before;
-                            if (alive) {
-                                cur_interrupt_at = scatters;
-                                cur_tag_resume = rng.x;
-                            }
-                        }
-                        ++n_created;
-                    }
-                    spare_mask |= __ballot_sync(0xffffffffu, take);
-                    const uint32_t wanted = __popc(need_mask);
-                    w_left -= min(wanted, w_left);
-                }
-            }
-
-            // ---------------------------------------------------------- pop
-            const unsigned popping = ~alive_mask & spare_mask;
-            if (popping & lane_bit) {
-                const float *st = start0 + cur * (kStartWords * kThreads);
-                pos.x = st[0 * kThreads]; pos.y = st[1 * kThreads]; pos.z = st[2 * kThreads];
-                dir.x = st[4 * kThreads]; dir.y = st[5 * kThreads]; dir.z = st[6 * kThreads];
-                abs_left = st[8 * kThreads];
-                f_scat = spare[0 * kThreads]; f_dust = spare[1 * kThreads]; f_pure = spare[2 * kThreads];
-                path = 0.f;
-                scatters = 0;
-                layer = min(max(__float2int_rz((pos.z - m.z0) * inv_h), 0), m.num_layers - 1);
-                alive = true;
-                if (SAVE_ALL) {
-                    cur_tag_create = spare_tag_create;
-                    cur_tag_pop = rng.x;
-                    cur_interrupt_at = 0xffffffffu;
-                }
-            }
-            spare_mask &= ~popping;
-            alive_mask |= popping;
-            if (alive_mask == 0u) {
-                if (!w_more && w_left == 0) break; // nothing in flight, nothing spare, nothing to fetch
-                continue;
-            }
+        const int limit = slow_phase<TILT, ANISO, SAVE_ALL>(args.scene_dev);
+        if (limit < 0) break;
+        // ---- fast phase: photon state in registers, no calls
+        Lane L;
+        load_lane<TILT, ANISO>(L, st);
+        for (;;) {
+            const unsigned idle = __ballot_sync(0xffffffffu, L.status != kActive);
+            if (__popc(idle) >= limit) break;
+            if (L.status == kActive)
+                advance_photon<TILT, ANISO, SAVE_ALL, false>(L, scene, nullptr, sp.layers, sp.strings, sp.near, rng_a, nullptr);
         }
-
-        if (alive) {
-            // -------------------------------------------------------------- R5: segment length
-            float z_eff = pos.z;
-            if (TILT) {
-                z_eff = pos.z - tilt_shift(m, pos.x, pos.y, pos.z);
-                layer = min(max(__float2int_rz((z_eff - m.z0) * inv_h), 0), m.num_layers - 1);
-            }
-            float inv_aniso = 1.f;
-            if (ANISO) {
-                // R4b: 1/f = (B2-nB)*An/2 (I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx:92-134)
-                const float n0 = m.azx * dir.x + m.azy * dir.y, n1 = m.neg_azy * dir.x + m.azx * dir.y;
-                const float s0 = n0 * n0, s1 = n1 * n1, s2 = dir.z * dir.z;
-                const float nB = s0 * m.rl[0] + s1 * m.rl[1] + s2 * m.rl[2];
-                const float An = s0 * m.l[0] + s1 * m.l[1] + s2 * m.l[2];
-                inv_aniso = (m.B2 - nB) * An * 0.5f;
-                abs_left *= mufu_rcp(inv_aniso);
-            }
-            const float dz = dir.z;
-            const float sca_left = -fast_ln(rng.oc());
-            float4 c = sp.layers[layer];
-            float b = c.x * f_scat;                       // 1/scattering length
-            float a = c.y * f_dust + c.z * f_pure;        // 1/absorption length
-            float boundary = m.z0 + m.h * static_cast<float>(layer + ((dz < 0.f) ? 0 : 1));
-            float ais = (dz * sca_left - (boundary - z_eff) * b) * inv_h;
-            float aia = (dz * abs_left - (boundary - z_eff) * a) * inv_h;
-            int j = layer;
-            if (dz < 0.f) {
-                while ((j > 0) && (ais < 0.f) && (aia < 0.f)) {
-                    --j;
-                    boundary -= m.h;
-                    c = sp.layers[j];
-                    b = c.x * f_scat;
-                    a = c.y * f_dust + c.z * f_pure;
-                    ais += b;
-                    aia += a;
-                }
-            } else {
-                while ((j < m.num_layers - 1) && (ais > 0.f) && (aia > 0.f)) {
-                    ++j;
-                    boundary += m.h;
-                    c = sp.layers[j];
-                    b = c.x * f_scat;
-                    a = c.y * f_dust + c.z * f_pure;
-                    ais -= b;
-                    aia -= a;
-                }
-            }
-            float travel;
-            if ((j == layer) || (fabsf(dz) < kEpsilon)) {
-                // same layer: d_scatter = sca_left/b, d_absorb = abs_left/a; one reciprocal
-                const bool absorbed = abs_left * b < sca_left * a;
-                travel = (absorbed ? abs_left : sca_left) * mufu_rcp(absorbed ? a : b);
-                abs_left = absorbed ? 0.f : abs_left - travel * a;
-            } else {
-                const float inv_dz = mufu_rcp(dz);
-                const float base = boundary - z_eff;
-                const float d_scatter = (ais * m.h * mufu_rcp(b) + base) * inv_dz;
-                const float d_absorb = (aia * m.h * mufu_rcp(a) + base) * inv_dz;
-                if (d_absorb < d_scatter) {
-                    travel = d_absorb;
-                    abs_left = 0.f;
-                } else {
-                    travel = d_scatter;
-                    abs_left = (d_absorb - d_scatter) * a;
-                }
-            }
-            if (!TILT) layer = j;
-            if (ANISO) abs_left *= inv_aniso;
-            ++n_segments;
-
-            // -------------------------------------------------------------- R6: DOM collision
-            Collision col{travel, 0, 0, false};
-            if (!SAVE_ALL) {
-                // distance-field early out: can this segment reach any string at all?
-                const int px = min(max(__float2int_rz((pos.x - geo.near_x0) * geo.near_inv_pixel), 0), geo.near_nx - 1);
-                const int py = min(max(__float2int_rz((pos.y - geo.near_y0) * geo.near_inv_pixel), 0), geo.near_ny - 1);
-                const int pixel = py * geo.near_nx + px;
-                const float reach = travel + geo.string_max_radius;
-                if (reach >= static_cast<float>(sp.near_d1[pixel])) {
-                    const float dir_xy2 = dir.x * dir.x + dir.y * dir.y;
-                    if (dir_xy2 > 0.f) {
-                        const float inv_xy2 = mufu_rcp(dir_xy2);
-                        const uint32_t info = __ldg(geo.near_info + pixel);
-                        if (reach < static_cast<float>((info >> 16) & 0xffu)) {
-                            test_string(sp, geo, static_cast<int>(info & 0xffffu), pos, dir, inv_xy2, scene.inv_pancake_factor, col);
-                        } else {
-                            cell_walk(sp, geo, lay, pos, dir, inv_xy2, scene.inv_pancake_factor, col);
-                        }
-                    }
-                }
-            }
-            bool emit = false;
-            float emit_dist_abs = 0.f;
-            if (col.hit) {
-                // distInAbsLens is taken for the unshortened segment (propagation_kernel.c.cl:718)
-                emit = true;
-                emit_dist_abs = life_of_current(start0, cur) - abs_left;
-                abs_left = 0.f;
-            }
-            travel = col.travel;
-
-            // -------------------------------------------------------------- advance
-            pos.x += dir.x * travel;
-            pos.y += dir.y * travel;
-            pos.z += dir.z * travel;
-            path += travel;
-
-            if (abs_left < kEpsilon) {
-                alive = false;
-                if (SAVE_ALL) {
-                    // propagation_kernel.c.cl:800-826
-                    if (rng.co() < scene.prescale) {
-                        emit = true;
-                        emit_dist_abs = life_of_current(start0, cur);
-                    }
-                }
-                if (emit)
-                    emit_record(scene, args, start0 + cur * (kStartWords * kThreads), pos, dir, path, scatters, col.string, col.dom,
-                                emit_dist_abs, SAVE_ALL, cur_tag_create, cur_tag_pop, cur_tag_resume, cur_interrupt_at, rng.a);
-                cur ^= 1; // the spare (if any) sits in the other buffer
-            } else {
-                // ---------------------------------------------------------- R9 + R8: scatter
-                if (ANISO) apply_matrix(m.pre, dir);
-                const float rr = rng.co();
-                float cs;
-                if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
-                    // both samplers are evaluated and one is selected: no divergent branch
-                    const float cos_sl = 2.f * fast_pow(rr * inv_fsl, m.sl_beta) - 1.f;
-                    const float s = 2.f * ((1.f - rr) * inv_omf) - 1.f;
-                    const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-                    const float cos_hg = (1.f + m.g2 - ii * ii) * inv_2g;
-                    cs = (rr < m.f_sl) ? cos_sl : cos_hg;
-                } else if (m.scat_kind == CLSIMCU_SCAT_HG) {
-                    const float s = 2.f * rr - 1.f;
-                    const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-                    cs = (1.f + m.g2 - ii * ii) * inv_2g;
-                } else {
-                    cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
-                }
-                cs = fminf(fmaxf(cs, -1.f), 1.f);
-                const float sn = mufu_sqrt(1.f - cs * cs);
-                rotate_by(cs, sn, dir, rng.co());
-                if (ANISO) apply_matrix(m.post, dir);
-                ++scatters;
-            }
-        }
+        store_lane<TILT, ANISO>(L, st);
+        __syncwarp();
     }
 
-    args.rng_x[gthread] = rng.x;
+    args.rng_x[gthread] = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
     if (args.count_stats) {
-        // warp-level reduction, one atomic per warp
-        for (int o = 16; o > 0; o >>= 1) {
-            n_created += __shfl_down_sync(0xffffffffu, n_created, o);
-            n_segments += __shfl_down_sync(0xffffffffu, n_segments, o);
-        }
+        // warp-level reduction, one atomic per warp; the lane's last photon has not been counted yet
+        unsigned long long segs = reinterpret_cast<uint32_t *>(smem + lay.off_nseg)[tid] + (__float_as_uint(st[kScatters * kThreads]) + 1u);
+        for (int o = 16; o > 0; o >>= 1) segs += __shfl_down_sync(0xffffffffu, segs, o);
         if (lane == 0) {
-            atomicAdd(args.stats + 0, n_created);
-            atomicAdd(args.stats + 1, n_segments);
+            const uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+            atomicAdd(args.stats + 0, static_cast<unsigned long long>(wctl[kWCreated]));
+            atomicAdd(args.stats + 1, segs);
         }
     }
 }
@@ -739,7 +976,7 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
     auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -3;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)) != cudaSuccess) return -3;
         configured = true;
     }
     kernel<<<blocks, kThreads, lay.total, stream>>>(scene, args, lay);
@@ -757,8 +994,16 @@ bool fast_kernel_supports(const DevScene &scene, const char **why)
     if (scene.history_entries > 0) { *why = k_history; return false; }
     if (!scene.save_all && !scene.stop_detected) { *why = k_nonstop; return false; }
     if (scene.medium.anisotropy && (!scene.medium.pre_renorm || !scene.medium.post_renorm)) { *why = k_renorm; return false; }
-    if (plan_smem(scene).total > 200u * 1024u / kBlocksPerSM) { *why = k_smem; return false; }
+    if (plan_smem(scene).total + 1024u > kSmemBudget / kBlocksPerSM) { *why = k_smem; return false; }
     return true;
+}
+
+bool fast_kernel_smem_is_the_problem(const DevScene &scene)
+{
+    DevScene probe = scene;
+    probe.geo.near_nx = probe.geo.near_ny = 0;
+    const char *why = nullptr;
+    return fast_kernel_supports(probe, &why) && !fast_kernel_supports(scene, &why);
 }
 
 void fast_kernel_geometry(int device, int *grid_blocks, int *threads_per_block)

@@ -8,9 +8,9 @@ host-side merge keyed by the bunch identifier.
 """
 import numpy as np
 
-# Rows of the multiplier table reserved per device: >= resident threads of the fast kernel
-# (148 SMs x 4 CTAs x 256 threads = 151 552 on B200).
-RNG_ROWS_PER_DEVICE = 163840
+# Rows of the multiplier table reserved per device: >= 2 streams (creation, propagation) per
+# resident thread of the fast kernel (148 SMs x 1024 threads x 2 = 303 104 on B200).
+RNG_ROWS_PER_DEVICE = 327680
 
 
 def rng_row_offset(rank):

@@ -279,17 +279,12 @@ int clsimcu_describe_tables_from_config(const clsimcu_config *config, char *buf,
  * rows [first, first+n) of the descending sequence that starts at 4294967118. */
 int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
 
-/* In SAVE_ALL mode with kernel FAST: per saved photon i the pieces of its lane's MWC
- * stream that it consumed, so a CPU checker can replay single photons:
- *   x[3*i]   state before the photon was created (the fast kernel creates photons ahead
- *            of time, so creation and propagation draws are not contiguous),
- *   x[3*i+1] state when its propagation started,
- *   x[3*i+2] state after the one possible interruption of its propagation by the creation
- *            of the lane's next photon, which happened after a[2*i+1] scatters
- *            (0xffffffff = not interrupted),
- *   a[2*i]   the stream's multiplier.
- * Parallel to the last result of clsimcu_download_resident; x has room for 3*cap and a
- * for 2*cap entries. */
+/* In SAVE_ALL mode with kernel FAST: per saved photon i the two MWC stream states it was made
+ * from, so a CPU checker can replay single photons.  The fast kernel keeps two streams per
+ * lane, one for photon creation and one for propagation:
+ *   x[2*i]   state of the creation stream before the photon was created,   a[2*i]   its multiplier,
+ *   x[2*i+1] state of the propagation stream when the photon started,      a[2*i+1] its multiplier.
+ * Parallel to the last result of clsimcu_download_resident; x and a have room for 2*cap entries. */
 int clsimcu_download_resident_rng_tags(clsimcu_engine *engine, uint64_t *x, uint32_t *a, size_t cap);
 
 const char *clsimcu_last_error(void);

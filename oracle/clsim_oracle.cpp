@@ -1174,8 +1174,7 @@ struct WorkItemStats {
 // One work-item of propKernel (propagation_kernel.c.cl:406-913).  max_photons limits the
 // photons taken from the step (single-photon replay uses 1).
 void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, HitSink &sink, WorkItemStats &st,
-                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr,
-                   uint32_t interruptAtScatters = 0xffffffffu, uint64_t xResume = 0)
+                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr, uint32_t aAfterCreation = 0)
 {
     const Medium &m = sc.med;
     Vec4 stepDir;
@@ -1206,16 +1205,16 @@ void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, Hi
             if (sc.fixedAbs) ph.absLensInitial = sc.fixedAbsLens;
             else ph.absLensInitial = -std::log(rand_oc(rng));
             abs_lens_left = ph.absLensInitial;
-            // replay of a photon whose creation and propagation draws are not contiguous in its stream
-            if (xAfterCreation) rng.x = *xAfterCreation;
+            // replay of a photon that was created from one stream and propagated from another
+            // (the B200 fast kernel keeps a creation stream and a propagation stream per lane)
+            if (xAfterCreation) {
+                rng.x = *xAfterCreation;
+                rng.a = aAfterCreation;
+            }
             ++st.photons;
             if (traj) traj->record(ph, abs_lens_left);
         }
 
-        if (xAfterCreation && ph.numScatters == interruptAtScatters) {
-            rng.x = xResume; // replay: the stream was used for something else at this point
-            interruptAtScatters = 0xffffffffu;
-        }
         float distancePropagated;
         {
             float effective_z;
@@ -1534,17 +1533,17 @@ int oracle_propagate_single_photon(const oracle_scene *scene, const oracle_step 
     return sink.count > 0 ? 1 : 0;
 }
 
-int oracle_propagate_single_photon_split(const oracle_scene *scene, const oracle_step *step, uint64_t x_create, uint64_t x_propagate,
-                                         uint32_t interrupt_at_scatters, uint64_t x_resume,
-                                         uint32_t a, oracle_photon *out, float *traj, int max_points, int *num_points)
+int oracle_propagate_single_photon_split(const oracle_scene *scene, const oracle_step *step, uint64_t x_create, uint32_t a_create,
+                                         uint64_t x_propagate, uint32_t a_propagate, oracle_photon *out, float *traj, int max_points,
+                                         int *num_points)
 {
-    Rng rng{x_create, a, 0};
+    Rng rng{x_create, a_create, 0};
     oracle_photon tmp[4];
     HitSink sink{tmp, 4, nullptr, 0, {}, {}, false};
     if (scene->history > 0) { sink.useLocal = true; }
     WorkItemStats st;
     TrajSink ts{traj, max_points, 0};
-    run_work_item(*scene, *step, rng, sink, st, 1, &ts, &x_propagate, interrupt_at_scatters, x_resume);
+    run_work_item(*scene, *step, rng, sink, st, 1, &ts, &x_propagate, a_propagate);
     if (num_points) *num_points = ts.n;
     if (sink.count > 0 && out) *out = sink.useLocal ? sink.local[0] : tmp[0];
     return sink.count > 0 ? 1 : 0;

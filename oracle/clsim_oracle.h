@@ -165,13 +165,11 @@ int oracle_propagate_single_photon(const oracle_scene *scene, const oracle_step 
                                    uint64_t *x, uint32_t a, oracle_photon *out,
                                    float *traj, int max_points, int *num_points);
 
-/* Same, for a photon whose creation draws start at x_create, whose propagation draws start
- * at x_propagate and continue from x_resume once it has scattered interrupt_at_scatters times
- * (0xffffffff: never).  The B200 fast kernel creates photons ahead of time on the same lane
- * stream, so a photon's draws are not contiguous. */
+/* Same, for a photon whose creation draws come from the stream (x_create, a_create) and whose
+ * propagation draws come from the stream (x_propagate, a_propagate): the B200 fast kernel keeps
+ * two MWC streams per lane, one for photon creation and one for propagation. */
 int oracle_propagate_single_photon_split(const oracle_scene *scene, const oracle_step *step,
-                                         uint64_t x_create, uint64_t x_propagate,
-                                         uint32_t interrupt_at_scatters, uint64_t x_resume, uint32_t a,
+                                         uint64_t x_create, uint32_t a_create, uint64_t x_propagate, uint32_t a_propagate,
                                          oracle_photon *out, float *traj, int max_points, int *num_points);
 
 /* MWC RNG (mwcrng_kernel.cl:12-28): n draws of [0,1) from (*x, a). */

@@ -37,7 +37,7 @@ def lib():
         L.oracle_propagate_single_photon.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p,
                                                      C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.oracle_propagate_single_photon_split.restype = C.c_int
-        L.oracle_propagate_single_photon_split.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32,
+        L.oracle_propagate_single_photon_split.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32,
                                                            C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.oracle_rng_uniform_co.argtypes = [C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_size_t]
         L.oracle_safeprimes.restype = C.c_int
@@ -125,11 +125,11 @@ class Scene(object):
                                                      traj.ctypes.data if max_points else None, max_points, C.byref(npts))
         return bool(saved), out[0], traj[:min(npts.value, max_points)], xs.value, npts.value
 
-    def single_photon_split(self, step, x_create, x_propagate, interrupt_at, x_resume, a):
+    def single_photon_split(self, step, x_create, a_create, x_propagate, a_propagate):
         step = np.ascontiguousarray(step, dtype=STEP_DTYPE).reshape(1)
         out = np.zeros(1, dtype=PHOTON_DTYPE)
         npts = C.c_int(0)
-        saved = lib().oracle_propagate_single_photon_split(self._h, step.ctypes.data, int(x_create), int(x_propagate), int(interrupt_at), int(x_resume), int(a),
+        saved = lib().oracle_propagate_single_photon_split(self._h, step.ctypes.data, int(x_create), int(a_create), int(x_propagate), int(a_propagate),
                                                            out.ctypes.data, None, 0, C.byref(npts))
         return bool(saved), out[0]
 

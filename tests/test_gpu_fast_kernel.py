@@ -44,7 +44,7 @@ def test_replay_parity_per_photon(name):
     worst = 0.0
     for i, p in enumerate(photons):
         s = int(p["identifier"])  # identifier == step index in this test
-        saved, q = osc.single_photon_split(bunch[s], tags_x[i, 0], tags_x[i, 1], tags_a[i, 1], tags_x[i, 2], tags_a[i, 0])
+        saved, q = osc.single_photon_split(bunch[s], tags_x[i, 0], tags_a[i, 0], tags_x[i, 1], tags_a[i, 1])
         assert saved
         # creation is reproduced (same stream, same draws): start point and wavelength agree tightly
         assert abs(q["start_x"] - p["start_x"]) < 1e-3 and abs(q["start_z"] - p["start_z"]) < 1e-3

@@ -76,7 +76,7 @@ def test_two_ranks_shard_and_merge(tmp_path):
 
 def test_sharding_helpers():
     assert rng_row_offset(0) == 0 and rng_row_offset(3) == 3 * RNG_ROWS_PER_DEVICE
-    assert RNG_ROWS_PER_DEVICE >= 148 * 4 * 256
+    assert RNG_ROWS_PER_DEVICE >= 2 * 148 * 1024
     assert shard_bunches(7, 1, 3) == [1, 4]
     s = steps.muon_track_steps(1000, seed=1)
     parts = split_steps(s, 4, granularity=64)

@@ -20,7 +20,7 @@ osc = pyoracle.Scene(sc.medium, None, sc.generators, sc.bias, opt)
 rows = []
 for i, p in enumerate(photons):
     s = int(p["identifier"])
-    saved, q = osc.single_photon_split(bunch[s], tags_x[i, 0], tags_x[i, 1], tags_a[i, 1], tags_x[i, 2], tags_a[i, 0])
+    saved, q = osc.single_photon_split(bunch[s], tags_x[i, 0], tags_a[i, 0], tags_x[i, 1], tags_a[i, 1])
     dev = max(abs(float(q[k]) - float(p[k])) for k in ("x", "y", "z"))
     rows.append((int(q["num_scatters"]), int(p["num_scatters"]), dev, float(q["cherenkov_dist"]), float(p["cherenkov_dist"]),
                  float(q["dist_in_abs_lens"]), float(p["dist_in_abs_lens"]), float(q["t"]), float(p["t"]), float(q["z"]), float(p["z"])))
