@@ -73,6 +73,7 @@ struct DevGeometry {
     // non-expansive and every string lies inside it).
     int near_nx, near_ny;
     float near_x0, near_y0, near_inv_pixel;
+    float near_off_x, near_off_y; // -near_x0 * near_inv_pixel, -near_y0 * near_inv_pixel
     const uint32_t *near_info;
     // index -> ID rewrite on the device (…ConverterOpenCL.cxx:1565-1602 does it on the host)
     const int16_t *string_index_to_id;

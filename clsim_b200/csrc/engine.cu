@@ -329,6 +329,8 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
             dg.near_x0 = xlo - pixel;
             dg.near_y0 = ylo - pixel;
             dg.near_inv_pixel = 1.f / pixel;
+            dg.near_off_x = -dg.near_x0 * dg.near_inv_pixel;
+            dg.near_off_y = -dg.near_y0 * dg.near_inv_pixel;
             dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * pixel) / pixel));
             dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * pixel) / pixel));
             const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-2; // + slack for fp32 pixel assignment

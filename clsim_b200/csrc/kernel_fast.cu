@@ -54,10 +54,10 @@ namespace clsimcu {
 namespace {
 
 #ifndef CLSIMCU_THREADS
-#define CLSIMCU_THREADS 256
+#define CLSIMCU_THREADS 1024
 #endif
 #ifndef CLSIMCU_BLOCKS_PER_SM
-#define CLSIMCU_BLOCKS_PER_SM 3
+#define CLSIMCU_BLOCKS_PER_SM 1
 #endif
 #ifndef CLSIMCU_IDLE_LIMIT
 #define CLSIMCU_IDLE_LIMIT 8
@@ -79,15 +79,23 @@ constexpr int kQueueWords = 16; // [10] scattering factor [11] dust factor [12] 
 // per-lane running state, parked in shared memory between fast phases
 enum StateWord {
     kPx = 0, kPy, kPz, kDx, kDy, kDz, kAbsLeft, kScaLeft, kPath, kFScat, kFDust, kFPure, kScatters, kLayer, kStatus, kRngLo, kRngHi,
-    kZEff, kInvAniso, kStateWords
+    kZEff, kInvAniso, kPendTravel, kPendWho, kStateWords
 };
 // per-lane replay tags of the photon in flight (save-all variants only)
 constexpr int kTagWords = 5; // x_create lo, hi, a_create, x_pop lo, hi
 // per-warp control block
 enum WarpCtl { kWLeft = 0, kWStepIndex, kWMore, kWQueued, kWCreated, kWarpCtlWords = 8 };
 constexpr int kWarpStepWords = 16; // the warp's step record (12 words) + its direction (3)
+// compile-time offsets (in words) inside the per-thread and per-warp regions of shared memory
+constexpr int kOffCStart = kStateWords * kThreads;
+constexpr int kOffNSeg = kOffCStart + kStartWords * kThreads;
+constexpr int kOffTags = kOffNSeg + kThreads;
+constexpr int kPerThreadWords = kStateWords + kStartWords + 1;
+constexpr int kOffWarpStep = kWarpsPerBlock * kQueueWords * 32;
+constexpr int kOffWarpCtl = kOffWarpStep + kWarpsPerBlock * kWarpStepWords;
 
-enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3 };
+// kCleared = active, and the collision test of the segment it is about to fly has already come back negative
+enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3, kCleared = 4 };
 
 // ---- approximate MUFU wrappers ---------------------------------------------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -122,8 +130,9 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 
 // Shared-memory plan, carved out of the dynamic allocation.
 struct SmemLayout {
-    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near;
-    uint32_t off_state, off_cstart, off_queue, off_nseg, off_tags, off_warp_step, off_warp_ctl;
+    uint32_t off_layers, off_bounds, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near;
+    uint32_t off_state;   // per-thread arrays: state | start-of-flight record | segment counter | replay tags (save-all only)
+    uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
     uint32_t cell_offset[kMaxSubdetectors];
     uint32_t total;
 };
@@ -137,6 +146,7 @@ struct SmemHeader {
 
 struct SmemPlan {
     float4 *layers;          // [num_layers] (b400, D*aDust+E, 1+0.01*dTau, 0)
+    float2 *bounds;          // [num_layers] (lower, upper) boundary z; -/+1e30 where there is no layer beyond
     float4 *strings;         // [num_strings] (x, y, zmax+R, zmin-R)
     float4 *sets;            // [num_sets] (start_z, 1/height, num_layers, row offset)
     uint8_t *string_set;     // [num_strings]
@@ -152,6 +162,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     SmemLayout L{};
     uint32_t at = align16(sizeof(SmemHeader));
     L.off_layers = at; at = align16(at + s.medium.num_layers * 16);
+    L.off_bounds = at; at = align16(at + s.medium.num_layers * 8);
     L.off_strings = at; at = align16(at + s.geo.num_strings * 16);
     L.off_sets = at; at = align16(at + s.geo.num_sets * 16);
     L.off_string_set = at; at = align16(at + s.geo.num_strings);
@@ -164,13 +175,8 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     }
     at = align16(at + cells * 2);
     L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
-    L.off_state = at; at = align16(at + kStateWords * kThreads * 4);
-    L.off_cstart = at; at = align16(at + kStartWords * kThreads * 4);
-    L.off_queue = at; at = align16(at + kWarpsPerBlock * kQueueWords * 32 * 4);
-    L.off_nseg = at; at = align16(at + kThreads * 4);
-    L.off_tags = at; at = align16(at + (s.save_all ? kTagWords * kThreads * 4 : 0));
-    L.off_warp_step = at; at = align16(at + kWarpsPerBlock * kWarpStepWords * 4);
-    L.off_warp_ctl = at; at = align16(at + kWarpsPerBlock * kWarpCtlWords * 4);
+    L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kTagWords : 0)) * kThreads * 4);
+    L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
     L.total = at;
     return L;
 }
@@ -186,6 +192,7 @@ __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
     uint8_t *smem = smem_base();
     SmemPlan sp;
     sp.layers = reinterpret_cast<float4 *>(smem + lay.off_layers);
+    sp.bounds = reinterpret_cast<float2 *>(smem + lay.off_bounds);
     sp.strings = reinterpret_cast<float4 *>(smem + lay.off_strings);
     sp.sets = reinterpret_cast<float4 *>(smem + lay.off_sets);
     sp.string_set = smem + lay.off_string_set;
@@ -585,26 +592,80 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(cons
     if (ANISO) st[kInvAniso * kThreads] = L.inv_aniso;
 }
 
-// One iteration: move the photon to its next event.  RESOLVE = false is the hot loop: a segment
-// that might touch a DOM parks the lane (status kFrozen) with nothing but the scattering-length
-// draw applied.  RESOLVE = true (slow phase) runs the same arithmetic again for such a lane,
-// this time with the full collision test and the hit output.  `scene_dev`/`cstart` are only
-// used by RESOLVE.
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool RESOLVE>
-__device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
-                                               const float4 *strings, const uint32_t *near, uint32_t rng_a, const float *cstart)
+// The part of an iteration that decides where the photon goes next: the event that ends this leg
+// of the flight (scatter / absorption inside the current ice layer, the layer boundary, or the
+// range limit of the collision map) and what is left of the two budgets afterwards.
+struct Leg {
+    float a, b;               // 1/absorption length, 1/scattering length in the current layer
+    float zb, zc;             // boundary ahead, current z (both in the layer frame)
+    float travel;
+    float rem_abs, rem_sca;   // budgets left at the end of the leg
+    float ox, oy;             // from the photon to the axis of the nearest string (xy)
+    int who;                  // that string
+    bool up, absorbed, limited, cross, walk;
+};
+
+template <bool TILT, bool SAVE_ALL>
+__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float2 *bounds,
+                                        const float4 *strings, const uint32_t *near)
+{
+    const DevGeometry &geo = scene.geo;
+    Leg g;
+    const float4 c = layers[L.layer];
+    const float2 zz = bounds[L.layer];
+    g.b = c.x * L.f_scat;
+    g.a = fmaf(c.y, L.f_dust, c.z * L.f_pure);
+    g.up = !(L.dir.z < 0.f);
+    g.zb = g.up ? zz.y : zz.x;                               // +-1e30 when there is no layer beyond
+    g.zc = TILT ? L.z_eff : L.pos.z;
+    const float d_b = fmaxf((g.zb - g.zc) * L.inv_dz, 0.f);
+    g.absorbed = L.abs_left * g.b < L.sca_left * g.a;        // d_absorb < d_scatter inside this layer
+    const float d_sa = (g.absorbed ? L.abs_left : L.sca_left) * mufu_rcp(g.absorbed ? g.a : g.b);
+    // pixel map: nearest string and the range within which no other string can be touched
+    g.who = -1;
+    float cap = __int_as_float(0x7f800000);
+    g.ox = g.oy = 0.f;
+    g.walk = false;
+    if (!SAVE_ALL) {
+        // (float -> unsigned conversion saturates below at 0)
+        const uint32_t px = min(__float2uint_rz(fmaf(L.pos.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
+        const uint32_t py = min(__float2uint_rz(fmaf(L.pos.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
+        const uint32_t cell = near[py * geo.near_nx + px];
+        g.who = static_cast<int>(cell & 0xffffu);
+        const float range = __uint_as_float(cell & 0xffff0000u);
+        g.walk = !(range > 0.f);        // strings too dense here for the map: no range limit, cell walk instead
+        if (!g.walk) cap = range;
+        const float2 sxy = *reinterpret_cast<const float2 *>(strings + g.who);
+        g.ox = sxy.x - L.pos.x;
+        g.oy = sxy.y - L.pos.y;
+    }
+    const float d_geo = fminf(d_b, cap);
+    g.limited = d_geo < d_sa;                                // the flight goes on after this leg
+    g.cross = g.limited && (d_b <= cap);
+    g.travel = g.limited ? d_geo : d_sa;
+    g.rem_abs = fmaf(-g.travel, g.a, L.abs_left);
+    g.rem_sca = fmaxf(fmaf(-g.travel, g.b, L.sca_left), 1e-30f);
+    return g;
+}
+
+// One iteration of the hot loop: move the photon to its next event.  A leg that might touch a DOM
+// parks the lane (status kFrozen, the leg's length and string in the state words kPend*) with
+// nothing but the scattering-length draw applied; the slow phase runs the full collision test
+// and either ends the photon there or sends the lane back with status kCleared, which lets
+// exactly this leg through.
+template <bool TILT, bool ANISO, bool SAVE_ALL>
+__device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const float4 *layers, const float2 *bounds,
+                                               const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st)
 {
     const DevMedium &m = scene.medium;
-    const DevGeometry &geo = scene.geo;
     Mwc rng{L.rng_x, rng_a};
-    const int top_layer = m.num_layers - 1;
 
     // ------------------------------------------------------------------ R5: next event of the flight
     if (L.sca_left <= 0.f) {
         // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
             L.z_eff = L.pos.z - tilt_shift(m, L.pos.x, L.pos.y, L.pos.z);
-            L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), top_layer);
+            L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
         }
         if (ANISO) {
             // R4b: 1/f = (B2-nB)*An/2 (I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx:92-134)
@@ -618,148 +679,122 @@ __device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, c
         L.sca_left = -fast_ln(rng.oc());
         L.rng_x = rng.x;
     }
-    const float4 c = layers[L.layer];
-    const float b = c.x * L.f_scat;                          // 1/scattering length
-    const float a = fmaf(c.y, L.f_dust, c.z * L.f_pure);     // 1/absorption length
-    const bool up = !(L.dir.z < 0.f);
-    const float zb = fmaf(m.h, static_cast<float>(L.layer + (up ? 1 : 0)), m.z0);
-    const float zc = TILT ? L.z_eff : L.pos.z;
-    const float d_b = fmaxf((zb - zc) * L.inv_dz, 0.f);
-    const bool can_cross = up ? (L.layer < top_layer) : (L.layer > 0);
-    const bool absorbed = L.abs_left * b < L.sca_left * a;   // d_absorb < d_scatter inside this layer
-    const float d_sa = (absorbed ? L.abs_left : L.sca_left) * mufu_rcp(absorbed ? a : b);
+    const Leg g = plan_leg<TILT, SAVE_ALL>(L, scene, layers, bounds, strings, near);
 
     // ------------------------------------------------------------------ R6: DOM collision, cheap part
-    // pixel map: nearest string and the range within which no other string can be touched
-    int who = -1;
-    float cap = __int_as_float(0x7f800000);
-    float ox = 0.f, oy = 0.f;
-    bool walk = false;
-    if (!SAVE_ALL) {
-        const int px = min(max(__float2int_rz((L.pos.x - geo.near_x0) * geo.near_inv_pixel), 0), geo.near_nx - 1);
-        const int py = min(max(__float2int_rz((L.pos.y - geo.near_y0) * geo.near_inv_pixel), 0), geo.near_ny - 1);
-        const uint32_t cell = near[py * geo.near_nx + px];
-        who = static_cast<int>(cell & 0xffffu);
-        const float range = __uint_as_float(cell & 0xffff0000u);
-        walk = !(range > 0.f);          // strings too dense here for the map: no range limit, cell walk instead
-        if (!walk) cap = range;
-        const float2 sxy = *reinterpret_cast<const float2 *>(strings + who);
-        ox = sxy.x - L.pos.x;
-        oy = sxy.y - L.pos.y;
-    }
-    const float d_geo = can_cross ? fminf(d_b, cap) : cap;
-    const bool limited = d_geo < d_sa;                       // the flight goes on after this iteration
-    const bool cross = limited && can_cross && (d_b <= cap);
-    float travel = limited ? d_geo : d_sa;
-    const float rem_abs = fmaf(-travel, a, L.abs_left);
-    const float rem_sca = fmaxf(fmaf(-travel, b, L.sca_left), 1e-30f);
-
-    Collision col{travel, 0, 0, false};
     if (!SAVE_ALL) {
         // 2-D segment / cylinder test against the one string in range
-        const float R = geo.string_max_radius;
-        const float o2 = ox * ox + oy * oy;
-        const float t = ox * L.dir.x + oy * L.dir.y;
+        const float R = scene.geo.string_max_radius;
+        const float o2 = g.ox * g.ox + g.oy * g.oy;
+        const float t = g.ox * L.dir.x + g.oy * L.dir.y;
         const float dxy2 = L.dir.x * L.dir.x + L.dir.y * L.dir.y;
-        const float reach = travel + R;
+        const float reach = g.travel + R;
         const float out2 = o2 - R * R;                       // > 0: the photon starts outside the cylinder
         const bool miss = (o2 > reach * reach) || ((t <= 0.f) && (out2 > 0.f)) || (out2 * dxy2 > t * t);
-        if (!miss || walk) {
-            if (!RESOLVE) {
-                L.status = kFrozen;
-                return;
-            }
-            col = collide(scene_dev, walk ? -1 : who, L.pos, L.dir, travel);
+        if ((!miss || g.walk) && !cleared) {
+            L.status = kFrozen;
+            st[kPendTravel * kThreads] = g.travel;
+            st[kPendWho * kThreads] = __int_as_float(g.walk ? -1 : g.who);
+            return;
         }
-    }
-    bool emit = false;
-    float emit_dist_abs = 0.f;
-    if (RESOLVE && col.hit) {
-        // distInAbsLens is taken for the unshortened flight (propagation_kernel.c.cl:718)
-        float at_end = absorbed ? 0.f : rem_abs;
-        if (limited)
-            at_end = abs_left_at_end_of_flight(layers, m.z0, m.h, m.num_layers, cross ? L.layer + (up ? 1 : -1) : L.layer,
-                                               cross ? zb : fmaf(L.dir.z, travel, zc), L.dir.z, L.inv_dz, rem_sca, rem_abs, L.f_scat,
-                                               L.f_dust, L.f_pure);
-        if (ANISO) at_end *= L.inv_aniso;
-        emit = true;
-        emit_dist_abs = cstart[8 * kThreads] - at_end;
-        travel = col.travel;
+        cleared = false;
     }
 
     // ------------------------------------------------------------------ advance
-    L.pos.x = fmaf(L.dir.x, travel, L.pos.x);
-    L.pos.y = fmaf(L.dir.y, travel, L.pos.y);
-    L.pos.z = fmaf(L.dir.z, travel, L.pos.z);
-    L.path += travel;
+    L.pos.x = fmaf(L.dir.x, g.travel, L.pos.x);
+    L.pos.y = fmaf(L.dir.y, g.travel, L.pos.y);
+    L.pos.z = fmaf(L.dir.z, g.travel, L.pos.z);
+    L.path += g.travel;
 
-    bool dead = RESOLVE && col.hit;
-    if (!limited) {
-        L.abs_left = absorbed ? 0.f : rem_abs;
-        if (ANISO) L.abs_left *= L.inv_aniso;
-        dead = dead || (L.abs_left < kEpsilon);
-    }
-    if (dead) {
-        L.status = SAVE_ALL ? kDying : kDead;
-        if (RESOLVE && emit)
-            emit_record(scene_dev, cstart, L.pos, L.dir, L.path, L.scatters, col.string, col.dom, emit_dist_abs, false, nullptr, rng_a);
-    } else if (limited) {
+    if (g.limited) {
         // the flight goes on (in the neighbouring layer, or past the range limit of the collision
         // map) with what is left of both budgets
-        if (cross) L.layer += up ? 1 : -1;
-        L.abs_left = rem_abs;
-        L.sca_left = rem_sca;
-        if (TILT) L.z_eff = cross ? zb : fmaf(L.dir.z, travel, L.z_eff);
-    } else {
-        // -------------------------------------------------------------- R9 + R8: scatter
-        if (ANISO) apply_matrix(m.pre, L.dir);
-        const float rr = rng.co();
-        float cs;
-        if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
-            // both samplers are evaluated and one is selected: no divergent branch
-            const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
-            const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
-            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-            const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
-            cs = (rr < m.f_sl) ? cos_sl : cos_hg;
-        } else if (m.scat_kind == CLSIMCU_SCAT_HG) {
-            const float s = 2.f * rr - 1.f;
-            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-            cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
-        } else {
-            cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
-        }
-        cs = fminf(fmaxf(cs, -1.f), 1.f);
-        const float sn = mufu_sqrt(1.f - cs * cs);
-        rotate_by(cs, sn, L.dir, rng.co());
-        if (ANISO) apply_matrix(m.post, L.dir);
-        L.inv_dz = safe_inv_dz(L.dir.z);
-        L.sca_left = 0.f;
-        ++L.scatters;
-        L.rng_x = rng.x;
+        if (g.cross) L.layer += g.up ? 1 : -1;
+        L.abs_left = g.rem_abs;
+        L.sca_left = g.rem_sca;
+        if (TILT) L.z_eff = g.cross ? g.zb : fmaf(L.dir.z, g.travel, L.z_eff);
+        return;
     }
+    L.abs_left = g.absorbed ? 0.f : g.rem_abs;
+    if (ANISO) L.abs_left *= L.inv_aniso;
+    if (L.abs_left < kEpsilon) {
+        L.status = SAVE_ALL ? kDying : kDead;
+        return;
+    }
+    // ------------------------------------------------------------------ R9 + R8: scatter
+    if (ANISO) apply_matrix(m.pre, L.dir);
+    const float rr = rng.co();
+    float cs;
+    if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
+        // both samplers are evaluated and one is selected: no divergent branch
+        const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
+        const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
+        const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+        const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
+        cs = (rr < m.f_sl) ? cos_sl : cos_hg;
+    } else if (m.scat_kind == CLSIMCU_SCAT_HG) {
+        const float s = 2.f * rr - 1.f;
+        const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+        cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
+    } else {
+        cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
+    }
+    cs = fminf(fmaxf(cs, -1.f), 1.f);
+    const float sn = mufu_sqrt(1.f - cs * cs);
+    rotate_by(cs, sn, L.dir, rng.co());
+    if (ANISO) apply_matrix(m.post, L.dir);
+    L.inv_dz = safe_inv_dz(L.dir.z);
+    L.sca_left = 0.f;
+    ++L.scatters;
+    L.rng_x = rng.x;
+}
+
+// Slow phase, for a parked lane: the reference's collision test over the pending leg.  No hit:
+// the lane goes back to the hot loop (kCleared).  Hit: the photon ends at the DOM and is
+// written out.
+template <bool TILT, bool ANISO>
+__device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, const float *cstart, uint32_t rng_a)
+{
+    const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
+    const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
+    const V3 dir{st[kDx * kThreads], st[kDy * kThreads], st[kDz * kThreads]};
+    const Collision col = collide(scene, __float_as_int(st[kPendWho * kThreads]), pos, dir, st[kPendTravel * kThreads]);
+    if (!col.hit) return kCleared;
+    // the leg again, for the budgets: distInAbsLens is taken for the unshortened flight
+    // (propagation_kernel.c.cl:718)
+    const SmemPlan sp = table_plan(lay);
+    Lane L;
+    load_lane<TILT, ANISO>(L, st);
+    const Leg g = plan_leg<TILT, false>(L, *scene, sp.layers, sp.bounds, sp.strings, sp.near);
+    float at_end = g.absorbed ? 0.f : g.rem_abs;
+    if (g.limited)
+        at_end = abs_left_at_end_of_flight(sp.layers, scene->medium.z0, scene->medium.h, scene->medium.num_layers,
+                                           g.cross ? L.layer + (g.up ? 1 : -1) : L.layer, g.cross ? g.zb : fmaf(L.dir.z, g.travel, g.zc),
+                                           L.dir.z, L.inv_dz, g.rem_sca, g.rem_abs, L.f_scat, L.f_dust, L.f_pure);
+    if (ANISO) at_end *= L.inv_aniso;
+    const V3 end{fmaf(dir.x, col.travel, pos.x), fmaf(dir.y, col.travel, pos.y), fmaf(dir.z, col.travel, pos.z)};
+    emit_record(scene, cstart, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, cstart[8 * kThreads] - at_end, false, nullptr,
+                rng_a);
+    return kDead;
 }
 
 // ---- slow phase ------------------------------------------------------------------------------
 // Runs converged, once per warp each time the hot loop has collected kIdleLimit idle lanes.
 // Returns the number of idle lanes that ends the next fast phase, or -1 when the warp is done.
-template <bool TILT, bool ANISO, bool SAVE_ALL> __device__ __noinline__ int slow_phase(const DevScene *scene)
+template <bool TILT, bool ANISO, bool SAVE_ALL>
+__device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *warp_region)
 {
-    uint8_t *smem = smem_base();
-    const SmemHeader *hdr = reinterpret_cast<const SmemHeader *>(smem);
-    const SmemLayout &lay = hdr->lay;
-    const LaunchArgs &args = hdr->args;
+    const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lane_bit = 1u << lane;
-    float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
-    float *cstart = reinterpret_cast<float *>(smem + lay.off_cstart) + tid;
-    float *queue = reinterpret_cast<float *>(smem + lay.off_queue) + warp * (kQueueWords * 32);
-    uint32_t *nseg = reinterpret_cast<uint32_t *>(smem + lay.off_nseg) + tid;
-    uint32_t *tags = SAVE_ALL ? reinterpret_cast<uint32_t *>(smem + lay.off_tags) + tid : nullptr;
-    uint32_t *wstep = reinterpret_cast<uint32_t *>(smem + lay.off_warp_step) + warp * kWarpStepWords;
-    uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+    float *cstart = st + kOffCStart;
+    uint32_t *nseg = reinterpret_cast<uint32_t *>(st + kOffNSeg);
+    uint32_t *tags = SAVE_ALL ? reinterpret_cast<uint32_t *>(st + kOffTags) : nullptr;
+    float *queue = warp_region + warp * (kQueueWords * 32);
+    uint32_t *wstep = reinterpret_cast<uint32_t *>(warp_region + kOffWarpStep) + warp * kWarpStepWords;
+    uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = __ldg(args.rng_a + gthread);
 
@@ -768,16 +803,8 @@ template <bool TILT, bool ANISO, bool SAVE_ALL> __device__ __noinline__ int slow
     __syncwarp();
     uint32_t status = __float_as_uint(st[kStatus * kThreads]);
 
-    // ---- photons whose next segment may touch a DOM: finish that segment with the full test
-    if (!SAVE_ALL && status == kFrozen) {
-        const SmemPlan sp = table_plan(lay);
-        Lane L;
-        load_lane<TILT, ANISO>(L, st);
-        L.status = kActive;
-        advance_photon<TILT, ANISO, SAVE_ALL, true>(L, *scene, scene, sp.layers, sp.strings, sp.near, rng_a, cstart);
-        store_lane<TILT, ANISO>(L, st);
-        status = L.status;
-    }
+    // ---- photons whose next leg may touch a DOM: the full collision test
+    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO>(scene, st, cstart, rng_a);
     // ---- save-all: every photon that ended is recorded with probability `prescale`
     //      (propagation_kernel.c.cl:800-826)
     if (SAVE_ALL && status == kDying) {
@@ -875,7 +902,7 @@ template <bool TILT, bool ANISO, bool SAVE_ALL> __device__ __noinline__ int slow
     }
     st[kStatus * kThreads] = __uint_as_float(status);
 
-    const int n_idle = __popc(__ballot_sync(0xffffffffu, status != kActive));
+    const int n_idle = __popc(__ballot_sync(0xffffffffu, status == kDead));
     if (lane == 0) {
         wctl[kWLeft] = w_left; wctl[kWStepIndex] = w_step_index; wctl[kWMore] = w_more ? 1u : 0u; wctl[kWQueued] = queued;
         wctl[kWCreated] = w_created;
@@ -904,7 +931,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
 
     // ---- stage the hot tables into shared memory (coalesced reads, once per CTA)
     for (int i = tid; i < m.num_layers; i += kThreads)
+    {
         sp.layers[i] = make_float4(__ldg(m.b400 + i), __ldg(m.abs_dust + i), __ldg(m.abs_tau + i), 0.f);
+        sp.bounds[i] = make_float2((i == 0) ? -1e30f : m.z0 + m.h * static_cast<float>(i),
+                                   (i == m.num_layers - 1) ? 1e30f : m.z0 + m.h * static_cast<float>(i + 1));
+    }
     if (!SAVE_ALL) {
         for (int i = tid; i < geo.num_strings; i += kThreads) {
             sp.strings[i] = make_float4(__ldg(geo.string_x + i), __ldg(geo.string_y + i), __ldg(geo.string_max_z + i) + geo.om_radius,
@@ -924,6 +955,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
 
     // ---- lane and warp state
     float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
+    float *warp_region = reinterpret_cast<float *>(smem + lay.off_queue);
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = args.rng_a[gthread];
     {
@@ -932,26 +964,29 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(x >> 32));
         st[kStatus * kThreads] = __uint_as_float(static_cast<uint32_t>(kDead));
         st[kScatters * kThreads] = __uint_as_float(0xffffffffu); // no photon yet: counts as 0 flights when replaced
-        reinterpret_cast<uint32_t *>(smem + lay.off_nseg)[tid] = 0u;
+        reinterpret_cast<uint32_t *>(st + kOffNSeg)[0] = 0u;
         if (lane == 0) {
-            uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+            uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
             wctl[kWLeft] = 0u; wctl[kWStepIndex] = 0xffffffffu; wctl[kWMore] = 1u; wctl[kWQueued] = 0u; wctl[kWCreated] = 0u;
         }
     }
     __syncthreads();
 
     for (;;) {
-        const int limit = slow_phase<TILT, ANISO, SAVE_ALL>(args.scene_dev);
+        const int limit = slow_phase<TILT, ANISO, SAVE_ALL>(args.scene_dev, st, warp_region);
         if (limit < 0) break;
         // ---- fast phase: photon state in registers, no calls
         Lane L;
         load_lane<TILT, ANISO>(L, st);
+        bool cleared = (L.status == kCleared);
+        if (cleared) L.status = kActive;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.status != kActive);
             if (__popc(idle) >= limit) break;
             if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL, false>(L, scene, nullptr, sp.layers, sp.strings, sp.near, rng_a, nullptr);
+                advance_photon<TILT, ANISO, SAVE_ALL>(L, cleared, scene, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st);
         }
+        if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
         __syncwarp();
     }
@@ -959,10 +994,10 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     args.rng_x[gthread] = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
     if (args.count_stats) {
         // warp-level reduction, one atomic per warp; the lane's last photon has not been counted yet
-        unsigned long long segs = reinterpret_cast<uint32_t *>(smem + lay.off_nseg)[tid] + (__float_as_uint(st[kScatters * kThreads]) + 1u);
+        unsigned long long segs = reinterpret_cast<uint32_t *>(st + kOffNSeg)[0] + (__float_as_uint(st[kScatters * kThreads]) + 1u);
         for (int o = 16; o > 0; o >>= 1) segs += __shfl_down_sync(0xffffffffu, segs, o);
         if (lane == 0) {
-            const uint32_t *wctl = reinterpret_cast<uint32_t *>(smem + lay.off_warp_ctl) + warp * kWarpCtlWords;
+            const uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
             atomicAdd(args.stats + 0, static_cast<unsigned long long>(wctl[kWCreated]));
             atomicAdd(args.stats + 1, segs);
         }
