@@ -83,3 +83,19 @@ def test_null_engine_calls_are_errors():
     steps = np.zeros(4, dtype=STEP_DTYPE)
     assert lib.clsimcu_enqueue(None, steps.ctypes.data, 4, 0) != 0
     assert lib.clsimcu_destroy(None) != 0
+
+
+def test_product_does_not_use_the_oracle():
+    """oracle/ is test infrastructure: the product library must neither link it nor mention it, and no
+    module of the package may import it."""
+    ldd = subprocess.run(["ldd", capi.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert "oracle" not in ldd
+    needed = subprocess.run(["readelf", "-d", capi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in needed
+    pkg = os.path.join(ROOT, "clsim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".cxx", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "clsim_oracle" not in text, f
