@@ -10,6 +10,7 @@ namespace clsimcu {
 
 constexpr int kMaxWlenGenerators = 8;
 constexpr int kMaxSubdetectors = 9; // sparse_collision_kernel.c.cl:455-457
+constexpr uint32_t kFastKernelStepIndexBits = 27; // the fast kernel tags photons with (step index | creating lane << 27)
 
 struct DevWlenGenerator {
     int kind, n;

@@ -334,7 +334,7 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
             dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * pixel) / pixel));
             dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * pixel) / pixel));
             const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-2; // + slack for fp32 pixel assignment
-            const double min_range = 3.0; // below this the map cannot limit flights sensibly: cell walk
+            const double min_range = 1.0; // below this the map cannot limit flights sensibly: cell walk
             std::vector<uint32_t> info(static_cast<size_t>(dg.near_nx) * dg.near_ny);
             for (int iy = 0; iy < dg.near_ny; ++iy) {
                 for (int ix = 0; ix < dg.near_nx; ++ix) {
@@ -438,7 +438,7 @@ void submit_loop(clsimcu_engine *e)
             std::memcpy(s.h_steps, bunch.steps.data(), s.num_steps * sizeof(clsimcu_step));
             CUDA_OK(cudaMemcpyAsync(s.d_steps, s.h_steps, s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
             CUDA_OK(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), s.xfer));
-            CUDA_OK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.xfer));
+            CUDA_OK(cudaMemsetAsync(s.d_stats, 0, 8 * sizeof(unsigned long long), s.xfer));
             CUDA_OK(cudaEventRecord(s.uploaded, s.xfer));
             {
                 std::lock_guard<std::mutex> lk(e->compute_mutex);
@@ -606,15 +606,18 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
         if (e->kernel_mode == CLSIMCU_KERNEL_FAST) {
             // the pixel map of the collision test takes whatever shared memory the other tables leave
             const char *why = nullptr;
-            int budget = 8192;
+            int budget = 40000;
+            if (const char *env = std::getenv("CLSIMCU_PIXEL_BUDGET")) budget = std::max(512, std::atoi(env)); // tuning knob
             for (;;) {
                 upload_tables(*e, budget);
                 if (fast_kernel_supports(e->scene, &why)) break;
                 if (budget <= 512 || !fast_kernel_smem_is_the_problem(e->scene))
                     throw std::runtime_error(std::string("the fast kernel does not support this configuration (") + why + "); use CLSIMCU_KERNEL_REFERENCE");
-                budget /= 2;
+                budget = budget * 7 / 8;
             }
             fast_kernel_geometry(e->device, &e->fast_blocks, &e->fast_threads);
+            if (e->max_items > (size_t(1) << kFastKernelStepIndexBits))
+                throw std::runtime_error("the fast kernel takes bunches of at most 2^27 steps (max_num_workitems is " + std::to_string(e->max_items) + ")");
         } else {
             upload_tables(*e, 4096);
         }
@@ -654,11 +657,11 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
             CUDA_OK(cudaMalloc(&s.d_steps, e->max_items * sizeof(clsimcu_step)));
             CUDA_OK(cudaMalloc(&s.d_photons, e->max_hits * sizeof(clsimcu_photon)));
             CUDA_OK(cudaMalloc(&s.d_counters, 2 * sizeof(uint32_t)));
-            CUDA_OK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
+            CUDA_OK(cudaMalloc(&s.d_stats, 8 * sizeof(unsigned long long)));
             CUDA_OK(cudaHostAlloc(&s.h_steps, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&s.h_photons, e->max_hits * sizeof(clsimcu_photon), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&s.h_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-            CUDA_OK(cudaHostAlloc(&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&s.h_stats, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
             if (e->history_entries > 0) {
                 const size_t hb = e->max_hits * e->history_entries * 4 * sizeof(float);
                 CUDA_OK(cudaMalloc(&s.d_history, hb));
@@ -803,9 +806,9 @@ int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t
             e->res_cap = e->max_hits;
             CUDA_OK(cudaMalloc(&e->d_res_photons, e->res_cap * sizeof(clsimcu_photon)));
             CUDA_OK(cudaMalloc(&e->d_res_counters, 2 * sizeof(uint32_t)));
-            CUDA_OK(cudaMalloc(&e->d_res_stats, 2 * sizeof(unsigned long long)));
+            CUDA_OK(cudaMalloc(&e->d_res_stats, 8 * sizeof(unsigned long long)));
             CUDA_OK(cudaHostAlloc(&e->h_res_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
-            CUDA_OK(cudaHostAlloc(&e->h_res_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&e->h_res_stats, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
             CUDA_OK(cudaMalloc(&e->d_l2_flush, kL2FlushBytes));
             if (e->save_all) {
                 CUDA_OK(cudaMalloc(&e->d_tag_x, 2 * e->res_cap * sizeof(uint64_t)));
@@ -836,7 +839,7 @@ int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint6
         for (auto &x : ev) CUDA_OK(cudaEventCreate(&x));
         uint64_t hits = 0, segs = 0;
         double ms = 0.;
-        CUDA_OK(cudaMemsetAsync(e->d_res_stats, 0, 2 * sizeof(unsigned long long), e->compute));
+        CUDA_OK(cudaMemsetAsync(e->d_res_stats, 0, 8 * sizeof(unsigned long long), e->compute));
         for (int r = 0; r < repeat; ++r) {
             CUDA_OK(cudaMemsetAsync(e->d_res_counters, 0, 2 * sizeof(uint32_t), e->compute));
             CUDA_OK(cudaMemsetAsync(e->d_l2_flush, r & 0xff, kL2FlushBytes, e->compute)); // L2 flush, outside the timed events
@@ -867,8 +870,11 @@ int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint6
             CUDA_OK(cudaEventElapsedTime(&one, ev[2 * r], ev[2 * r + 1]));
             ms += one;
         }
-        CUDA_OK(cudaMemcpy(e->h_res_stats, e->d_res_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(e->h_res_stats, e->d_res_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         segs = e->h_res_stats[1];
+        if (std::getenv("CLSIMCU_DEBUG_STATS")) // counters of a -DCLSIMCU_DEBUG_COUNTERS build of the fast kernel
+            std::fprintf(stderr, "clsimcu debug stats: %llu %llu %llu %llu %llu %llu\n", e->h_res_stats[2], e->h_res_stats[3], e->h_res_stats[4],
+                         e->h_res_stats[5], e->h_res_stats[6], e->h_res_stats[7]);
         for (auto &x : ev) cudaEventDestroy(x);
         if (kernel_ms) *kernel_ms = ms;
         if (photons_generated) *photons_generated = e->res_generated_per_run * static_cast<uint64_t>(repeat);

@@ -60,37 +60,46 @@ namespace {
 #define CLSIMCU_BLOCKS_PER_SM 1
 #endif
 #ifndef CLSIMCU_IDLE_LIMIT
-#define CLSIMCU_IDLE_LIMIT 8
+#define CLSIMCU_IDLE_LIMIT 2
+#endif
+#ifndef CLSIMCU_IDLE_LIMIT_SAVE_ALL
+#define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
 #endif
 constexpr int kThreads = CLSIMCU_THREADS;
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
-constexpr int kIdleLimit = CLSIMCU_IDLE_LIMIT; // idle lanes that end a fast phase
+constexpr int kIdleLimit = CLSIMCU_IDLE_LIMIT;                  // parked lanes (possible DOM contact) that end a fast phase
+constexpr int kIdleLimitSaveAll = CLSIMCU_IDLE_LIMIT_SAVE_ALL;  // save-all: every photon ends in the slow phase
 constexpr float kSpeedOfLight = 0.299792458f;
 constexpr float kPi = 3.14159265359f;
 constexpr float kEpsilon = 0.00001f;
 constexpr float kLn2 = 0.69314718056f;
 constexpr uint32_t kSmemBudget = 227u * 1024u;
 
-// start-of-flight record (what a hit needs besides the running state)
-constexpr int kStartWords = 10; // x y z t dx dy dz wlen abs_initial step_index
-// queue slot: start record + the three wavelength-only ice factors + replay tags
-constexpr int kQueueWords = 16; // [10] scattering factor [11] dust factor [12] pure-ice absorption [13,14] x_create [15] a_create
+// queue slot (one photon waiting for a lane): where it starts, what is left of its life, the three
+// wavelength-only ice factors, and its BIRTH TAG: the state of the creation stream it was made from and
+// the step it belongs to.  The start-of-flight record a hit needs (start point, direction, time,
+// wavelength, lifetime) is not carried along: one photon in a thousand is detected, and for those the
+// record is re-created from the tag (creation is deterministic).
+enum QueueWord { kQx = 0, kQy, kQz, kQDx, kQDy, kQDz, kQLife, kQFScat, kQFDust, kQFPure, kQTagLo, kQTagHi, kQTagStep, kQueueWords };
+constexpr uint32_t kStepIndexBits = kFastKernelStepIndexBits; // tag word kQTagStep = step index | (creating lane << 27)
 // per-lane running state, parked in shared memory between fast phases
 enum StateWord {
     kPx = 0, kPy, kPz, kDx, kDy, kDz, kAbsLeft, kScaLeft, kPath, kFScat, kFDust, kFPure, kScatters, kLayer, kStatus, kRngLo, kRngHi,
     kZEff, kInvAniso, kPendTravel, kPendWho, kStateWords
 };
-// per-lane replay tags of the photon in flight (save-all variants only)
-constexpr int kTagWords = 5; // x_create lo, hi, a_create, x_pop lo, hi
+// per-lane birth tag of the photon in flight (3 words) and, in the save-all variants, the state of the
+// propagation stream when it started (2 words): what a checker needs to replay the photon
+constexpr int kBirthTagWords = 3;
+constexpr int kPopTagWords = 2;
 // per-warp control block
 enum WarpCtl { kWLeft = 0, kWStepIndex, kWMore, kWQueued, kWCreated, kWarpCtlWords = 8 };
 constexpr int kWarpStepWords = 16; // the warp's step record (12 words) + its direction (3)
 // compile-time offsets (in words) inside the per-thread and per-warp regions of shared memory
-constexpr int kOffCStart = kStateWords * kThreads;
-constexpr int kOffNSeg = kOffCStart + kStartWords * kThreads;
-constexpr int kOffTags = kOffNSeg + kThreads;
-constexpr int kPerThreadWords = kStateWords + kStartWords + 1;
+constexpr int kOffBirthTag = kStateWords * kThreads;
+constexpr int kOffNSeg = kOffBirthTag + kBirthTagWords * kThreads;
+constexpr int kOffPopTag = kOffNSeg + kThreads;
+constexpr int kPerThreadWords = kStateWords + kBirthTagWords + 1;
 constexpr int kOffWarpStep = kWarpsPerBlock * kQueueWords * 32;
 constexpr int kOffWarpCtl = kOffWarpStep + kWarpsPerBlock * kWarpStepWords;
 
@@ -123,6 +132,8 @@ struct Mwc {
     }
 };
 
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
 __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 {
     return static_cast<uint64_t>(__float_as_uint(lo)) | (static_cast<uint64_t>(__float_as_uint(hi)) << 32);
@@ -131,7 +142,7 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 // Shared-memory plan, carved out of the dynamic allocation.
 struct SmemLayout {
     uint32_t off_layers, off_bounds, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near;
-    uint32_t off_state;   // per-thread arrays: state | start-of-flight record | segment counter | replay tags (save-all only)
+    uint32_t off_state;   // per-thread arrays: state | birth tag | segment counter | propagation-stream tag (save-all only)
     uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
     uint32_t cell_offset[kMaxSubdetectors];
     uint32_t total;
@@ -175,7 +186,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     }
     at = align16(at + cells * 2);
     L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
-    L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kTagWords : 0)) * kThreads * 4);
+    L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kPopTagWords : 0)) * kThreads * 4);
     L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
     L.total = at;
     return L;
@@ -421,13 +432,84 @@ __device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos
     return c;
 }
 
+// ---- R3: photon creation ------------------------------------------------------------------------
+// createPhotonFromTrack (propagation_kernel.c.cl:132-184).  Deterministic in (step, creation-stream
+// state): the queue fill calls it to make a photon, the hit path calls it again with the photon's birth
+// tag to get the start-of-flight record back.
+struct StepView {
+    float x, y, z, t, length, beta;
+    uint32_t source;
+    V3 axis; // direction of travel (propagation_kernel.c.cl:482-489)
+};
+struct Born {
+    V3 pos;
+    float t;
+    V3 dir;
+    float wlen, life;
+};
+
+__device__ __forceinline__ V3 step_axis(float theta, float phi)
+{
+    float sth, cth, sph, cph;
+    __sincosf(theta, &sth, &cth);
+    __sincosf(phi, &sph, &cph);
+    return V3{sth * cph, sth * sph, cth};
+}
+
+__device__ __forceinline__ Born create_core(const DevScene *scene, const StepView &s, Mwc &rng)
+{
+    const DevMedium &m = scene->medium;
+    Born b;
+    const float shift = s.length * rng.co();
+    b.dir = s.axis;
+    if (scene->num_generators <= 1 || s.source == 0) {
+        b.wlen = draw_wavelength(scene->generators[0], rng);
+        const float cos_c = fminf(1.f, mufu_rcp(s.beta * phase_index(m, b.wlen)));
+        const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
+        rotate_by(cos_c, sin_c, b.dir, rng.co());
+    } else {
+        b.wlen = (s.source < static_cast<uint32_t>(scene->num_generators)) ? draw_wavelength(scene->generators[s.source], rng) : 0.f;
+    }
+    b.life = scene->fixed_abs ? scene->fixed_abs_lens : -fast_ln(rng.oc());
+    b.pos = V3{s.x + s.axis.x * shift, s.y + s.axis.y * shift, s.z + s.axis.z * shift};
+    b.t = s.t + shift * mufu_rcp(kSpeedOfLight * s.beta);
+    return b;
+}
+
+// Queue fill: one photon of the warp's current step into queue slot `slot` (word stride 32), together
+// with the wavelength-only factors of the ice model (R4, …_Optimizers.cxx:123-250).  The scene is read
+// from its copy in global memory (uniform addresses).  Returns the advanced creation-stream state.
+__device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float *slot, uint64_t rng_x, uint32_t rng_a,
+                                               uint32_t tag_step)
+{
+    const DevMedium &m = scene->medium;
+    Mwc rng{rng_x, rng_a};
+    StepView s;
+    s.x = __uint_as_float(wstep[0]); s.y = __uint_as_float(wstep[1]); s.z = __uint_as_float(wstep[2]); s.t = __uint_as_float(wstep[3]);
+    s.length = __uint_as_float(wstep[6]); s.beta = __uint_as_float(wstep[7]);
+    s.source = wstep[11] & 0xffu;
+    s.axis = V3{__uint_as_float(wstep[12]), __uint_as_float(wstep[13]), __uint_as_float(wstep[14])};
+    const Born b = create_core(scene, s, rng);
+    slot[kQx * 32] = b.pos.x; slot[kQy * 32] = b.pos.y; slot[kQz * 32] = b.pos.z;
+    slot[kQDx * 32] = b.dir.x; slot[kQDy * 32] = b.dir.y; slot[kQDz * 32] = b.dir.z;
+    slot[kQLife * 32] = b.life;
+    const float nm = b.wlen * 1e9f;
+    slot[kQFScat * 32] = fast_pow(b.wlen * m.inv_ref_wlen, -m.alpha);              // 1/scatLen = b400 * this
+    slot[kQFDust * 32] = fast_pow(nm, -m.kappa);                                  // dust term factor
+    slot[kQFPure * 32] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
+    slot[kQTagLo * 32] = __uint_as_float(static_cast<uint32_t>(rng_x));
+    slot[kQTagHi * 32] = __uint_as_float(static_cast<uint32_t>(rng_x >> 32));
+    slot[kQTagStep * 32] = __uint_as_float(tag_step);
+    return rng.x;
+}
+
 // ---- R10: hit output ----------------------------------------------------------------------------
-// Called by the lanes whose photon was just detected (or absorbed, in save-all mode): `pos` is
-// the end point, `path` the full path length, `st` the lane's start-of-flight record.
-// Reservation is aggregated over the lanes that arrive together; the record leaves as five
-// 16-byte stores.
-__device__ __noinline__ void emit_record(const DevScene *scene_dev, const float *st, V3 pos, V3 dir, float path, uint32_t scatters,
-                                         int hit_string, int hit_dom, float dist_abs, bool save_all, const uint32_t *tags, uint32_t rng_a)
+// Called by the lanes whose photon was just detected (or absorbed, in save-all mode): `pos` is the end
+// point, `path` the full path length.  The photon's start-of-flight record is re-created from its birth
+// tag into the lane's state words `st` (the photon is over, its state is dead).  Reservation is
+// aggregated over the lanes that arrive together; the record leaves as five 16-byte stores.
+__device__ __noinline__ void emit_record(const DevScene *scene_dev, float *st, V3 pos, V3 dir, float path, uint32_t scatters,
+                                         int hit_string, int hit_dom, float abs_left_at_end, bool save_all, uint32_t rng_a)
 {
     const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
     const DevScene &scene = *scene_dev;
@@ -439,10 +521,24 @@ __device__ __noinline__ void emit_record(const DevScene *scene_dev, const float 
     base = __shfl_sync(peers, base, leader);
     const uint32_t slot = base + __popc(peers & ((1u << lane) - 1u));
     if (slot >= args.max_hits) return; // counted but dropped (quirk 10)
-    const DevGeometry &geo = scene.geo;
-    const float stt = st[3 * kThreads], wlen = st[7 * kThreads];
-    const uint32_t step_index = __float_as_uint(st[9 * kThreads]);
+
+    // birth tag -> start-of-flight record
+    const uint32_t *btag = reinterpret_cast<const uint32_t *>(st + kOffBirthTag);
+    const uint32_t tag_step = btag[2 * kThreads];
+    const uint32_t step_index = tag_step & ((1u << kStepIndexBits) - 1u);
+    const uint32_t made_by = (blockIdx.x * kThreads + (threadIdx.x & ~31u)) + (tag_step >> kStepIndexBits);
+    const uint64_t birth_x = static_cast<uint64_t>(btag[0 * kThreads]) | (static_cast<uint64_t>(btag[1 * kThreads]) << 32);
+    const uint32_t birth_a = __ldg(args.rng_a + args.rng_creation_offset + made_by);
     const clsimcu_step *step = static_cast<const clsimcu_step *>(args.steps) + step_index;
+    StepView sv;
+    sv.x = __ldg(&step->x); sv.y = __ldg(&step->y); sv.z = __ldg(&step->z); sv.t = __ldg(&step->t);
+    sv.length = __ldg(&step->length); sv.beta = __ldg(&step->beta);
+    sv.source = __ldg(reinterpret_cast<const uint32_t *>(step) + 11) & 0xffu;
+    sv.axis = step_axis(__ldg(&step->theta), __ldg(&step->phi));
+    Mwc birth{birth_x, birth_a};
+    const Born born = create_core(scene_dev, sv, birth);
+
+    const DevGeometry &geo = scene.geo;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     uint32_t ids = 0;
     if (!save_all) {
@@ -460,68 +556,24 @@ __device__ __noinline__ void emit_record(const DevScene *scene_dev, const float 
         const uint16_t oid = __ldg(geo.dom_ids + __ldg(geo.dom_id_offset + hit_string) + hit_dom);
         ids = static_cast<uint32_t>(static_cast<uint16_t>(sid)) | (static_cast<uint32_t>(oid) << 16);
     }
-    const float ivg = inv_group_velocity(scene.medium, wlen);
+    const float ivg = inv_group_velocity(scene.medium, born.wlen);
     float th, ph, sth, sph;
     to_spherical(dir.x, dir.y, dir.z, th, ph);
-    to_spherical(st[4 * kThreads], st[5 * kThreads], st[6 * kThreads], sth, sph);
+    to_spherical(born.dir.x, born.dir.y, born.dir.z, sth, sph);
     float4 *dst = reinterpret_cast<float4 *>(static_cast<clsimcu_photon *>(args.photons) + slot);
-    dst[0] = make_float4(pos.x - qx, pos.y - qy, pos.z - qz, stt + path * ivg);
-    dst[1] = make_float4(th, ph, wlen, path);
-    dst[2] = make_float4(__uint_as_float(scatters), __ldg(&step->weight) / bias_at(scene.bias, wlen),
+    dst[0] = make_float4(pos.x - qx, pos.y - qy, pos.z - qz, born.t + path * ivg);
+    dst[1] = make_float4(th, ph, born.wlen, path);
+    dst[2] = make_float4(__uint_as_float(scatters), __ldg(&step->weight) / bias_at(scene.bias, born.wlen),
                          __uint_as_float(__ldg(&step->identifier)), __uint_as_float(ids));
-    dst[3] = make_float4(st[0 * kThreads], st[1 * kThreads], st[2 * kThreads], stt);
-    dst[4] = make_float4(sth, sph, 1.f / ivg, dist_abs);
-    if (save_all && args.rng_tag_x && tags) {
-        args.rng_tag_x[2 * static_cast<size_t>(slot)] = static_cast<uint64_t>(tags[0 * kThreads]) | (static_cast<uint64_t>(tags[1 * kThreads]) << 32);
-        args.rng_tag_x[2 * static_cast<size_t>(slot) + 1] = static_cast<uint64_t>(tags[3 * kThreads]) | (static_cast<uint64_t>(tags[4 * kThreads]) << 32);
-        args.rng_tag_a[2 * static_cast<size_t>(slot)] = tags[2 * kThreads];
+    dst[3] = make_float4(born.pos.x, born.pos.y, born.pos.z, born.t);
+    dst[4] = make_float4(sth, sph, 1.f / ivg, born.life - abs_left_at_end);
+    if (save_all && args.rng_tag_x) {
+        const uint32_t *ptag = reinterpret_cast<const uint32_t *>(st + kOffPopTag);
+        args.rng_tag_x[2 * static_cast<size_t>(slot)] = birth_x;
+        args.rng_tag_x[2 * static_cast<size_t>(slot) + 1] = static_cast<uint64_t>(ptag[0 * kThreads]) | (static_cast<uint64_t>(ptag[1 * kThreads]) << 32);
+        args.rng_tag_a[2 * static_cast<size_t>(slot)] = birth_a;
         args.rng_tag_a[2 * static_cast<size_t>(slot) + 1] = rng_a;
     }
-}
-
-// R3: createPhotonFromTrack (propagation_kernel.c.cl:132-184) plus the wavelength-only factors of
-// the ice model (R4, …_Optimizers.cxx:123-250), written to queue slot `slot` (word stride 32).
-// The scene is read from its copy in global memory (uniform addresses).  Returns the advanced
-// state of the creation stream.
-__device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float *slot, uint64_t rng_x, uint32_t rng_a,
-                                               uint32_t step_index)
-{
-    const DevMedium &m = scene->medium;
-    Mwc rng{rng_x, rng_a};
-    const float s_x = __uint_as_float(wstep[0]), s_y = __uint_as_float(wstep[1]), s_z = __uint_as_float(wstep[2]);
-    const float s_t = __uint_as_float(wstep[3]), s_len = __uint_as_float(wstep[6]), s_beta = __uint_as_float(wstep[7]);
-    const uint32_t source = (wstep[11] & 0xffu);
-    const V3 axis{__uint_as_float(wstep[12]), __uint_as_float(wstep[13]), __uint_as_float(wstep[14])};
-    const float shift = s_len * rng.co();
-    V3 d = axis;
-    float wlen;
-    if (scene->num_generators <= 1 || source == 0) {
-        wlen = draw_wavelength(scene->generators[0], rng);
-        const float cos_c = fminf(1.f, mufu_rcp(s_beta * phase_index(m, wlen)));
-        const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
-        rotate_by(cos_c, sin_c, d, rng.co());
-    } else {
-        wlen = (source < static_cast<uint32_t>(scene->num_generators)) ? draw_wavelength(scene->generators[source], rng) : 0.f;
-    }
-    const float life = scene->fixed_abs ? scene->fixed_abs_lens : -fast_ln(rng.oc());
-    slot[0 * 32] = s_x + axis.x * shift;
-    slot[1 * 32] = s_y + axis.y * shift;
-    slot[2 * 32] = s_z + axis.z * shift;
-    slot[3 * 32] = s_t + shift * mufu_rcp(kSpeedOfLight * s_beta);
-    slot[4 * 32] = d.x;
-    slot[5 * 32] = d.y;
-    slot[6 * 32] = d.z;
-    slot[7 * 32] = wlen;
-    slot[8 * 32] = life;
-    slot[9 * 32] = __uint_as_float(step_index);
-    const float nm = wlen * 1e9f;
-    slot[10 * 32] = fast_pow(wlen * m.inv_ref_wlen, -m.alpha);                // 1/scatLen = b400 * this
-    slot[11 * 32] = fast_pow(nm, -m.kappa);                                  // dust term factor
-    slot[12 * 32] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
-    slot[13 * 32] = __uint_as_float(static_cast<uint32_t>(rng_x));
-    slot[14 * 32] = __uint_as_float(static_cast<uint32_t>(rng_x >> 32));
-    slot[15 * 32] = __uint_as_float(rng_a);
-    return rng.x;
 }
 
 // The rest of a flight that was cut short by a DOM: the reference reports distInAbsLens for the
@@ -583,6 +635,7 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(cons
     st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
     st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
     st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = L.sca_left; st[kPath * kThreads] = L.path;
+    st[kFScat * kThreads] = L.f_scat; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_pure; // lanes change photons inside a fast phase
     st[kScatters * kThreads] = __uint_as_float(L.scatters);
     st[kLayer * kThreads] = __int_as_float(L.layer);
     st[kStatus * kThreads] = __uint_as_float(L.status);
@@ -692,6 +745,16 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
         const float out2 = o2 - R * R;                       // > 0: the photon starts outside the cylinder
         const bool miss = (o2 > reach * reach) || ((t <= 0.f) && (out2 > 0.f)) || (out2 * dxy2 > t * t);
         if ((!miss || g.walk) && !cleared) {
+#ifdef CLSIMCU_DEBUG_COUNTERS
+            {
+                const LaunchArgs &dbg = reinterpret_cast<const SmemHeader *>(smem_base())->args;
+                atomicAdd(dbg.stats + 2, 1ull);                                  // legs parked
+                if (g.walk) atomicAdd(dbg.stats + 3, 1ull);                      // ... in a dense-string pixel
+                if (out2 <= 0.f) atomicAdd(dbg.stats + 4, 1ull);                 // ... starting inside the cylinder
+                if (L.scatters == 0u) atomicAdd(dbg.stats + 5, 1ull);            // ... before the first scatter
+                if (g.travel > 20.f) atomicAdd(dbg.stats + 6, 1ull);             // ... long legs
+            }
+#endif
             L.status = kFrozen;
             st[kPendTravel * kThreads] = g.travel;
             st[kPendWho * kThreads] = __int_as_float(g.walk ? -1 : g.who);
@@ -753,7 +816,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
 // the lane goes back to the hot loop (kCleared).  Hit: the photon ends at the DOM and is
 // written out.
 template <bool TILT, bool ANISO>
-__device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, const float *cstart, uint32_t rng_a)
+__device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, uint32_t rng_a)
 {
     const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
     const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
@@ -773,14 +836,103 @@ __device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st
                                            L.dir.z, L.inv_dz, g.rem_sca, g.rem_abs, L.f_scat, L.f_dust, L.f_pure);
     if (ANISO) at_end *= L.inv_aniso;
     const V3 end{fmaf(dir.x, col.travel, pos.x), fmaf(dir.y, col.travel, pos.y), fmaf(dir.z, col.travel, pos.z)};
-    emit_record(scene, cstart, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, cstart[8 * kThreads] - at_end, false, nullptr,
-                rng_a);
+    emit_record(scene, st, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, at_end, false, rng_a);
     return kDead;
 }
 
+// Queue fill, by all 32 lanes of the warp at once: the next photons of the warp's step (and of the
+// steps after it, fetched from the global work counter) go to queue slots 0, 1, ...; the slot index is
+// the creating lane.  Called with an empty queue.  Control state lives in the warp's control block.
+__device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_region)
+{
+    const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const unsigned lane_bit = 1u << lane;
+    float *queue = warp_region + warp * (kQueueWords * 32);
+    uint32_t *wstep = reinterpret_cast<uint32_t *>(warp_region + kOffWarpStep) + warp * kWarpStepWords;
+    uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
+    const uint32_t gthread = blockIdx.x * kThreads + tid;
+    uint32_t w_left = wctl[kWLeft], w_step_index = wctl[kWStepIndex], queued = 0, w_created = wctl[kWCreated];
+    bool w_more = wctl[kWMore] != 0;
+    __syncwarp();
+    Mwc crng{args.rng_x[args.rng_creation_offset + gthread], __ldg(args.rng_a + args.rng_creation_offset + gthread)};
+    bool need = true;
+    for (;;) {
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+        if (need_mask == 0) break;
+        if (w_left == 0) {
+            if (!w_more) break;
+            // next step for this warp
+            uint32_t idx = 0;
+            if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (idx >= args.num_steps) { w_more = false; break; }
+            __syncwarp();
+            if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
+            __syncwarp();
+            w_step_index = idx;
+            w_left = wstep[8];
+            if (lane == 0) {
+                const V3 axis = step_axis(__uint_as_float(wstep[4]), __uint_as_float(wstep[5]));
+                wstep[12] = __float_as_uint(axis.x);
+                wstep[13] = __float_as_uint(axis.y);
+                wstep[14] = __float_as_uint(axis.z);
+            }
+            __syncwarp();
+            if (w_left == 0) continue; // dummy step (quirk 11)
+        }
+        // the lanes still in need are the upper ones, so the filled slots stay a prefix
+        const int rank = __popc(need_mask & (lane_bit - 1u));
+        const bool take = need && (static_cast<uint32_t>(rank) < w_left);
+        if (take) {
+            crng.x = create_photon(scene, wstep, queue + lane, crng.x, crng.a, w_step_index | (static_cast<uint32_t>(lane) << kStepIndexBits));
+            need = false;
+        }
+        const uint32_t took = __popc(__ballot_sync(0xffffffffu, take));
+        queued += took;
+        w_created += took;
+        w_left -= took;
+    }
+    args.rng_x[args.rng_creation_offset + gthread] = crng.x;
+    __syncwarp();
+    if (lane == 0) {
+        wctl[kWLeft] = w_left; wctl[kWStepIndex] = w_step_index; wctl[kWMore] = w_more ? 1u : 0u; wctl[kWQueued] = queued;
+        wctl[kWCreated] = w_created;
+    }
+    __syncwarp();
+}
+
+// A lane takes the photon in queue slot `slot` (word stride 32): running state into `L`, birth tag (and,
+// save-all, the propagation-stream state) into the lane's tag words.
+template <bool SAVE_ALL>
+__device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *st, const DevMedium &m)
+{
+    L.pos.x = slot[kQx * 32]; L.pos.y = slot[kQy * 32]; L.pos.z = slot[kQz * 32];
+    L.dir.x = slot[kQDx * 32]; L.dir.y = slot[kQDy * 32]; L.dir.z = slot[kQDz * 32];
+    L.inv_dz = safe_inv_dz(L.dir.z);
+    L.abs_left = slot[kQLife * 32];
+    L.sca_left = 0.f;
+    L.path = 0.f;
+    L.f_scat = slot[kQFScat * 32]; L.f_dust = slot[kQFDust * 32]; L.f_pure = slot[kQFPure * 32];
+    L.scatters = 0u;
+    L.layer = min(max(__float2int_rz((L.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1);
+    L.status = kActive;
+    float *btag = st + kOffBirthTag;
+    btag[0 * kThreads] = slot[kQTagLo * 32]; btag[1 * kThreads] = slot[kQTagHi * 32]; btag[2 * kThreads] = slot[kQTagStep * 32];
+    if (SAVE_ALL) {
+        float *ptag = st + kOffPopTag;
+        ptag[0 * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x));
+        ptag[1 * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x >> 32));
+    }
+}
+
 // ---- slow phase ------------------------------------------------------------------------------
-// Runs converged, once per warp each time the hot loop has collected kIdleLimit idle lanes.
-// Returns the number of idle lanes that ends the next fast phase, or -1 when the warp is done.
+// Runs converged, once per warp each time the hot loop cannot go on by itself: parked lanes get the full
+// collision test (hits are written out), save-all photons that ended are recorded, the queue is
+// refilled, lanes without a photon take one.  Returns the number of idle lanes that ends the next fast
+// phase, or -1 when the warp is done.
 template <bool TILT, bool ANISO, bool SAVE_ALL>
 __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *warp_region)
 {
@@ -789,22 +941,15 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lane_bit = 1u << lane;
-    float *cstart = st + kOffCStart;
     uint32_t *nseg = reinterpret_cast<uint32_t *>(st + kOffNSeg);
-    uint32_t *tags = SAVE_ALL ? reinterpret_cast<uint32_t *>(st + kOffTags) : nullptr;
-    float *queue = warp_region + warp * (kQueueWords * 32);
-    uint32_t *wstep = reinterpret_cast<uint32_t *>(warp_region + kOffWarpStep) + warp * kWarpStepWords;
+    const float *queue = warp_region + warp * (kQueueWords * 32);
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = __ldg(args.rng_a + gthread);
-
-    uint32_t w_left = wctl[kWLeft], w_step_index = wctl[kWStepIndex], queued = wctl[kWQueued], w_created = wctl[kWCreated];
-    bool w_more = wctl[kWMore] != 0;
-    __syncwarp();
     uint32_t status = __float_as_uint(st[kStatus * kThreads]);
 
     // ---- photons whose next leg may touch a DOM: the full collision test
-    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO>(scene, st, cstart, rng_a);
+    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO>(scene, st, rng_a);
     // ---- save-all: every photon that ended is recorded with probability `prescale`
     //      (propagation_kernel.c.cl:800-826)
     if (SAVE_ALL && status == kDying) {
@@ -815,101 +960,50 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
         if (keep) {
             const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
             const V3 dir{st[kDx * kThreads], st[kDy * kThreads], st[kDz * kThreads]};
-            emit_record(scene, cstart, pos, dir, st[kPath * kThreads], __float_as_uint(st[kScatters * kThreads]), 0, 0, cstart[8 * kThreads],
-                        true, tags, rng_a);
+            emit_record(scene, st, pos, dir, st[kPath * kThreads], __float_as_uint(st[kScatters * kThreads]), 0, 0, 0.f, true, rng_a);
         }
         status = kDead;
     }
+    __syncwarp();
 
-    // ---- idle lanes take the next photons of the warp's queue; an empty queue is refilled by
-    //      all lanes at once from the warp's step (and the steps after it)
+    // ---- lanes without a photon take the next ones of the warp's queue; an empty queue is refilled
+    //      first, and once more at the end so that the hot loop starts with photons in stock
+    uint32_t queued = wctl[kWQueued];
     for (;;) {
         const unsigned dead = __ballot_sync(0xffffffffu, status == kDead);
-        if (dead == 0u) break;
         if (queued == 0) {
-            if (!(w_more || w_left > 0)) break;
-            Mwc crng{args.rng_x[args.rng_creation_offset + gthread], __ldg(args.rng_a + args.rng_creation_offset + gthread)};
-            bool need = true;
-            for (;;) {
-                const unsigned need_mask = __ballot_sync(0xffffffffu, need);
-                if (need_mask == 0) break;
-                if (w_left == 0) {
-                    if (!w_more) break;
-                    // next step for this warp
-                    uint32_t idx = 0;
-                    if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
-                    idx = __shfl_sync(0xffffffffu, idx, 0);
-                    if (idx >= args.num_steps) { w_more = false; break; }
-                    __syncwarp();
-                    if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
-                    __syncwarp();
-                    w_step_index = idx;
-                    w_left = wstep[8];
-                    if (lane == 0) {
-                        float sth, cth, sph, cph;
-                        __sincosf(__uint_as_float(wstep[4]), &sth, &cth);
-                        __sincosf(__uint_as_float(wstep[5]), &sph, &cph);
-                        wstep[12] = __float_as_uint(sth * cph);
-                        wstep[13] = __float_as_uint(sth * sph);
-                        wstep[14] = __float_as_uint(cth);
-                    }
-                    __syncwarp();
-                    if (w_left == 0) continue; // dummy step (quirk 11)
-                }
-                // the lanes still in need are the upper ones, so the filled slots stay a prefix
-                const int rank = __popc(need_mask & (lane_bit - 1u));
-                const bool take = need && (static_cast<uint32_t>(rank) < w_left);
-                if (take) {
-                    crng.x = create_photon(scene, wstep, queue + lane, crng.x, crng.a, w_step_index);
-                    need = false;
-                }
-                const uint32_t took = __popc(__ballot_sync(0xffffffffu, take));
-                queued += took;
-                w_created += took;
-                w_left -= took;
-            }
-            args.rng_x[args.rng_creation_offset + gthread] = crng.x;
-            __syncwarp();
+            if (!(wctl[kWMore] != 0 || wctl[kWLeft] > 0)) break;
+            fill_queue(scene, warp_region);
+            queued = wctl[kWQueued];
             if (queued == 0) break; // nothing left to create
         }
+        if (dead == 0u) break;
         const uint32_t rank = __popc(dead & (lane_bit - 1u));
         if (status == kDead && rank < queued) {
-            const float *slot = queue + (queued - 1u - rank);
             // statistics: one flight (reference: segment) per scatter, plus the last one
             *nseg += __float_as_uint(st[kScatters * kThreads]) + 1u;
-#pragma unroll
-            for (int w = 0; w < kStartWords; ++w) cstart[w * kThreads] = slot[w * 32];
-            const float z = slot[2 * 32];
-            st[kPx * kThreads] = slot[0 * 32]; st[kPy * kThreads] = slot[1 * 32]; st[kPz * kThreads] = z;
-            st[kDx * kThreads] = slot[4 * 32]; st[kDy * kThreads] = slot[5 * 32]; st[kDz * kThreads] = slot[6 * 32];
-            st[kAbsLeft * kThreads] = slot[8 * 32];
-            st[kScaLeft * kThreads] = 0.f;
-            st[kPath * kThreads] = 0.f;
-            st[kFScat * kThreads] = slot[10 * 32]; st[kFDust * kThreads] = slot[11 * 32]; st[kFPure * kThreads] = slot[12 * 32];
+            Lane L;
+            L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
+            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st, scene->medium);
+            st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
+            st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
+            st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
+            st[kFScat * kThreads] = L.f_scat; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_pure;
             st[kScatters * kThreads] = __uint_as_float(0u);
-            st[kLayer * kThreads] = __int_as_float(min(max(__float2int_rz((z - scene->medium.z0) * scene->medium.inv_h), 0), scene->medium.num_layers - 1));
+            st[kLayer * kThreads] = __int_as_float(L.layer);
             status = kActive;
-            if (SAVE_ALL) {
-                tags[0 * kThreads] = __float_as_uint(slot[13 * 32]);
-                tags[1 * kThreads] = __float_as_uint(slot[14 * 32]);
-                tags[2 * kThreads] = __float_as_uint(slot[15 * 32]);
-                tags[3 * kThreads] = __float_as_uint(st[kRngLo * kThreads]);
-                tags[4 * kThreads] = __float_as_uint(st[kRngHi * kThreads]);
-            }
         }
         queued -= min(static_cast<uint32_t>(__popc(dead)), queued);
         __syncwarp();
     }
     st[kStatus * kThreads] = __uint_as_float(status);
+    if (lane == 0) wctl[kWQueued] = queued;
 
     const int n_idle = __popc(__ballot_sync(0xffffffffu, status == kDead));
-    if (lane == 0) {
-        wctl[kWLeft] = w_left; wctl[kWStepIndex] = w_step_index; wctl[kWMore] = w_more ? 1u : 0u; wctl[kWQueued] = queued;
-        wctl[kWCreated] = w_created;
-    }
     __syncwarp();
     if (n_idle == 32) return -1;                    // nothing in flight, nothing queued, nothing to fetch
-    return (n_idle > 0) ? n_idle + 1 : kIdleLimit;  // idle lanes remain only when the work has run out: drain
+    // idle lanes remain only when the work has run out: drain
+    return (n_idle > 0) ? n_idle + 1 : (SAVE_ALL ? kIdleLimitSaveAll : kIdleLimit);
 }
 
 template <bool TILT, bool ANISO, bool SAVE_ALL>
@@ -956,8 +1050,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     // ---- lane and warp state
     float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
     float *warp_region = reinterpret_cast<float *>(smem + lay.off_queue);
+    const float *queue = warp_region + warp * (kQueueWords * 32);
+    uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = args.rng_a[gthread];
+    uint32_t flights = 0u; // statistics: flights (reference: segments) of the photons this lane finished in the hot loop
     {
         const uint64_t x = args.rng_x[gthread];
         st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(x));
@@ -966,7 +1063,6 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         st[kScatters * kThreads] = __uint_as_float(0xffffffffu); // no photon yet: counts as 0 flights when replaced
         reinterpret_cast<uint32_t *>(st + kOffNSeg)[0] = 0u;
         if (lane == 0) {
-            uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
             wctl[kWLeft] = 0u; wctl[kWStepIndex] = 0xffffffffu; wctl[kWMore] = 1u; wctl[kWQueued] = 0u; wctl[kWCreated] = 0u;
         }
     }
@@ -975,29 +1071,50 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     for (;;) {
         const int limit = slow_phase<TILT, ANISO, SAVE_ALL>(args.scene_dev, st, warp_region);
         if (limit < 0) break;
-        // ---- fast phase: photon state in registers, no calls
+        // ---- fast phase: photon state in registers, no calls.  A lane whose photon ended takes the next
+        //      one from the warp's queue right here; the phase ends when the queue runs dry, or when
+        //      `limit` lanes wait for the slow phase.
         Lane L;
         load_lane<TILT, ANISO>(L, st);
         bool cleared = (L.status == kCleared);
         if (cleared) L.status = kActive;
+        uint32_t queued = wctl[kWQueued];
+        const bool more = (wctl[kWMore] != 0u) || (wctl[kWLeft] > 0u);
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.status != kActive);
-            if (__popc(idle) >= limit) break;
+            if (idle != 0u) {
+                const unsigned dead = __ballot_sync(0xffffffffu, L.status == kDead);
+                uint32_t n_dead = __popc(dead);
+                if (n_dead > 0u && queued > 0u) {
+                    const uint32_t rank = __popc(dead & lanemask_lt());
+                    if (L.status == kDead && rank < queued) {
+                        flights += L.scatters + 1u;
+                        take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st, m);
+                    }
+                    const uint32_t taken = min(n_dead, queued);
+                    queued -= taken;
+                    n_dead -= taken;
+                }
+                // lanes left without a photon: the slow phase refills the queue (unless the work has run out)
+                if (n_dead > 0u && more) break;
+                if (__popc(idle & ~dead) + static_cast<int>(n_dead) >= limit) break;
+            }
             if (L.status == kActive)
                 advance_photon<TILT, ANISO, SAVE_ALL>(L, cleared, scene, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st);
         }
         if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
+        if (lane == 0) wctl[kWQueued] = queued;
         __syncwarp();
     }
 
     args.rng_x[gthread] = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
     if (args.count_stats) {
         // warp-level reduction, one atomic per warp; the lane's last photon has not been counted yet
-        unsigned long long segs = reinterpret_cast<uint32_t *>(st + kOffNSeg)[0] + (__float_as_uint(st[kScatters * kThreads]) + 1u);
+        unsigned long long segs = static_cast<unsigned long long>(reinterpret_cast<uint32_t *>(st + kOffNSeg)[0]) + flights +
+                                  (__float_as_uint(st[kScatters * kThreads]) + 1u);
         for (int o = 16; o > 0; o >>= 1) segs += __shfl_down_sync(0xffffffffu, segs, o);
         if (lane == 0) {
-            const uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
             atomicAdd(args.stats + 0, static_cast<unsigned long long>(wctl[kWCreated]));
             atomicAdd(args.stats + 1, segs);
         }
@@ -1053,6 +1170,7 @@ int launch_fast_kernel(const DevScene &scene, const LaunchArgs &args, int grid_b
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (args.num_steps == 0) return 0;
+    if (args.num_steps > (1u << kStepIndexBits)) return -1;
     const bool tilt = scene.medium.tilt_nd > 0, aniso = scene.medium.anisotropy != 0;
     if (scene.save_all) {
         if (tilt && aniso) return launch_variant<true, true, true>(scene, args, grid_blocks, stream);
