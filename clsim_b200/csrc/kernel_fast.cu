@@ -60,7 +60,7 @@ namespace {
 #define CLSIMCU_BLOCKS_PER_SM 1
 #endif
 #ifndef CLSIMCU_IDLE_LIMIT
-#define CLSIMCU_IDLE_LIMIT 2
+#define CLSIMCU_IDLE_LIMIT 1
 #endif
 #ifndef CLSIMCU_IDLE_LIMIT_SAVE_ALL
 #define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
@@ -81,7 +81,7 @@ constexpr uint32_t kSmemBudget = 227u * 1024u;
 // the step it belongs to.  The start-of-flight record a hit needs (start point, direction, time,
 // wavelength, lifetime) is not carried along: one photon in a thousand is detected, and for those the
 // record is re-created from the tag (creation is deterministic).
-enum QueueWord { kQx = 0, kQy, kQz, kQDx, kQDy, kQDz, kQLife, kQFScat, kQFDust, kQFPure, kQTagLo, kQTagHi, kQTagStep, kQueueWords };
+enum QueueWord { kQx = 0, kQy, kQz, kQDx, kQDy, kQDz, kQInvDz, kQLayer, kQLife, kQFScat, kQFDust, kQFPure, kQTagLo, kQTagHi, kQTagStep, kQueueWords };
 constexpr uint32_t kStepIndexBits = kFastKernelStepIndexBits; // tag word kQTagStep = step index | (creating lane << 27)
 // per-lane running state, parked in shared memory between fast phases
 enum StateWord {
@@ -492,6 +492,9 @@ __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint
     const Born b = create_core(scene, s, rng);
     slot[kQx * 32] = b.pos.x; slot[kQy * 32] = b.pos.y; slot[kQz * 32] = b.pos.z;
     slot[kQDx * 32] = b.dir.x; slot[kQDy * 32] = b.dir.y; slot[kQDz * 32] = b.dir.z;
+    // derived here, where all 32 lanes work, rather than when a lane takes the photon
+    slot[kQInvDz * 32] = safe_inv_dz(b.dir.z);
+    slot[kQLayer * 32] = __int_as_float(min(max(__float2int_rz((b.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1));
     slot[kQLife * 32] = b.life;
     const float nm = b.wlen * 1e9f;
     slot[kQFScat * 32] = fast_pow(b.wlen * m.inv_ref_wlen, -m.alpha);              // 1/scatLen = b400 * this
@@ -907,17 +910,17 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
 // A lane takes the photon in queue slot `slot` (word stride 32): running state into `L`, birth tag (and,
 // save-all, the propagation-stream state) into the lane's tag words.
 template <bool SAVE_ALL>
-__device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *st, const DevMedium &m)
+__device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *st)
 {
     L.pos.x = slot[kQx * 32]; L.pos.y = slot[kQy * 32]; L.pos.z = slot[kQz * 32];
     L.dir.x = slot[kQDx * 32]; L.dir.y = slot[kQDy * 32]; L.dir.z = slot[kQDz * 32];
-    L.inv_dz = safe_inv_dz(L.dir.z);
+    L.inv_dz = slot[kQInvDz * 32];
     L.abs_left = slot[kQLife * 32];
     L.sca_left = 0.f;
     L.path = 0.f;
     L.f_scat = slot[kQFScat * 32]; L.f_dust = slot[kQFDust * 32]; L.f_pure = slot[kQFPure * 32];
     L.scatters = 0u;
-    L.layer = min(max(__float2int_rz((L.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1);
+    L.layer = __float_as_int(slot[kQLayer * 32]);
     L.status = kActive;
     float *btag = st + kOffBirthTag;
     btag[0 * kThreads] = slot[kQTagLo * 32]; btag[1 * kThreads] = slot[kQTagHi * 32]; btag[2 * kThreads] = slot[kQTagStep * 32];
@@ -984,7 +987,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
             *nseg += __float_as_uint(st[kScatters * kThreads]) + 1u;
             Lane L;
             L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
-            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st, scene->medium);
+            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
             st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
             st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
             st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
@@ -1089,7 +1092,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                     const uint32_t rank = __popc(dead & lanemask_lt());
                     if (L.status == kDead && rank < queued) {
                         flights += L.scatters + 1u;
-                        take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st, m);
+                        take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
                     }
                     const uint32_t taken = min(n_dead, queued);
                     queued -= taken;
