@@ -102,6 +102,20 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(bunch_steps):
+    """DRAM bytes (read + write) of one launch of the fast kernel at this bunch size, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None if there is
+    no capture of this launch shape."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    if int(d.get("bunch_steps", -1)) != int(bunch_steps):
+        return None
+    return d.get("dram_bytes_total")
+
+
 def build_scene():
     from clsim_b200 import geometry, ice
     medium = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_mie", useTiltIfAvailable=False)
@@ -276,7 +290,9 @@ def main():
     hit_bytes = hits_all * 80.0
     roofline = {
         "bound": "compute-fp32-issue", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
-        "frac": achieved_ops / peak_ops, "traffic": None,
+        "frac": achieved_ops / peak_ops, "traffic": measured_traffic(n),
+        "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), algorithmic: %d" % int(
+            n * 48 + hits_all / max(1, args.steps * world) * 80),
         "peak_source": "%d SMs x 128 lanes x %.0f MHz (sm_max_mhz %s)" % (sms, peaks["sm_max_mhz"], peaks["source"]),
         "ops_per_segment": OPS_PER_SEGMENT, "ops_per_photon": OPS_PER_PHOTON,
         "segments_per_photon": segments_all / photons_all,

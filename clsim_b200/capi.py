@@ -24,7 +24,7 @@ SYMBOLS = [
     "clsimcu_get_statistics", "clsimcu_upload_resident", "clsimcu_run_resident", "clsimcu_download_resident",
     "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
     "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
-    "clsimcu_sizeof_config",
+    "clsimcu_sizeof_config", "clsimcu_device_count",
 ]
 
 STAT_KEYS = ["TotalDeviceTime", "TotalHostTime", "NumKernelCalls", "TotalNumPhotonsGenerated", "TotalNumPhotonsAtDOMs",
@@ -79,6 +79,13 @@ def lib():
 def _check(rc):
     if rc != 0:
         raise ClsimCudaError(rc, lib().clsimcu_last_error().decode())
+
+
+def device_count():
+    """Usable CUDA devices; raises when there is none (no CPU fallback)."""
+    n = C.c_int(0)
+    _check(lib().clsimcu_device_count(C.byref(n)))
+    return n.value
 
 
 def safeprime_multipliers(first, n):

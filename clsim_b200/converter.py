@@ -269,8 +269,10 @@ def configureCUDADevices(UseGPUs=True, UseCPUs=False, UseOnlyDeviceNumber=None, 
     if not UseGPUs:
         raise RuntimeError("No matching OpenCL devices. Nothing to do.")
     if numDevices is None:
-        import torch  # device enumeration only
-        numDevices = torch.cuda.device_count()
+        try:
+            numDevices = capi.device_count()
+        except capi.ClsimCudaError:
+            numDevices = 0
     if numDevices == 0:
         raise RuntimeError("No matching CUDA devices. Nothing to do.")
     ordinals = list(range(numDevices))

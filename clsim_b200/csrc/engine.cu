@@ -560,6 +560,19 @@ void free_engine(clsimcu_engine *e)
 
 extern "C" {
 
+int clsimcu_device_count(int *count)
+{
+    if (!count) return fail(CLSIMCU_ERR_INVALID, "count pointer is NULL");
+    int n = 0;
+    const cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        *count = 0;
+        return fail(CLSIMCU_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); libclsimcuda has no CPU fallback");
+    }
+    *count = n;
+    return CLSIMCU_OK;
+}
+
 const char *clsimcu_last_error(void) { return t_last_error.c_str(); }
 const char *clsimcu_version(void) { return "clsimcuda 0.1 (sm_100a)"; }
 size_t clsimcu_sizeof_config(void) { return sizeof(clsimcu_config); }

@@ -8,16 +8,19 @@
 //  * One photon per LANE.  The kernel alternates between two phases per warp:
 //      FAST  -- a straight-line loop with the photon state in registers: every iteration moves
 //               each live photon to its next EVENT (scatter, absorption, ice-layer boundary, or
-//               the range limit of the collision map).  No calls, no rare paths, no spills.
-//               Lanes whose photon ended, or whose segment might touch a DOM, go idle; the
-//               loop runs until kIdleLimit lanes are idle.
-//      SLOW  -- out of line, lane state parked in shared memory: the few segments that may touch
-//               a DOM get the reference's full collision test and hits are written out; idle
-//               lanes take their next photon from the warp's QUEUE; an empty queue is refilled
-//               by all 32 lanes at once (photon creation: wavelength table search, Cherenkov
-//               cone, the wavelength-only transcendental factors of the ice model, lifetime).
+//               the range limit of the collision map).  A lane whose photon ended takes the next
+//               one from the warp's QUEUE in shared memory right inside the loop, so all 32 lanes
+//               stay busy.  No calls, no rare paths, no spills.
+//      SLOW  -- out of line, lane state parked in shared memory; entered when a leg might touch
+//               a DOM (about one leg in 600) or the queue has run dry (every 32 photons): the
+//               reference's full collision test, hit output, and the queue refill by all 32
+//               lanes at once (photon creation: wavelength table search, Cherenkov cone, the
+//               wavelength-only transcendental factors of the ice model, lifetime).
 //    Batching the rare work this way keeps its cost per photon small and, more importantly,
 //    keeps it from diverging the hot loop on almost every iteration.
+//  * A photon carries a 3-word BIRTH TAG (creation-stream state, step index, creating lane)
+//    instead of its 10-word start-of-flight record: one photon in a thousand is detected, and for
+//    those the record is re-created from the tag (creation is deterministic).
 //  * Two MWC streams per lane (multipliers from the safe-prime table): one drives creation, one
 //    drives propagation, so a photon's propagation draws are contiguous in its stream and any
 //    photon can be replayed by a checker from two recorded states.

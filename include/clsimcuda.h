@@ -287,6 +287,11 @@ int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
  * Parallel to the last result of clsimcu_download_resident; x and a have room for 2*cap entries. */
 int clsimcu_download_resident_rng_tags(clsimcu_engine *engine, uint64_t *x, uint32_t *a, size_t cap);
 
+/* Number of usable CUDA devices (reference: I3CLSimOpenCLDevice::GetAllDevices,
+ * private/opencl/I3CLSimOpenCLDevice.cxx, as used by python/traysegments/common.py:10-77).
+ * 0 devices is an error: there is no CPU fallback. */
+int clsimcu_device_count(int *count);
+
 const char *clsimcu_last_error(void);
 const char *clsimcu_version(void);
 size_t clsimcu_sizeof_config(void);

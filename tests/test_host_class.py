@@ -105,3 +105,25 @@ def test_cxx_converter_on_the_device(binary):
     print(res.stdout)
     assert res.returncode == 0, res.stdout
     assert "0 failed" in res.stdout
+
+
+SERVER_BINARY = os.path.join(ROOT, "clsim_b200", "host", "build", "test_server_inprocess")
+
+
+def test_server_seam_with_dummy_converters(binary):
+    """resources/tests/testCLSimServer.py restated in C++ (DummyConverter, three clients, results matched by
+    identifier), plus the bunch-size harmonisation of I3CLSimServer.cxx:95-113.  No device needed."""
+    res = subprocess.run([SERVER_BINARY], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout
+    assert "0 failed" in res.stdout
+
+
+@pytest.mark.gpu
+def test_server_seam_on_devices(binary):
+    """Two CUDA converters behind one in-process server (one per device; on a 1-GPU box both on device 0), three
+    clients; photon conservation through the summed statistics."""
+    res = subprocess.run([SERVER_BINARY, "--gpu", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout
+    assert "0 failed" in res.stdout
