@@ -68,7 +68,11 @@ namespace {
 #ifndef CLSIMCU_IDLE_LIMIT_SAVE_ALL
 #define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
 #endif
+#ifndef CLSIMCU_REFILL_BATCH
+#define CLSIMCU_REFILL_BATCH 4
+#endif
 constexpr int kThreads = CLSIMCU_THREADS;
+constexpr int kRefillBatch = CLSIMCU_REFILL_BATCH;            // lanes without a photon that make the warp stop for a refill
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
 constexpr int kIdleLimit = CLSIMCU_IDLE_LIMIT;                  // parked lanes (possible DOM contact) that end a fast phase
@@ -651,6 +655,40 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(cons
     if (ANISO) st[kInvAniso * kThreads] = L.inv_aniso;
 }
 
+// Second look at a leg the 2-D cylinder test could not rule out, still in the hot loop (one leg in ~600 gets here,
+// four in five of them leave again): the part of the leg inside the cylinder around string `who` covers a short
+// range in z; only if a DOM of that string sits within om_radius of that range can the leg touch it.  Every DOM
+// lies wholly inside its z-layer of the string's set (the table builder guarantees it), so the layers the range
+// covers name the candidates.  Conservative: the margins cover the rounding of the approximate root.
+__device__ __noinline__ bool dom_within_reach(const DevScene *scene, int who, float z, float dz, float travel, float t, float dxy2, float out2)
+{
+    const SmemPlan sp = table_plan(reinterpret_cast<const SmemHeader *>(smem_base())->lay);
+    const DevGeometry &geo = scene->geo;
+    float s0 = 0.f, s1 = travel, slack = 0.01f;
+    if (dxy2 > 1e-12f) {
+        const float inv = mufu_rcp(dxy2);
+        const float sq = mufu_sqrt(fmaxf(fmaf(t, t, -dxy2 * out2), 0.f));
+        s0 = fmaxf((t - sq) * inv, 0.f);
+        s1 = fminf((t + sq) * inv, travel);
+        slack = fmaf(5e-4f * inv, fabsf(t * dz), 0.01f);
+        if (s0 > s1 + slack) return false;
+    }
+    const float za = fmaf(dz, s0, z), zb = fmaf(dz, s1, z);
+    const float zlo = fminf(za, zb) - slack, zhi = fmaxf(za, zb) + slack;
+    const float4 set = sp.sets[sp.string_set[who]];
+    const int nl = static_cast<int>(set.z);
+    const int la = min(max(__float2int_rd((zlo - set.x) * set.y), 0), nl - 1), lb = min(max(__float2int_rd((zhi - set.x) * set.y), 0), nl - 1);
+    const uint16_t *row = sp.layer_to_dom + static_cast<int>(set.w);
+    const uint32_t first = __ldg(geo.string_tmpl_start + who);
+    for (int l = la; l <= lb; ++l) {
+        const int dom = row[l];
+        if (dom == 0xFFFF) continue;
+        const float zd = __ldg(geo.tmpl_z + first + static_cast<uint32_t>(dom));
+        if ((zd >= zlo - geo.om_radius) && (zd <= zhi + geo.om_radius)) return true;
+    }
+    return false;
+}
+
 // The part of an iteration that decides where the photon goes next: the event that ends this leg
 // of the flight (scatter / absorption inside the current ice layer, the layer boundary, or the
 // range limit of the collision map) and what is left of the two budgets afterwards.
@@ -713,8 +751,8 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
 // and either ends the photon there or sends the lane back with status kCleared, which lets
 // exactly this leg through.
 template <bool TILT, bool ANISO, bool SAVE_ALL>
-__device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const float4 *layers, const float2 *bounds,
-                                               const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st)
+__device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
+                                               const float2 *bounds, const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st)
 {
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
@@ -761,10 +799,15 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
                 if (g.travel > 20.f) atomicAdd(dbg.stats + 6, 1ull);             // ... long legs
             }
 #endif
-            L.status = kFrozen;
-            st[kPendTravel * kThreads] = g.travel;
-            st[kPendWho * kThreads] = __int_as_float(g.walk ? -1 : g.who);
-            return;
+#ifndef CLSIMCU_NO_Z_PRETEST
+            if (g.walk || dom_within_reach(scene_dev, g.who, L.pos.z, L.dir.z, g.travel, t, dxy2, out2))
+#endif
+            {
+                L.status = kFrozen;
+                st[kPendTravel * kThreads] = g.travel;
+                st[kPendWho * kThreads] = __int_as_float(g.walk ? -1 : g.who);
+                return;
+            }
         }
         cleared = false;
     }
@@ -1091,22 +1134,27 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             if (idle != 0u) {
                 const unsigned dead = __ballot_sync(0xffffffffu, L.status == kDead);
                 uint32_t n_dead = __popc(dead);
-                if (n_dead > 0u && queued > 0u) {
-                    const uint32_t rank = __popc(dead & lanemask_lt());
-                    if (L.status == kDead && rank < queued) {
-                        flights += L.scatters + 1u;
-                        take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
+                const int n_waiting = __popc(idle & ~dead);    // parked (or, save-all, ended) lanes: the slow phase's business
+                // Lanes without a photon are served in batches: taking a photon costs the whole warp some
+                // fifty instructions however many lanes take one, an idle lane costs 1/32 of an iteration.
+                if (n_dead >= static_cast<uint32_t>(kRefillBatch) || n_waiting > 0 || idle == 0xffffffffu) {
+                    if (n_dead > 0u && queued > 0u) {
+                        const uint32_t rank = __popc(dead & lanemask_lt());
+                        if (L.status == kDead && rank < queued) {
+                            flights += L.scatters + 1u;
+                            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
+                        }
+                        const uint32_t taken = min(n_dead, queued);
+                        queued -= taken;
+                        n_dead -= taken;
                     }
-                    const uint32_t taken = min(n_dead, queued);
-                    queued -= taken;
-                    n_dead -= taken;
+                    // lanes left without a photon: the slow phase refills the queue (unless the work has run out)
+                    if (n_dead > 0u && more) break;
+                    if (n_waiting + static_cast<int>(n_dead) >= limit) break;
                 }
-                // lanes left without a photon: the slow phase refills the queue (unless the work has run out)
-                if (n_dead > 0u && more) break;
-                if (__popc(idle & ~dead) + static_cast<int>(n_dead) >= limit) break;
             }
             if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL>(L, cleared, scene, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st);
+                advance_photon<TILT, ANISO, SAVE_ALL>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st);
         }
         if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);

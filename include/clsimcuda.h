@@ -229,6 +229,9 @@ typedef struct clsimcu_result {
     uint64_t num_photons_generated; /* sum of step.num_photons of the bunch */
     uint64_t num_hits_counted;   /* device counter; > num_photons means truncated (…OpenCL.cxx:1027-1032) */
     void *opaque;
+    /* photon -> MCPE conversion on the device (clsimcu_attach_mcpe_converter below); NULL / 0 otherwise */
+    struct clsimcu_mcpe *mcpes;
+    size_t num_mcpes;
 } clsimcu_result;
 int clsimcu_get_result(clsimcu_engine *engine, clsimcu_result *result);
 int clsimcu_release_result(clsimcu_engine *engine, clsimcu_result *result);
@@ -286,6 +289,79 @@ int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
  *   x[2*i+1] state of the propagation stream when the photon started,      a[2*i+1] its multiplier.
  * Parallel to the last result of clsimcu_download_resident; x and a have room for 2*cap entries. */
 int clsimcu_download_resident_rng_tags(clsimcu_engine *engine, uint64_t *x, uint32_t *a, size_t cap);
+
+/* ---- photon -> MCPE on the device -------------------------- */
+
+/* One photo-electron: I3MCPE(ParticleID, npe, time) (simclasses/I3MCPE.h as used at
+ * private/clsim/dom/I3PhotonToMCPEConverter.cxx:521, 668) together with the OMKey of the
+ * series it belongs to.  `identifier` is the step identifier of the photon; the caller maps
+ * it to the particle's major/minor ID (private/clsim/I3CLSimClientModule.cxx:385-412). */
+typedef struct clsimcu_mcpe {
+    int16_t string_id;
+    uint16_t om_id;
+    float time;
+    uint32_t npe;
+    uint32_t identifier;
+} clsimcu_mcpe;
+
+/* CLSIMCU_MCPE_INLOOP: I3CLSimPhotonToMCPEConverterForDOMs::Convert
+ *   (private/clsim/dom/I3PhotonToMCPEConverter.cxx:602-669): p = weight * acceptance[OM](wavelength)
+ *   * angular(-dir.z); the photon position (relative to the DOM) must lie within 3 cm of the
+ *   165.1 mm sphere; time unchanged.
+ * CLSIMCU_MCPE_MODULE: I3PhotonToMCPEConverter::Convert (…cxx:395-523): cos = -(dir . dom_dir),
+ *   p = weight * acceptance(wavelength) * angular(cos) * efficiency[OM]; position check only for
+ *   pancake_factor == 1 against dom_radius * oversize_factor; time += (p . dir) * (1 - pancake /
+ *   oversize) / groupVelocity with p = DOM centre - photon position.
+ * Both: weight < 0 and p > 1 are fatal in the reference and are errors here; weight == 0 is
+ * skipped; the photon survives when p > u, u uniform in [0,1). */
+#define CLSIMCU_MCPE_INLOOP 0
+#define CLSIMCU_MCPE_MODULE 1
+typedef struct clsimcu_mcpe_config {
+    int32_t struct_size;          /* sizeof(clsimcu_mcpe_config) */
+    int32_t device;
+    int32_t flavour;              /* CLSIMCU_MCPE_* */
+    int32_t num_acceptances;      /* wavelength acceptance curves (I3CLSimFunctionFromTable / Constant) */
+    const clsimcu_wlen_bias *acceptances;
+    int32_t num_doms;
+    int32_t num_angular_coefficients;
+    const int32_t *string_id;     /* [num_doms] */
+    const uint32_t *dom_id;       /* [num_doms] */
+    const uint8_t *acceptance_of_dom;    /* [num_doms] index into acceptances; NULL = all 0 */
+    const double *efficiency_of_dom;     /* [num_doms] MODULE: relative DOM efficiency x SPE compensation; NULL = all 1 */
+    const double *angular_coefficients;  /* I3CLSimFunctionPolynomial(coefficients), argument cos(angle) */
+    double dom_dir[3];            /* MODULE: PMT axis, (0,0,-1) for IceCube */
+    double dom_radius;            /* without oversize (165.1 mm) */
+    double oversize_factor, pancake_factor;
+    int32_t only_warn_about_positions;   /* OnlyWarnAboutInvalidPhotonPositions */
+    int32_t reserved0;
+    /* MWC streams of the thinning draws: rows [rng_first_multiplier, +num streams) of the
+       safe-prime table, states drawn from rng_seed like clsimcu_config's */
+    uint64_t rng_seed;
+    uint64_t rng_first_multiplier;
+} clsimcu_mcpe_config;
+
+typedef struct clsimcu_mcpe_converter clsimcu_mcpe_converter;
+
+int clsimcu_mcpe_create(const clsimcu_mcpe_config *config, clsimcu_mcpe_converter **converter);
+int clsimcu_mcpe_destroy(clsimcu_mcpe_converter *converter);
+
+/* Converts a photon series held in HOST memory (copies in, one kernel, copies out).  uniforms:
+ * NULL = the converter's MWC streams; else one explicit draw per photon (test hook: makes the
+ * survivors a pure function of the inputs).  Survivors are written in photon order; *n_out may
+ * exceed cap (then only cap records were written). */
+int clsimcu_mcpe_convert(clsimcu_mcpe_converter *converter, const clsimcu_photon *photons, size_t n, const float *uniforms,
+                         clsimcu_mcpe *out, size_t cap, size_t *n_out);
+
+/* Number of MWC streams of a converter and its states (test hook: photon j is thinned with
+ * draw number j / streams of stream j % streams). */
+int clsimcu_mcpe_rng_get(clsimcu_mcpe_converter *converter, uint64_t *x, uint32_t *a, size_t cap, size_t *streams);
+
+/* Runs the conversion on the engine's stream right after every propagation launch, on the hits
+ * while they are still in HBM: results then carry `mcpes` (and, unless keep_photons, no photons:
+ * 16 bytes per surviving photo-electron cross PCIe instead of 80 per photon; the docs ask for
+ * exactly this, resources/docs/clsim_server_worklist.txt:85-124).  Call before the first
+ * clsimcu_enqueue; the converter must outlive the engine and be on the same device. */
+int clsimcu_attach_mcpe_converter(clsimcu_engine *engine, clsimcu_mcpe_converter *converter, int keep_photons);
 
 /* Number of usable CUDA devices (reference: I3CLSimOpenCLDevice::GetAllDevices,
  * private/opencl/I3CLSimOpenCLDevice.cxx, as used by python/traysegments/common.py:10-77).
