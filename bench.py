@@ -257,20 +257,26 @@ def main():
     for i in range(2):
         eng.get_result()
     barrier()
+    stats0 = eng.statistics()
     t0 = time.perf_counter()
     e2e_hits = 0
     pending = 0
+    timeline = []  # (what, ms since t0): where the host side spends the end-to-end time
     for i in range(args.steps):
         eng.enqueue(bunch, 100 + i)  # blocks when 5 bunches are queued, like the reference
+        timeline.append(("enq", round(1e3 * (time.perf_counter() - t0), 1)))
         pending += 1
         while eng.more_photons_available():
             e2e_hits += len(eng.get_result().photons)
+            timeline.append(("res", round(1e3 * (time.perf_counter() - t0), 1)))
             pending -= 1
     while pending:
         e2e_hits += len(eng.get_result().photons)
+        timeline.append(("res", round(1e3 * (time.perf_counter() - t0), 1)))
         pending -= 1
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_kernel_ms = (eng.statistics()["TotalDeviceTime"] - stats0["TotalDeviceTime"]) * 1e-6
     barrier()
     clocks = sampler.stop()
     e2e_value = sum_over_ranks(float(bunch["num_photons"].sum()) * args.steps) / e2e_s
@@ -311,7 +317,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(n * 48),
                 "d2h_bytes_per_step": int(e2e_hits / max(1, args.steps) * 80 + 8),
                 "api": "clsimcu_enqueue/clsimcu_get_result (EnqueueSteps/GetConversionResult), double buffering on",
-                "device_utilization": stats["DeviceUtilization"]},
+                "kernel_ms_per_step": e2e_kernel_ms / max(1, args.steps), "wall_ms": e2e_s * 1e3, "timeline_ms": timeline},
         "gpu_launches": args.steps,
         "roofline": roofline,
         "clocks": clocks,

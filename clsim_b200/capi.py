@@ -25,6 +25,7 @@ SYMBOLS = [
     "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
     "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
     "clsimcu_sizeof_config", "clsimcu_device_count",
+    "clsimcu_mcpe_create", "clsimcu_mcpe_destroy", "clsimcu_mcpe_convert", "clsimcu_mcpe_rng_get", "clsimcu_attach_mcpe_converter",
 ]
 
 STAT_KEYS = ["TotalDeviceTime", "TotalHostTime", "NumKernelCalls", "TotalNumPhotonsGenerated", "TotalNumPhotonsAtDOMs",
@@ -106,7 +107,7 @@ def describe_tables(medium, geometry, wlen_generators, wlen_bias, options):
 
 
 class Result(object):
-    __slots__ = ("identifier", "photons", "history", "num_photons_generated", "num_hits_counted")
+    __slots__ = ("identifier", "photons", "history", "num_photons_generated", "num_hits_counted", "mcpes")
 
 
 class Engine(object):
@@ -158,6 +159,11 @@ class Engine(object):
                 out.history = np.zeros((0, self.history_entries, 4), dtype=np.float32)
         out.num_photons_generated = int(r.num_photons_generated)
         out.num_hits_counted = int(r.num_hits_counted)
+        out.mcpes = None
+        if getattr(self, "_mcpe", None) is not None:
+            from .mcpe import MCPE_DTYPE
+            m = int(r.num_mcpes)
+            out.mcpes = np.frombuffer(C.string_at(r.mcpes, m * 16), dtype=MCPE_DTYPE).copy() if m else np.zeros(0, dtype=MCPE_DTYPE)
         _check(lib().clsimcu_release_result(self._h, C.byref(r)))
         return out
 

@@ -33,6 +33,7 @@
 
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
+#include "mcpe.h"
 #include "tables.h"
 
 namespace clsimcu {
@@ -70,6 +71,15 @@ public:
         not_empty_.notify_one();
         return true;
     }
+    bool try_get(T &out)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
     bool get(T &out)
     {
         std::unique_lock<std::mutex> lk(m_);
@@ -102,27 +112,35 @@ private:
     bool closed_ = false;
 };
 
+// A bunch on its way to the device: the caller's steps were copied ONCE, straight into a pinned staging
+// buffer (index `staging` of the engine's pool), from where the copy engine takes them.
 struct Bunch {
     uint32_t identifier = 0;
-    std::vector<clsimcu_step> steps;
+    int staging = -1;
+    size_t num_steps = 0;
+    uint64_t generated = 0;
 };
 
 struct HostResult {
     uint32_t identifier = 0;
     std::vector<clsimcu_photon> photons;
     std::vector<float> history;
+    std::vector<clsimcu_mcpe> mcpes;
     uint64_t generated = 0, counted = 0;
 };
 
 struct Slot {
     int index = 0;
     cudaStream_t xfer = nullptr;
-    cudaEvent_t uploaded = nullptr, k_start = nullptr, k_stop = nullptr, counted = nullptr;
-    clsimcu_step *d_steps = nullptr, *h_steps = nullptr;
+    cudaEvent_t uploaded = nullptr, k_start = nullptr, k_stop = nullptr, counted = nullptr, converted = nullptr;
+    clsimcu_step *d_steps = nullptr;
+    int staging = -1;                                               // pinned staging buffer the bunch came in
     clsimcu_photon *d_photons = nullptr, *h_photons = nullptr;
     float *d_history = nullptr, *h_history = nullptr;
     uint32_t *d_counters = nullptr, *h_counters = nullptr;           // [0] hits, [1] work
     unsigned long long *d_stats = nullptr, *h_stats = nullptr;      // [0] photons, [1] segments
+    clsimcu_mcpe *d_mcpes = nullptr, *h_mcpes = nullptr;            // photon -> MCPE conversion attached
+    uint32_t *d_mcpe_counters = nullptr, *h_mcpe_counters = nullptr;
     uint32_t identifier = 0;
     size_t num_steps = 0;
     uint64_t generated = 0;
@@ -171,9 +189,17 @@ struct clsimcu_engine {
     std::vector<Slot> slots;
     BlockingQueue<Bunch> inbox{5};                 // queueToOpenCL_ depth 5 (…OpenCL.cxx:77)
     BlockingQueue<int> free_slots{0}, in_flight{0};
+    // pinned staging buffers for incoming bunches: as many as can be waiting (5) or in a slot, allocated on demand
+    clsimcu_step *staging[16] = {nullptr};      // fixed storage: the submit thread reads entries while enqueue adds new ones
+    size_t staging_count = 0, staging_max = 0;  // guarded by staging_mutex
+    BlockingQueue<int> free_staging{0};
+    std::mutex staging_mutex;
     BlockingQueue<std::shared_ptr<HostResult>> outbox{0};
     std::thread submit_thread, drain_thread;
     std::atomic<bool> stopping{false};
+    std::atomic<bool> enqueued_any{false};
+    clsimcu_mcpe_converter *mcpe = nullptr;        // clsimcu_attach_mcpe_converter
+    bool mcpe_keep_photons = false;
     std::mutex error_mutex;
     std::string async_error;
     // statistics (…OpenCL.h:377-381)
@@ -400,6 +426,12 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     CUDA_OK(cudaMemcpy(e.d_scene, &s, sizeof(DevScene), cudaMemcpyHostToDevice));
 }
 
+} // namespace
+
+int report_error(int code, const std::string &msg) { return fail(code, msg); }
+std::string prime_cache_path();
+std::string prime_cache_file() { return prime_cache_path(); }
+
 std::string prime_cache_path()
 {
     if (const char *p = std::getenv("CLSIMCU_SAFEPRIMES_CACHE")) return p;
@@ -412,6 +444,8 @@ std::string prime_cache_path()
     }
     return std::string();
 }
+
+namespace {
 
 void launch(clsimcu_engine &e, const LaunchArgs &args, cudaStream_t stream)
 {
@@ -431,12 +465,10 @@ void submit_loop(clsimcu_engine *e)
             if (!e->free_slots.get(si)) break;
             Slot &s = e->slots[si];
             s.identifier = bunch.identifier;
-            s.num_steps = bunch.steps.size();
-            uint64_t generated = 0;
-            for (const clsimcu_step &st : bunch.steps) generated += st.num_photons;
-            s.generated = generated;
-            std::memcpy(s.h_steps, bunch.steps.data(), s.num_steps * sizeof(clsimcu_step));
-            CUDA_OK(cudaMemcpyAsync(s.d_steps, s.h_steps, s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
+            s.num_steps = bunch.num_steps;
+            s.generated = bunch.generated;
+            s.staging = bunch.staging;
+            CUDA_OK(cudaMemcpyAsync(s.d_steps, e->staging[bunch.staging], s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
             CUDA_OK(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), s.xfer));
             CUDA_OK(cudaMemsetAsync(s.d_stats, 0, 8 * sizeof(unsigned long long), s.xfer));
             CUDA_OK(cudaEventRecord(s.uploaded, s.xfer));
@@ -461,8 +493,17 @@ void submit_loop(clsimcu_engine *e)
                 a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
                 launch(*e, a, e->compute);
                 CUDA_OK(cudaEventRecord(s.k_stop, e->compute));
+                if (e->mcpe) {
+                    // the hits never leave HBM as photons: thin them to photo-electrons right behind the kernel
+                    CUDA_OK(cudaMemsetAsync(s.d_mcpe_counters, 0, kMcpeCounters * sizeof(uint32_t), e->compute));
+                    McpeLaunch l{s.d_photons, s.d_counters, static_cast<uint32_t>(e->max_hits), nullptr, s.d_mcpes, static_cast<uint32_t>(e->max_hits),
+                                 s.d_mcpe_counters};
+                    mcpe_enqueue(e->mcpe, l, e->compute);
+                    CUDA_OK(cudaEventRecord(s.converted, e->compute));
+                }
             }
-            CUDA_OK(cudaStreamWaitEvent(s.xfer, s.k_stop, 0));
+            CUDA_OK(cudaStreamWaitEvent(s.xfer, e->mcpe ? s.converted : s.k_stop, 0));
+            if (e->mcpe) CUDA_OK(cudaMemcpyAsync(s.h_mcpe_counters, s.d_mcpe_counters, kMcpeCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.xfer));
             CUDA_OK(cudaMemcpyAsync(s.h_counters, s.d_counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.xfer));
             CUDA_OK(cudaEventRecord(s.counted, s.xfer));
             if (!e->in_flight.put(si)) break;
@@ -497,6 +538,8 @@ void drain_loop(clsimcu_engine *e)
         while (e->in_flight.get(si)) {
             Slot &s = e->slots[si];
             CUDA_OK(cudaEventSynchronize(s.counted));
+            e->free_staging.put(s.staging);   // the upload is long done
+            s.staging = -1;
             const auto now = std::chrono::steady_clock::now();
             float k_ms = 0.f;
             CUDA_OK(cudaEventElapsedTime(&k_ms, s.k_start, s.k_stop));
@@ -508,7 +551,18 @@ void drain_loop(clsimcu_engine *e)
             res->identifier = s.identifier;
             res->generated = s.generated;
             res->counted = counted;
-            if (n > 0) {
+            size_t n_pe = 0;
+            if (e->mcpe) {
+                const std::string bad = mcpe_error_text(e->mcpe, s.h_mcpe_counters);
+                if (!bad.empty()) throw std::runtime_error(bad);
+                n_pe = std::min<size_t>(s.h_mcpe_counters[kMcpeSurvivors], e->max_hits);
+                if (n_pe > 0) {
+                    CUDA_OK(cudaMemcpyAsync(s.h_mcpes, s.d_mcpes, n_pe * sizeof(clsimcu_mcpe), cudaMemcpyDeviceToHost, s.xfer));
+                    CUDA_OK(cudaStreamSynchronize(s.xfer));
+                    res->mcpes.assign(s.h_mcpes, s.h_mcpes + n_pe);
+                }
+            }
+            if (n > 0 && (!e->mcpe || e->mcpe_keep_photons)) {
                 CUDA_OK(cudaMemcpyAsync(s.h_photons, s.d_photons, n * sizeof(clsimcu_photon), cudaMemcpyDeviceToHost, s.xfer));
                 if (e->history_entries > 0)
                     CUDA_OK(cudaMemcpyAsync(s.h_history, s.d_history, n * e->history_entries * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.xfer));
@@ -540,13 +594,16 @@ void free_engine(clsimcu_engine *e)
     for (Slot &s : e->slots) {
         if (s.xfer) cudaStreamSynchronize(s.xfer);
         cudaFree(s.d_steps); cudaFree(s.d_photons); cudaFree(s.d_history); cudaFree(s.d_counters); cudaFree(s.d_stats);
-        cudaFreeHost(s.h_steps); cudaFreeHost(s.h_photons); cudaFreeHost(s.h_history); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_stats);
+        cudaFreeHost(s.h_photons); cudaFreeHost(s.h_history); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_stats);
+        cudaFree(s.d_mcpes); cudaFree(s.d_mcpe_counters); cudaFreeHost(s.h_mcpes); cudaFreeHost(s.h_mcpe_counters);
+        if (s.converted) cudaEventDestroy(s.converted);
         if (s.uploaded) cudaEventDestroy(s.uploaded);
         if (s.k_start) cudaEventDestroy(s.k_start);
         if (s.k_stop) cudaEventDestroy(s.k_stop);
         if (s.counted) cudaEventDestroy(s.counted);
         if (s.xfer) cudaStreamDestroy(s.xfer);
     }
+    for (clsimcu_step *b : e->staging) cudaFreeHost(b);
     cudaFree(e->d_arena); cudaFree(e->d_scene); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
     cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
     cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush);
@@ -667,11 +724,11 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
             CUDA_OK(cudaEventCreate(&s.k_start));
             CUDA_OK(cudaEventCreate(&s.k_stop));
             CUDA_OK(cudaEventCreate(&s.counted));
+            CUDA_OK(cudaEventCreate(&s.converted));
             CUDA_OK(cudaMalloc(&s.d_steps, e->max_items * sizeof(clsimcu_step)));
             CUDA_OK(cudaMalloc(&s.d_photons, e->max_hits * sizeof(clsimcu_photon)));
             CUDA_OK(cudaMalloc(&s.d_counters, 2 * sizeof(uint32_t)));
             CUDA_OK(cudaMalloc(&s.d_stats, 8 * sizeof(unsigned long long)));
-            CUDA_OK(cudaHostAlloc(&s.h_steps, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&s.h_photons, e->max_hits * sizeof(clsimcu_photon), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&s.h_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&s.h_stats, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -682,6 +739,7 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
             }
             e->free_slots.put(i);
         }
+        e->staging_max = 5 + static_cast<size_t>(nslots);
         e->last_stamp = std::chrono::steady_clock::now();
         e->submit_thread = std::thread(submit_loop, e);
         e->drain_thread = std::thread(drain_loop, e);
@@ -704,6 +762,7 @@ int clsimcu_destroy(clsimcu_engine *e)
     e->stopping = true;
     e->inbox.close();
     e->free_slots.close();
+    e->free_staging.close();
     if (e->submit_thread.joinable()) e->submit_thread.join();
     e->in_flight.close();
     if (e->drain_thread.joinable()) e->drain_thread.join();
@@ -722,9 +781,26 @@ int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint
     if (n == 0) return fail(CLSIMCU_ERR_INVALID, "Steps are empty!");
     if (n > e->max_items) return fail(CLSIMCU_ERR_INVALID, "Number of steps is greater than maximum number of work items!");
     if (n % e->granularity != 0) return fail(CLSIMCU_ERR_INVALID, "The number of steps is not a multiple of the workgroup size!");
+    e->enqueued_any = true;
     Bunch b;
     b.identifier = identifier;
-    b.steps.assign(steps, steps + n);
+    b.num_steps = n;
+    // a staging buffer: a free one, a new one while the pool may grow, else wait for one to come back
+    if (!e->free_staging.try_get(b.staging)) {
+        std::unique_lock<std::mutex> lk(e->staging_mutex);
+        if (e->staging_count < e->staging_max) {
+            clsimcu_step *buf = nullptr;
+            if (cudaSetDevice(e->device) != cudaSuccess || cudaHostAlloc(&buf, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault) != cudaSuccess)
+                return fail(CLSIMCU_ERR_CUDA, std::string("cudaHostAlloc of a staging buffer: ") + cudaGetErrorString(cudaGetLastError()));
+            e->staging[e->staging_count] = buf;
+            b.staging = static_cast<int>(e->staging_count++);
+        } else {
+            lk.unlock();
+            if (!e->free_staging.get(b.staging)) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+        }
+    }
+    std::memcpy(e->staging[b.staging], steps, n * sizeof(clsimcu_step));
+    for (size_t i = 0; i < n; ++i) b.generated += steps[i].num_photons;
     if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
     return CLSIMCU_OK;
 }
@@ -749,6 +825,8 @@ int clsimcu_get_result(clsimcu_engine *e, clsimcu_result *r)
     r->num_photons_generated = res->generated;
     r->num_hits_counted = res->counted;
     r->opaque = holder;
+    r->mcpes = res->mcpes.empty() ? nullptr : res->mcpes.data();
+    r->num_mcpes = res->mcpes.size();
     return CLSIMCU_OK;
 }
 
@@ -757,6 +835,29 @@ int clsimcu_release_result(clsimcu_engine *, clsimcu_result *r)
     if (!r) return fail(CLSIMCU_ERR_INVALID, "result pointer is NULL");
     delete static_cast<std::shared_ptr<HostResult> *>(r->opaque);
     std::memset(r, 0, sizeof *r);
+    return CLSIMCU_OK;
+}
+
+int clsimcu_attach_mcpe_converter(clsimcu_engine *e, clsimcu_mcpe_converter *c, int keep_photons)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    if (!c) return fail(CLSIMCU_ERR_INVALID, "MCPE converter is NULL");
+    if (e->enqueued_any || e->mcpe) return fail(CLSIMCU_ERR_STATE, "the MCPE converter must be attached once, before the first EnqueueSteps");
+    if (mcpe_device(c) != e->device) return fail(CLSIMCU_ERR_INVALID, "the MCPE converter lives on another device than the engine");
+    if (e->save_all) return fail(CLSIMCU_ERR_INVALID, "saveAllPhotons records photons that are on no DOM: they cannot be converted to MCPEs");
+    try {
+        CUDA_OK(cudaSetDevice(e->device));
+        for (Slot &s : e->slots) {
+            CUDA_OK(cudaMalloc(&s.d_mcpes, e->max_hits * sizeof(clsimcu_mcpe)));
+            CUDA_OK(cudaMalloc(&s.d_mcpe_counters, kMcpeCounters * sizeof(uint32_t)));
+            CUDA_OK(cudaHostAlloc(&s.h_mcpes, e->max_hits * sizeof(clsimcu_mcpe), cudaHostAllocDefault));
+            CUDA_OK(cudaHostAlloc(&s.h_mcpe_counters, kMcpeCounters * sizeof(uint32_t), cudaHostAllocDefault));
+        }
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    e->mcpe_keep_photons = keep_photons != 0;
+    e->mcpe = c;   // read by the submit thread only after a bunch has been enqueued (queue hand-off orders it)
     return CLSIMCU_OK;
 }
 

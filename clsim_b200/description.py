@@ -104,6 +104,7 @@ class ResultStruct(C.Structure):
         ("identifier", C.c_uint32), ("reserved0", C.c_uint32), ("num_photons", C.c_size_t),
         ("photons", C.c_void_p), ("history", C.POINTER(C.c_float)),
         ("num_photons_generated", C.c_uint64), ("num_hits_counted", C.c_uint64), ("opaque", C.c_void_p),
+        ("mcpes", C.c_void_p), ("num_mcpes", C.c_size_t),
     ]
 
 

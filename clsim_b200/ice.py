@@ -198,12 +198,29 @@ def MakeHomogeneousIceMediumProperties(iceDataDirectory="spice_mie", atZ=0.0, de
     return m
 
 
-def GetIceCubeDOMAcceptance(domRadius=0.16510, efficiency=1.0):
+def GetIceCubeDOMAcceptance(domRadius=0.16510, efficiency=1.0, highQE=False, highQERatio=None):
     """Wavelength acceptance of the IceCube DOM as a 43-entry table starting at 260 nm in
-    10 nm steps, normalised to the DOM cross-section."""
+    10 nm steps, normalised to the DOM cross-section (python/GetIceCubeDOMAcceptance.py:36-135).
+
+    highQE multiplies by the wavelength-dependent relative efficiency of the DeepCore PMTs.  The reference
+    reads it from ice-models' wv.rde (python/GetIceCubeDOMAcceptance.py:128-130), which is not part of its
+    tree: pass the two columns as highQERatio=(wavelengths [nm], ratio)."""
     eff_area = np.array(_packaged()["_dom2007a_eff_area"], dtype=float)
     dom_area = math.pi * domRadius ** 2.0
-    return WlenBias(values=efficiency * (eff_area / dom_area), start_wlen=260.0 * NANOMETER, wlen_step=10.0 * NANOMETER)
+    values = efficiency * (eff_area / dom_area)
+    if highQE:
+        if highQERatio is None:
+            raise RuntimeError("highQE needs the wv.rde table of ice-models (not vendored by the reference): pass highQERatio=(wv_nm, rde)")
+        wv, rde = highQERatio
+        values = values * np.interp(260 + 10 * np.arange(len(values)), np.asarray(wv, dtype=float), np.asarray(rde, dtype=float))
+    return WlenBias(values=values, start_wlen=260.0 * NANOMETER, wlen_step=10.0 * NANOMETER)
+
+
+def envelope(functions):
+    """Point-wise maximum of acceptance tables on one grid: the generation bias when DOM types differ
+    (python/traysegments/common.py:191)."""
+    first = functions[0]
+    return WlenBias(values=np.max([f.values for f in functions], axis=0), start_wlen=first.start_wlen, wlen_step=first.wlen_step)
 
 
 def GetFlasherLED405Spectrum():

@@ -260,6 +260,29 @@ def main():
     with open(os.path.join(HERE, "flasher_405nm.json"), "w") as f:
         json.dump(ice_data["_flasher_led_405nm"], f)
 
+    # hole-ice angular acceptance (python/GetIceCubeDOMAngularSensitivity.py:30-42): the reference's function,
+    # through the stubs, on the one parameterisation file its tree ships (ice-models is un-vendored); row 0 of
+    # the file is the peak value the tray segment folds into the DOM efficiency (traysegments/common.py:183-184)
+    GetAngular = importlib.import_module("clsim_ref.GetIceCubeDOMAngularSensitivity").GetIceCubeDOMAngularSensitivity
+    as_file = os.path.join(REF, "resources", "ice", "ppc_aha_0.80", "as.holeice")
+    ang = GetAngular(holeIce=as_file)
+    assert ang._cls == "I3CLSimFunctionPolynomial"
+    angular = {"source": os.path.relpath(as_file, REF), "peak": float(numpy.loadtxt(as_file)[0]), "coefficients": _floats(ang.args[0])}
+    # known answers: the polynomial as I3CLSimFunctionPolynomial::GetValue sums it (…Polynomial.cxx:86-102)
+    xs = numpy.linspace(-1.0, 1.0, 41)
+    vals = []
+    for x in xs:
+        total, mult = angular["coefficients"][0], 1.0
+        for c in angular["coefficients"][1:]:
+            mult *= x
+            total += c * mult
+        vals.append(total)
+    angular["cos"] = _floats(xs)
+    angular["value"] = _floats(vals)
+    with open(os.path.join(HERE, "angular_acceptance.json"), "w") as f:
+        json.dump(angular, f)
+    ice_data["_angsens_holeice"] = {"peak": angular["peak"], "coefficients": angular["coefficients"]}
+
     os.makedirs(os.path.join(REPO, "clsim_b200", "data"), exist_ok=True)
     with open(os.path.join(REPO, "clsim_b200", "data", "ice_models.json"), "w") as f:
         json.dump(ice_data, f)
