@@ -147,7 +147,8 @@ class Engine(object):
         out.identifier = int(r.identifier)
         n = int(r.num_photons)
         if n:
-            out.photons = np.frombuffer(C.string_at(r.photons, n * PHOTON_DTYPE.itemsize), dtype=PHOTON_DTYPE).copy()
+            # one copy out of the library's buffer (released below)
+            out.photons = np.frombuffer((C.c_char * (n * PHOTON_DTYPE.itemsize)).from_address(r.photons), dtype=PHOTON_DTYPE).copy()
         else:
             out.photons = np.zeros(0, dtype=PHOTON_DTYPE)
         out.history = None
