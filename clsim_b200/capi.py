@@ -26,6 +26,7 @@ SYMBOLS = [
     "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
     "clsimcu_sizeof_config", "clsimcu_device_count",
     "clsimcu_mcpe_create", "clsimcu_mcpe_destroy", "clsimcu_mcpe_convert", "clsimcu_mcpe_rng_get", "clsimcu_attach_mcpe_converter",
+    "clsimcu_stepgen_create", "clsimcu_stepgen_destroy", "clsimcu_stepgen_generate", "clsimcu_stepgen_rng_get", "clsimcu_enqueue_sources",
 ]
 
 STAT_KEYS = ["TotalDeviceTime", "TotalHostTime", "NumKernelCalls", "TotalNumPhotonsGenerated", "TotalNumPhotonsAtDOMs",

@@ -34,6 +34,7 @@
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
 #include "mcpe.h"
+#include "stepgen.h"
 #include "tables.h"
 
 namespace clsimcu {
@@ -119,6 +120,10 @@ struct Bunch {
     int staging = -1;
     size_t num_steps = 0;
     uint64_t generated = 0;
+    // steps still to be made on the device (clsimcu_enqueue_sources): the staging buffer holds num_sources queue
+    // entries followed by num_sources + 1 first-step indices
+    clsimcu_step_generator *generator = nullptr;
+    size_t num_sources = 0;
 };
 
 struct HostResult {
@@ -134,6 +139,7 @@ struct Slot {
     cudaStream_t xfer = nullptr;
     cudaEvent_t uploaded = nullptr, k_start = nullptr, k_stop = nullptr, counted = nullptr, converted = nullptr;
     clsimcu_step *d_steps = nullptr;
+    uint8_t *d_sources = nullptr;                                   // queue entries + first-step indices of a generated bunch
     int staging = -1;                                               // pinned staging buffer the bunch came in
     clsimcu_photon *d_photons = nullptr, *h_photons = nullptr;
     float *d_history = nullptr, *h_history = nullptr;
@@ -468,13 +474,26 @@ void submit_loop(clsimcu_engine *e)
             s.num_steps = bunch.num_steps;
             s.generated = bunch.generated;
             s.staging = bunch.staging;
-            CUDA_OK(cudaMemcpyAsync(s.d_steps, e->staging[bunch.staging], s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
+            const size_t source_bytes = (bunch.num_sources * sizeof(clsimcu_step_source) + 15) & ~size_t(15);
+            if (bunch.generator) {
+                if (!s.d_sources) CUDA_OK(cudaMalloc(&s.d_sources, kMaxSourcesPerBunch * (sizeof(clsimcu_step_source) + sizeof(uint64_t)) + 64));
+                CUDA_OK(cudaMemcpyAsync(s.d_sources, e->staging[bunch.staging], source_bytes + (bunch.num_sources + 1) * sizeof(uint64_t),
+                                        cudaMemcpyHostToDevice, s.xfer));
+            } else {
+                CUDA_OK(cudaMemcpyAsync(s.d_steps, e->staging[bunch.staging], s.num_steps * sizeof(clsimcu_step), cudaMemcpyHostToDevice, s.xfer));
+            }
             CUDA_OK(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), s.xfer));
             CUDA_OK(cudaMemsetAsync(s.d_stats, 0, 8 * sizeof(unsigned long long), s.xfer));
             CUDA_OK(cudaEventRecord(s.uploaded, s.xfer));
             {
                 std::lock_guard<std::mutex> lk(e->compute_mutex);
                 CUDA_OK(cudaStreamWaitEvent(e->compute, s.uploaded, 0));
+                if (bunch.generator) {
+                    // the bunch is made where it is consumed: 48 bytes per step never cross PCIe
+                    StepGenLaunch g{reinterpret_cast<const clsimcu_step_source *>(s.d_sources), reinterpret_cast<const uint64_t *>(s.d_sources + source_bytes),
+                                    static_cast<uint32_t>(bunch.num_sources), s.num_steps, s.d_steps};
+                    stepgen_enqueue(bunch.generator, g, e->compute);
+                }
                 CUDA_OK(cudaEventRecord(s.k_start, e->compute));
                 LaunchArgs a{};
                 a.steps = s.d_steps;
@@ -593,7 +612,7 @@ void free_engine(clsimcu_engine *e)
     cudaSetDevice(e->device);
     for (Slot &s : e->slots) {
         if (s.xfer) cudaStreamSynchronize(s.xfer);
-        cudaFree(s.d_steps); cudaFree(s.d_photons); cudaFree(s.d_history); cudaFree(s.d_counters); cudaFree(s.d_stats);
+        cudaFree(s.d_steps); cudaFree(s.d_sources); cudaFree(s.d_photons); cudaFree(s.d_history); cudaFree(s.d_counters); cudaFree(s.d_stats);
         cudaFreeHost(s.h_photons); cudaFreeHost(s.h_history); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_stats);
         cudaFree(s.d_mcpes); cudaFree(s.d_mcpe_counters); cudaFreeHost(s.h_mcpes); cudaFreeHost(s.h_mcpe_counters);
         if (s.converted) cudaEventDestroy(s.converted);
@@ -771,6 +790,61 @@ int clsimcu_destroy(clsimcu_engine *e)
     return CLSIMCU_OK;
 }
 
+// A pinned staging buffer for an incoming bunch: a free one, a new one while the pool may grow, else wait for
+// one to come back.
+static int acquire_staging(clsimcu_engine *e, int &index)
+{
+    if (e->free_staging.try_get(index)) return CLSIMCU_OK;
+    std::unique_lock<std::mutex> lk(e->staging_mutex);
+    if (e->staging_count < e->staging_max) {
+        clsimcu_step *buf = nullptr;
+        if (cudaSetDevice(e->device) != cudaSuccess || cudaHostAlloc(&buf, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault) != cudaSuccess)
+            return fail(CLSIMCU_ERR_CUDA, std::string("cudaHostAlloc of a staging buffer: ") + cudaGetErrorString(cudaGetLastError()));
+        e->staging[e->staging_count] = buf;
+        index = static_cast<int>(e->staging_count++);
+        return CLSIMCU_OK;
+    }
+    lk.unlock();
+    if (!e->free_staging.get(index)) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    return CLSIMCU_OK;
+}
+
+int clsimcu_enqueue_sources(clsimcu_engine *e, clsimcu_step_generator *g, const clsimcu_step_source *sources, size_t n, uint32_t identifier)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
+    if (!g) return fail(CLSIMCU_ERR_STATE, "I3CLSimLightSourceToStepConverterPPC is not initialized!");
+    std::string err;
+    if (e->check_async_error(err)) return fail(CLSIMCU_ERR_CUDA, err);
+    if (stepgen_device(g) != e->device) return fail(CLSIMCU_ERR_INVALID, "the step generator lives on another device than the engine");
+    if (!sources || n == 0) return fail(CLSIMCU_ERR_INVALID, "Steps are empty!");
+    if (n > kMaxSourcesPerBunch) return fail(CLSIMCU_ERR_INVALID, "more than 65536 step sources in one bunch");
+    std::vector<uint64_t> first;
+    uint64_t photons = 0;
+    const std::string bad = stepgen_layout(sources, n, first, &photons);
+    if (!bad.empty()) return fail(CLSIMCU_ERR_INVALID, bad);
+    const uint64_t total = first[n];
+    // the preconditions of EnqueueSteps (…OpenCL.cxx:1527-1540) on the bunch that will exist on the device
+    if (total == 0) return fail(CLSIMCU_ERR_INVALID, "Steps are empty!");
+    if (total > e->max_items) return fail(CLSIMCU_ERR_INVALID, "Number of steps is greater than maximum number of work items!");
+    if (total % e->granularity != 0) return fail(CLSIMCU_ERR_INVALID, "The number of steps is not a multiple of the workgroup size!");
+    const size_t source_bytes = (n * sizeof(clsimcu_step_source) + 15) & ~size_t(15);
+    if (source_bytes + (n + 1) * sizeof(uint64_t) > e->max_items * sizeof(clsimcu_step))
+        return fail(CLSIMCU_ERR_INVALID, "too many step sources for this engine's staging buffers (raise max_num_workitems)");
+    e->enqueued_any = true;
+    Bunch b;
+    b.identifier = identifier;
+    b.num_steps = total;
+    b.generated = photons;
+    b.generator = g;
+    b.num_sources = n;
+    if (int rc = acquire_staging(e, b.staging)) return rc;
+    uint8_t *dst = reinterpret_cast<uint8_t *>(e->staging[b.staging]);
+    std::memcpy(dst, sources, n * sizeof(clsimcu_step_source));
+    std::memcpy(dst + source_bytes, first.data(), (n + 1) * sizeof(uint64_t));
+    if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    return CLSIMCU_OK;
+}
+
 int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint32_t identifier)
 {
     if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
@@ -785,20 +859,7 @@ int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint
     Bunch b;
     b.identifier = identifier;
     b.num_steps = n;
-    // a staging buffer: a free one, a new one while the pool may grow, else wait for one to come back
-    if (!e->free_staging.try_get(b.staging)) {
-        std::unique_lock<std::mutex> lk(e->staging_mutex);
-        if (e->staging_count < e->staging_max) {
-            clsimcu_step *buf = nullptr;
-            if (cudaSetDevice(e->device) != cudaSuccess || cudaHostAlloc(&buf, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault) != cudaSuccess)
-                return fail(CLSIMCU_ERR_CUDA, std::string("cudaHostAlloc of a staging buffer: ") + cudaGetErrorString(cudaGetLastError()));
-            e->staging[e->staging_count] = buf;
-            b.staging = static_cast<int>(e->staging_count++);
-        } else {
-            lk.unlock();
-            if (!e->free_staging.get(b.staging)) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
-        }
-    }
+    if (int rc = acquire_staging(e, b.staging)) return rc;
     std::memcpy(e->staging[b.staging], steps, n * sizeof(clsimcu_step));
     for (size_t i = 0; i < n; ++i) b.generated += steps[i].num_photons;
     if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");

@@ -363,6 +363,65 @@ int clsimcu_mcpe_rng_get(clsimcu_mcpe_converter *converter, uint64_t *x, uint32_
  * clsimcu_enqueue; the converter must outlive the engine and be on the same device. */
 int clsimcu_attach_mcpe_converter(clsimcu_engine *engine, clsimcu_mcpe_converter *converter, int keep_photons);
 
+/* ---- light source -> steps on the device ---------------------- */
+
+/* One entry of the reference's step generation queue: what EnqueueLightSource leaves behind for
+ * MakeSteps (CascadeStepData_t / MuonStepData_t, public/clsim/I3CLSimLightSourceToStepConverterPPC.h;
+ * filled at private/clsim/I3CLSimLightSourceToStepConverterPPC.cxx:336-366, 437-471).  The yield
+ * (number of photons, hence steps) is the caller's business, exactly as in the reference, where it
+ * needs I3RandomService and sim-services' shower parameterisation; the per-step work -- the part
+ * that scales with the light yield -- is done on the device:
+ *   CLSIMCU_SOURCE_CASCADE             longitudinal position pb * Gamma(pa) [m] along the axis, direction
+ *                                      smeared (…PPC.cxx:523-537, 785-819)
+ *   CLSIMCU_SOURCE_TRACK_CASCADE_LIKE  position uniform in [0, length), direction smeared (…cxx:546-556)
+ *   CLSIMCU_SOURCE_TRACK_MUON_LIKE     one step of the whole length at the vertex (…cxx:557-563, 821-842)
+ * An entry makes num_steps steps of photons_per_step photons plus, if photons_in_last_step > 0, one
+ * more with that many (…cxx:566-607). */
+#define CLSIMCU_SOURCE_CASCADE            0
+#define CLSIMCU_SOURCE_TRACK_CASCADE_LIKE 1
+#define CLSIMCU_SOURCE_TRACK_MUON_LIKE    2
+typedef struct clsimcu_step_source {
+    double x, y, z, t;            /* particle vertex [m], time [ns]     */
+    double dir_x, dir_y, dir_z;   /* direction of travel (unit vector)  */
+    double length;                /* TRACK_*: track length [m]          */
+    double pa, pb;                /* CASCADE: gamma shape, scale [m]    */
+    uint64_t num_steps;
+    uint32_t photons_per_step;
+    uint32_t photons_in_last_step;
+    uint32_t identifier;
+    int32_t kind;                 /* CLSIMCU_SOURCE_* */
+} clsimcu_step_source;
+
+typedef struct clsimcu_step_generator_config {
+    int32_t struct_size;          /* sizeof(clsimcu_step_generator_config) */
+    int32_t device;
+    double angular_a, angular_b;  /* cascade angular smearing, 0.39 and 2.61 in the reference (…PPC.cxx:105) */
+    /* MWC streams, one per generator thread: rows [rng_first_multiplier, +streams) of the safe-prime
+       table, states drawn from rng_seed like clsimcu_config's */
+    uint64_t rng_seed;
+    uint64_t rng_first_multiplier;
+} clsimcu_step_generator_config;
+
+typedef struct clsimcu_step_generator clsimcu_step_generator;
+
+int clsimcu_stepgen_create(const clsimcu_step_generator_config *config, clsimcu_step_generator **generator);
+int clsimcu_stepgen_destroy(clsimcu_step_generator *generator);
+
+/* Makes the steps of n queue entries and copies them to the host: entry after entry, each entry's
+ * partial last step at the end of its run.  *n_out = total number of steps (may exceed cap).  With T
+ * streams, step j draws from stream j % T, the steps of one stream in ascending order
+ * (clsimcu_stepgen_rng_get: test hook for replaying that). */
+int clsimcu_stepgen_generate(clsimcu_step_generator *generator, const clsimcu_step_source *sources, size_t n,
+                             clsimcu_step *out, size_t cap, size_t *n_out);
+int clsimcu_stepgen_rng_get(clsimcu_step_generator *generator, uint64_t *x, uint32_t *a, size_t cap, size_t *streams);
+
+/* EnqueueSteps for steps that do not exist yet: the bunch is generated on the device from the n queue
+ * entries (at most 65536 per bunch) and propagated without ever visiting the host: a few KB go over
+ * PCIe instead of 48 bytes per step.  The total number of steps must respect max_num_workitems and
+ * the workgroup size like clsimcu_enqueue.  Results come back through clsimcu_get_result. */
+int clsimcu_enqueue_sources(clsimcu_engine *engine, clsimcu_step_generator *generator, const clsimcu_step_source *sources,
+                            size_t n, uint32_t identifier);
+
 /* Number of usable CUDA devices (reference: I3CLSimOpenCLDevice::GetAllDevices,
  * private/opencl/I3CLSimOpenCLDevice.cxx, as used by python/traysegments/common.py:10-77).
  * 0 devices is an error: there is no CPU fallback. */
