@@ -146,6 +146,52 @@ def oracle_rate(scene, sample_steps, seed, threads):
     return st["photons"] / dt, dt, st, hits
 
 
+def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, sum_over_ranks):
+    """The same end-to-end loop with (a) photons thinned to MCPEs on the device (only photo-electrons come back) and
+    (b) additionally the bunch generated on the device from step-generation queue entries (nothing but a few hundred
+    bytes goes up).  Informational: the headline `e2e` stays the plain EnqueueSteps / GetConversionResult path."""
+    from clsim_b200 import capi, geometry, ice, mcpe, stepgen, steps
+    medium, geo, gens, bias = scene
+    ang = mcpe.GetIceCubeDOMAngularSensitivity()
+    # acceptance = the generation bias itself (UnshadowedFraction and hole-ice peak folded in would only scale both)
+    acc_of = {(int(s), int(o)): bias for s, o in zip(geo.stringIDs, geo.domIDs)}
+    out = {}
+    photons_per_bunch = float(bunch["num_photons"].sum())
+    for name in ("host_steps_mcpe_out", "device_steps_mcpe_out"):
+        conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(900 + rank, acc_of, ang, device=local, rngFirstMultiplierRow=7000000 + 100000 * rank)
+        gen = stepgen.StepGenerator(device=local, rng_seed=950 + rank, rng_first_multiplier=8000000 + 100000 * rank)
+        src = steps.muon_track_sources(len(bunch), photons_per_step=PHOTONS_PER_STEP)
+        eng = capi.Engine(medium, geo, gens, bias, opt)
+        conv.attach_to(eng)
+        send = (lambda i: eng.enqueue(bunch, i)) if name == "host_steps_mcpe_out" else (lambda i: gen.enqueue_into(eng, src, i))
+        for i in range(args.warmup):
+            send(10 + i)
+        for i in range(args.warmup):
+            eng.get_result()
+        barrier()
+        t0 = time.perf_counter()
+        pes, hits, pending = 0, 0, 0
+        for i in range(args.steps):
+            send(100 + i)
+            pending += 1
+            while eng.more_photons_available():
+                r = eng.get_result()
+                pes += len(r.mcpes); hits += r.num_hits_counted; pending -= 1
+        while pending:
+            r = eng.get_result()
+            pes += len(r.mcpes); hits += r.num_hits_counted; pending -= 1
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        out[name] = {"value": sum_over_ranks(photons_per_bunch * args.steps) / dt, "unit": "photons/s",
+                     "h2d_bytes_per_step": int(len(bunch) * 48) if name == "host_steps_mcpe_out" else int(src.nbytes + 24),
+                     "d2h_bytes_per_step": int(pes / max(1, args.steps) * 16 + 40),
+                     "mcpe_per_hit": pes / float(max(1, hits))}
+        eng.close()
+        conv.close()
+        gen.close()
+    return out
+
+
 def run_reference_arm(args):
     """The reference's own implementation of the path on the host cores: the oracle ("port";
     the OpenCL reference cannot be built or run here)."""
@@ -187,6 +233,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bunch", type=int, default=STEPS_PER_BUNCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-variants", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -252,9 +299,9 @@ def main():
     value = photons_all / (kernel_ms * 1e-3)
 
     # ---------------- e2e: host buffers through the C ABI -----------------------------------
-    for i in range(2):  # warm the pipeline (pinned staging, first-touch of result buffers)
+    for i in range(args.warmup):  # warm the pipeline (first-touch of staging and result buffers)
         eng.enqueue(bunch, 10 + i)
-    for i in range(2):
+    for i in range(args.warmup):
         eng.get_result()
     barrier()
     stats0 = eng.statistics()
@@ -282,6 +329,11 @@ def main():
     e2e_value = sum_over_ranks(float(bunch["num_photons"].sum()) * args.steps) / e2e_s
     stats = eng.statistics()
     eng.close()
+
+    # ---------------- e2e with the neighbours on the device (rows f2/f3): informational -------------
+    variants = None
+    if not args.no_variants:
+        variants = run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, sum_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -319,6 +371,7 @@ def main():
                 "api": "clsimcu_enqueue/clsimcu_get_result (EnqueueSteps/GetConversionResult), double buffering on",
                 "kernel_ms_per_step": e2e_kernel_ms / max(1, args.steps), "wall_ms": e2e_s * 1e3, "timeline_ms": timeline},
         "gpu_launches": args.steps,
+        "e2e_variants": variants,
         "roofline": roofline,
         "clocks": clocks,
     }

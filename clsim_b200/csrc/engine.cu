@@ -195,11 +195,10 @@ struct clsimcu_engine {
     std::vector<Slot> slots;
     BlockingQueue<Bunch> inbox{5};                 // queueToOpenCL_ depth 5 (…OpenCL.cxx:77)
     BlockingQueue<int> free_slots{0}, in_flight{0};
-    // pinned staging buffers for incoming bunches: as many as can be waiting (5) or in a slot, allocated on demand
-    clsimcu_step *staging[16] = {nullptr};      // fixed storage: the submit thread reads entries while enqueue adds new ones
-    size_t staging_count = 0, staging_max = 0;  // guarded by staging_mutex
+    // pinned staging buffers for incoming bunches: as many as can be waiting (5) or in a slot
+    clsimcu_step *staging[16] = {nullptr};
+    size_t staging_count = 0, staging_max = 0;
     BlockingQueue<int> free_staging{0};
-    std::mutex staging_mutex;
     BlockingQueue<std::shared_ptr<HostResult>> outbox{0};
     std::thread submit_thread, drain_thread;
     std::atomic<bool> stopping{false};
@@ -622,7 +621,7 @@ void free_engine(clsimcu_engine *e)
         if (s.counted) cudaEventDestroy(s.counted);
         if (s.xfer) cudaStreamDestroy(s.xfer);
     }
-    for (clsimcu_step *b : e->staging) cudaFreeHost(b);
+    for (size_t i = 0; i < e->staging_count; ++i) cudaFreeHost(e->staging[i]);
     cudaFree(e->d_arena); cudaFree(e->d_scene); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
     cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
     cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush);
@@ -758,7 +757,14 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
             }
             e->free_slots.put(i);
         }
+        // every staging buffer up front (5 bunches can wait in the inbox, one per slot is in flight): pinning 48 MiB
+        // takes tens of milliseconds and stalls the device -- not something to do between two bunches
         e->staging_max = 5 + static_cast<size_t>(nslots);
+        for (size_t i = 0; i < e->staging_max; ++i) {
+            CUDA_OK(cudaHostAlloc(&e->staging[i], e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault));
+            e->staging_count = i + 1;
+            e->free_staging.put(static_cast<int>(i));
+        }
         e->last_stamp = std::chrono::steady_clock::now();
         e->submit_thread = std::thread(submit_loop, e);
         e->drain_thread = std::thread(drain_loop, e);
@@ -790,21 +796,9 @@ int clsimcu_destroy(clsimcu_engine *e)
     return CLSIMCU_OK;
 }
 
-// A pinned staging buffer for an incoming bunch: a free one, a new one while the pool may grow, else wait for
-// one to come back.
+// A pinned staging buffer for an incoming bunch; waits for one to come back when all are in use.
 static int acquire_staging(clsimcu_engine *e, int &index)
 {
-    if (e->free_staging.try_get(index)) return CLSIMCU_OK;
-    std::unique_lock<std::mutex> lk(e->staging_mutex);
-    if (e->staging_count < e->staging_max) {
-        clsimcu_step *buf = nullptr;
-        if (cudaSetDevice(e->device) != cudaSuccess || cudaHostAlloc(&buf, e->max_items * sizeof(clsimcu_step), cudaHostAllocDefault) != cudaSuccess)
-            return fail(CLSIMCU_ERR_CUDA, std::string("cudaHostAlloc of a staging buffer: ") + cudaGetErrorString(cudaGetLastError()));
-        e->staging[e->staging_count] = buf;
-        index = static_cast<int>(e->staging_count++);
-        return CLSIMCU_OK;
-    }
-    lk.unlock();
     if (!e->free_staging.get(index)) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
     return CLSIMCU_OK;
 }

@@ -105,6 +105,27 @@ def muon_track_steps(num_steps, photons_per_step=200, energy_gev=1e4, track_leng
     return steps
 
 
+def muon_track_sources(num_steps, photons_per_step=200, energy_gev=1e4, track_length=1000.0, zenith_deg=45.0, azimuth_deg=30.0,
+                       center=(0.0, 0.0, 0.0), t0=0.0, identifier=0):
+    """The same workload as ``muon_track_steps`` as two entries of the step generation queue (muon-like and
+    cascade-like steps of one track), for bunches that are made on the device (stepgen.py)."""
+    from .stepgen import SOURCE_DTYPE, TRACK_CASCADE_LIKE, TRACK_MUON_LIKE
+    zen, azi = math.radians(zenith_deg), math.radians(azimuth_deg)
+    travel = -np.array([math.sin(zen) * math.cos(azi), math.sin(zen) * math.sin(azi), math.cos(zen)])
+    start = np.asarray(center, dtype=float) - 0.5 * track_length * travel
+    extr = 1.0 + max(0.0, 0.1880 + 0.0206 * math.log(energy_gev))
+    n_muon = int(round(num_steps / extr))
+    src = np.zeros(2, dtype=SOURCE_DTYPE)
+    src["x"], src["y"], src["z"], src["t"] = start[0], start[1], start[2], t0
+    src["dir_x"], src["dir_y"], src["dir_z"] = travel
+    src["length"] = track_length
+    src["kind"] = [TRACK_MUON_LIKE, TRACK_CASCADE_LIKE]
+    src["num_steps"] = [n_muon, num_steps - n_muon]
+    src["photons_per_step"] = photons_per_step
+    src["identifier"] = identifier
+    return src
+
+
 def muon_bundle_steps(num_steps, num_muons=100, spread=20.0, seed=3, **kw):
     """BASELINE config 3: parallel muons with a lateral spread."""
     rng = np.random.default_rng(seed)
