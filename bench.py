@@ -150,7 +150,8 @@ def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, 
     """The same end-to-end loop with (a) photons thinned to MCPEs on the device (only photo-electrons come back) and
     (b) additionally the bunch generated on the device from step-generation queue entries (nothing but a few hundred
     bytes goes up).  Informational: the headline `e2e` stays the plain EnqueueSteps / GetConversionResult path."""
-    from clsim_b200 import capi, geometry, ice, mcpe, stepgen, steps
+    from clsim_b200 import capi, mcpe, stepgen, steps
+    from clsim_b200.sharding import mcpe_row_offset, stepgen_row_offset
     medium, geo, gens, bias = scene
     ang = mcpe.GetIceCubeDOMAngularSensitivity()
     # acceptance = the generation bias itself (UnshadowedFraction and hole-ice peak folded in would only scale both)
@@ -158,8 +159,8 @@ def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, 
     out = {}
     photons_per_bunch = float(bunch["num_photons"].sum())
     for name in ("host_steps_mcpe_out", "device_steps_mcpe_out"):
-        conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(900 + rank, acc_of, ang, device=local, rngFirstMultiplierRow=7000000 + 100000 * rank)
-        gen = stepgen.StepGenerator(device=local, rng_seed=950 + rank, rng_first_multiplier=8000000 + 100000 * rank)
+        conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(900 + rank, acc_of, ang, device=local, rngFirstMultiplierRow=mcpe_row_offset(rank))
+        gen = stepgen.StepGenerator(device=local, rng_seed=950 + rank, rng_first_multiplier=stepgen_row_offset(rank))
         src = steps.muon_track_sources(len(bunch), photons_per_step=PHOTONS_PER_STEP)
         eng = capi.Engine(medium, geo, gens, bias, opt)
         conv.attach_to(eng)

@@ -17,6 +17,22 @@ def rng_row_offset(rank):
     return int(rank) * RNG_ROWS_PER_DEVICE
 
 
+# Behind the rows of 8 propagation engines: the streams of the two neighbours on the device.  Per device
+# 131 072 rows: the photon -> MCPE converter (148 x 256 = 37 888 streams) and the step generator
+# (2 x 148 x 256 = 75 776 streams).  The whole table has about 5.9 million rows.
+AUX_ROWS_BASE = 8 * RNG_ROWS_PER_DEVICE
+AUX_ROWS_PER_DEVICE = 131072
+TOTAL_ROWS_RESERVED = AUX_ROWS_BASE + 8 * AUX_ROWS_PER_DEVICE
+
+
+def mcpe_row_offset(rank):
+    return AUX_ROWS_BASE + int(rank) * AUX_ROWS_PER_DEVICE
+
+
+def stepgen_row_offset(rank):
+    return AUX_ROWS_BASE + int(rank) * AUX_ROWS_PER_DEVICE + 49152
+
+
 def shard_bunches(num_bunches, rank, world):
     """Round-robin assignment of bunch indices to ranks."""
     return list(range(int(rank), int(num_bunches), int(world)))

@@ -9,6 +9,7 @@ import pytest
 from clsim_b200 import capi, geometry, ice, mcpe, steps
 from clsim_b200.description import KERNEL_FAST, PHOTON_DTYPE
 from oracle import mcpe_oracle
+from clsim_b200.sharding import mcpe_row_offset, stepgen_row_offset
 from tests.scenes import Scene, make_scene
 from tests.test_mcpe_oracle import golden_angular, photons_on_sphere
 
@@ -75,10 +76,10 @@ def test_inloop_converter_on_propagated_photons_explicit_uniforms():
 def test_device_rng_draw_assignment_is_replayable():
     sc, acc_of, ang = detector()
     photons = np.concatenate([detected_photons(sc, seed=31), detected_photons(sc, seed=32)])
-    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(12345, acc_of, ang, rngFirstMultiplierRow=2000000)
+    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(12345, acc_of, ang, rngFirstMultiplierRow=mcpe_row_offset(1))
     x0, a = conv.rng_state()
     assert len(x0) == len(a) and len(x0) % 256 == 0 and len(np.unique(a)) == len(a)
-    assert np.array_equal(a, capi.safeprime_multipliers(2000000, len(a)))
+    assert np.array_equal(a, capi.safeprime_multipliers(mcpe_row_offset(1), len(a)))
     big = np.concatenate([photons] * 8)      # several draws per stream
     assert len(big) > 2 * len(x0)
     got = conv.Convert(big)
@@ -161,7 +162,7 @@ def test_conversion_attached_to_the_engine():
     sc, acc_of, ang = detector()
     n_steps = 1 << 15
     opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n_steps, rng_seed=5, enable_double_buffering=True)
-    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(77, acc_of, ang, rngFirstMultiplierRow=3000000)
+    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(77, acc_of, ang, rngFirstMultiplierRow=mcpe_row_offset(2))
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         conv.attach_to(eng, keep_photons=True)
         with pytest.raises(capi.ClsimCudaError, match="attached once"):
@@ -177,7 +178,7 @@ def test_conversion_attached_to_the_engine():
             assert as_set(res.mcpes) == as_set(expected(res.photons, keep, t))
     conv.close()
     # photo-electrons only: the photons stay on the device
-    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(78, acc_of, ang, rngFirstMultiplierRow=3000000)
+    conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(78, acc_of, ang, rngFirstMultiplierRow=mcpe_row_offset(2))
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         conv.attach_to(eng)
         eng.enqueue(steps.muon_track_steps(n_steps, seed=40), 9)

@@ -8,6 +8,7 @@ import pytest
 from clsim_b200 import capi, stepgen, steps as steplib
 from clsim_b200.description import KERNEL_FAST, STEP_DTYPE
 from oracle import stepgen_oracle as so
+from clsim_b200.sharding import mcpe_row_offset, stepgen_row_offset
 from tests.scenes import make_scene
 
 pytestmark = pytest.mark.gpu
@@ -51,9 +52,9 @@ def close_steps(got, want):
 
 
 def test_every_step_of_every_stream_replayed():
-    gen = stepgen.StepGenerator(rng_seed=99, rng_first_multiplier=4000000)
+    gen = stepgen.StepGenerator(rng_seed=99, rng_first_multiplier=stepgen_row_offset(1))
     x0, a = gen.rng_state()
-    assert np.array_equal(a, capi.safeprime_multipliers(4000000, len(a)))
+    assert np.array_equal(a, capi.safeprime_multipliers(stepgen_row_offset(1), len(a)))
     src = sources_mixed()
     # make some entries long enough that streams are used more than once
     src["num_steps"][5] = 2 * len(a) + 17
@@ -139,7 +140,7 @@ def test_bunches_generated_and_propagated_on_the_device():
     sc = make_scene("spice_mie")
     n_steps = 1 << 15
     opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n_steps, rng_seed=5)
-    gen = stepgen.StepGenerator(rng_seed=8, rng_first_multiplier=5000000)
+    gen = stepgen.StepGenerator(rng_seed=8, rng_first_multiplier=stepgen_row_offset(2))
     # the muon-track workload of the benchmark as two queue entries per muon
     track = dict(x=-300.0, y=50.0, z=-350.0, t=0.0, dir_x=math.sqrt(0.5), dir_y=0.0, dir_z=math.sqrt(0.5), length=1000.0, photons_per_step=200)
     src = np.zeros(2, dtype=stepgen.SOURCE_DTYPE)
@@ -179,7 +180,7 @@ def test_converter_feeds_the_engine_without_host_steps():
     conv.SetMediumProperties(sc.medium)
     conv.SetWlenBias(sc.bias)
     conv.SetRandomService(17)
-    conv.Initialize(rngFirstMultiplierRow=6000000)
+    conv.Initialize(rngFirstMultiplierRow=stepgen_row_offset(3))
     for i in range(6):
         conv.EnqueueLightSource(stepgen.Particle("MuMinus", 1e3, (-200 + 50 * i, 10, -300), (0.5, 0.1, 0.86), length=700.0), i)
     conv.EnqueueBarrier()
