@@ -116,9 +116,9 @@ def measured_traffic(bunch_steps):
     return d.get("dram_bytes_total")
 
 
-def build_scene():
+def build_scene(ice_model="spice_mie", tilt=False):
     from clsim_b200 import geometry, ice
-    medium = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_mie", useTiltIfAvailable=False)
+    medium = ice.MakeIceCubeMediumProperties(iceDataDirectory=ice_model, useTiltIfAvailable=tilt)
     geo = geometry.make_ic86_like_geometry(oversize=5.0)
     bias = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0)
     gen = ice.makeCherenkovWavelengthGenerator(bias, False, medium)
@@ -235,6 +235,9 @@ def main():
     ap.add_argument("--bunch", type=int, default=STEPS_PER_BUNCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-variants", action="store_true", help=argparse.SUPPRESS)
+    # side measurements (not the headline): BASELINE config 3's ice, "spice_lea" = SpiceLea with tilt and anisotropy
+    ap.add_argument("--ice", default="spice_mie", help=argparse.SUPPRESS)
+    ap.add_argument("--tilt", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
@@ -276,7 +279,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    scene = build_scene()
+    scene = build_scene(args.ice, args.tilt)
     medium, geo, gens, bias = scene
     n = args.bunch
     bunch = make_bunch(n, seed=1000 + rank)  # every rank its own bunch: weak scaling
@@ -364,7 +367,8 @@ def main():
         "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "256 MiB memset between timed launches (L2 flush)", "kernel": "fast persistent",
+        "config": {"workload": WORKLOAD if (args.ice == "spice_mie" and not args.tilt) else WORKLOAD.replace("SpiceMie 171 layers tilt off", "%s tilt %s (side measurement)" % (args.ice, "on" if args.tilt else "off")),
+                   "l2": "256 MiB memset between timed launches (L2 flush)", "kernel": "fast persistent",
                    "ns_per_photon": 1e9 / value, "hit_fraction": hits_all / photons_all,
                    "parallelism": "steps sharded by bunch, %d independent GPU(s), no collective" % world},
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(n * 48),
