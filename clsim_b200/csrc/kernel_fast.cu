@@ -68,10 +68,16 @@ namespace {
 #ifndef CLSIMCU_IDLE_LIMIT_SAVE_ALL
 #define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
 #endif
+#ifndef CLSIMCU_RENORM_EVERY
+#define CLSIMCU_RENORM_EVERY 0
+#endif
 #ifndef CLSIMCU_REFILL_BATCH
 #define CLSIMCU_REFILL_BATCH 4
 #endif
 constexpr int kThreads = CLSIMCU_THREADS;
+// Direction renormalisation in the hot loop: 0 = only when a fast phase starts (every few dozen iterations, the
+// drift of the unit length is a few 1e-7 per scatter); N (power of two) = on every N-th iteration as well
+constexpr uint32_t kRenormEvery = CLSIMCU_RENORM_EVERY;
 constexpr int kRefillBatch = CLSIMCU_REFILL_BATCH;            // lanes without a photon that make the warp stop for a refill
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
@@ -225,11 +231,14 @@ struct V3 {
 };
 
 // R8 (propagation_kernel.c.cl:83-129) with approximate MUFU ops
-__device__ __forceinline__ void rotate_by(float cosa, float sina, V3 &d, float rnd)
+__device__ __forceinline__ void rotate_by(float cosa, float sina, V3 &d, float rnd, bool renormalize = true)
 {
     float sinb, cosb;
     __sincosf(2.0f * kPi * rnd, &sinb, &cosb);
-    const float s2 = fmaxf(0.f, 1.f - d.z * d.z);
+    // sin^2(theta) from x and y, not as 1 - z^2: for a direction whose length is off by eps the rotation below then
+    // gives a length off by at most eps again (with 1 - z^2 the error is amplified by sin^2(a)/sin^2(theta) near the
+    // poles), so the length only random-walks by rounding and need not be restored after every scatter
+    const float s2 = fmaf(d.x, d.x, d.y * d.y);
     float nx, ny, nz;
     if (s2 > 0.f) {
         const float inv_s = mufu_rsqrt(s2);
@@ -243,10 +252,14 @@ __device__ __forceinline__ void rotate_by(float cosa, float sina, V3 &d, float r
         ny = sina * sinb;
         nz = (d.z > 0.f) ? cosa : ((d.z < 0.f) ? -cosa : cosa * d.z);
     }
-    // the rotation preserves the length up to rounding, so one Newton step of 1/sqrt about 1 is
-    // exact to fp32 here and keeps the special-function unit free
-    const float inv = fmaf(nx * nx + ny * ny + nz * nz, -0.5f, 1.5f);
-    d.x = nx * inv; d.y = ny * inv; d.z = nz * inv;
+    // the rotation preserves the length up to rounding (a few 1e-7 per scatter with the approximate sine and
+    // cosine), so one Newton step of 1/sqrt about 1 is exact to fp32 here and keeps the special-function unit
+    // free; the hot loop leaves it to the start of each fast phase (kRenormEvery)
+    if (renormalize) {
+        const float inv = fmaf(nx * nx + ny * ny + nz * nz, -0.5f, 1.5f);
+        nx *= inv; ny *= inv; nz *= inv;
+    }
+    d.x = nx; d.y = ny; d.z = nz;
 }
 
 __device__ __forceinline__ float phase_index(const DevMedium &m, float wlen)
@@ -750,9 +763,10 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
 // nothing but the scattering-length draw applied; the slow phase runs the full collision test
 // and either ends the photon there or sends the lane back with status kCleared, which lets
 // exactly this leg through.
-template <bool TILT, bool ANISO, bool SAVE_ALL>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
-                                               const float2 *bounds, const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st)
+                                               const float2 *bounds, const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st,
+                                               bool renormalize)
 {
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
@@ -837,14 +851,15 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
     if (ANISO) apply_matrix(m.pre, L.dir);
     const float rr = rng.co();
     float cs;
-    if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
+    const int scat_kind = MIXED ? CLSIMCU_SCAT_MIXED_SL_HG : m.scat_kind;   // the IceCube models' mix is compiled in
+    if (scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
         // both samplers are evaluated and one is selected: no divergent branch
         const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
         const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
         const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
         const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
         cs = (rr < m.f_sl) ? cos_sl : cos_hg;
-    } else if (m.scat_kind == CLSIMCU_SCAT_HG) {
+    } else if (scat_kind == CLSIMCU_SCAT_HG) {
         const float s = 2.f * rr - 1.f;
         const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
         cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
@@ -853,7 +868,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
     }
     cs = fminf(fmaxf(cs, -1.f), 1.f);
     const float sn = mufu_sqrt(1.f - cs * cs);
-    rotate_by(cs, sn, L.dir, rng.co());
+    rotate_by(cs, sn, L.dir, rng.co(), ANISO ? false : renormalize);   // apply_matrix renormalises
     if (ANISO) apply_matrix(m.post, L.dir);
     L.inv_dz = safe_inv_dz(L.dir.z);
     L.sca_left = 0.f;
@@ -1055,7 +1070,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     return (n_idle > 0) ? n_idle + 1 : (SAVE_ALL ? kIdleLimitSaveAll : kIdleLimit);
 }
 
-template <bool TILT, bool ANISO, bool SAVE_ALL>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 propagate_persistent(const __grid_constant__ DevScene scene, const __grid_constant__ LaunchArgs args, const __grid_constant__ SmemLayout lay)
 {
@@ -1125,10 +1140,17 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         //      `limit` lanes wait for the slow phase.
         Lane L;
         load_lane<TILT, ANISO>(L, st);
+        if (!ANISO) {
+            // the unit length of the direction, restored once per fast phase (see rotate_by)
+            const float inv = fmaf(L.dir.x * L.dir.x + L.dir.y * L.dir.y + L.dir.z * L.dir.z, -0.5f, 1.5f);
+            L.dir.x *= inv; L.dir.y *= inv; L.dir.z *= inv;
+            L.inv_dz = safe_inv_dz(L.dir.z);
+        }
         bool cleared = (L.status == kCleared);
         if (cleared) L.status = kActive;
         uint32_t queued = wctl[kWQueued];
         const bool more = (wctl[kWMore] != 0u) || (wctl[kWLeft] > 0u);
+        uint32_t iteration = 0u;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.status != kActive);
             if (idle != 0u) {
@@ -1154,7 +1176,9 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                 }
             }
             if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st);
+                advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st,
+                                                             kRenormEvery != 0u && (iteration & (kRenormEvery - 1u)) == 0u);
+            if (kRenormEvery != 0u) ++iteration;
         }
         if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
@@ -1175,11 +1199,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     }
 }
 
-template <bool TILT, bool ANISO, bool SAVE_ALL>
-int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cudaStream_t stream)
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+int launch_mix(const DevScene &scene, const LaunchArgs &args, int blocks, cudaStream_t stream)
 {
     const SmemLayout lay = plan_smem(scene);
-    auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL>;
+    auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL, MIXED>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)) != cudaSuccess) return -3;
@@ -1187,6 +1211,16 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
     }
     kernel<<<blocks, kThreads, lay.total, stream>>>(scene, args, lay);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+template <bool TILT, bool ANISO, bool SAVE_ALL>
+int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cudaStream_t stream)
+{
+    // the save-all variants are checkers' tools: no need to specialise them further
+    if constexpr (!SAVE_ALL) {
+        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) return launch_mix<TILT, ANISO, SAVE_ALL, true>(scene, args, blocks, stream);
+    }
+    return launch_mix<TILT, ANISO, SAVE_ALL, false>(scene, args, blocks, stream);
 }
 
 } // namespace
