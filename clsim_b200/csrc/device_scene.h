@@ -34,7 +34,7 @@ struct DevMedium {
     float f_sl, one_minus_f_sl, g, g2, sl_beta;
     float inv_f_sl, inv_one_minus_f_sl, inv_2g; // fast kernel: reciprocals (0 where undefined)
     int tilt_nd, tilt_nz;
-    float tilt_z0, tilt_dz, tilt_lnx, tilt_lny;
+    float tilt_z0, tilt_dz, tilt_inv_dz, tilt_lnx, tilt_lny;
     int anisotropy, pre_renorm, post_renorm;
     float l[3], rl[3], azx, azy, neg_azy, B2;
     float pre[9], post[9];

@@ -264,6 +264,7 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     dm.inv_2g = (m.g != 0.f) ? 1.f / (2.f * m.g) : 0.f;
     dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
     dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
+    dm.tilt_inv_dz = (m.tilt_nd > 0 && m.tilt_dz != 0.f) ? 1.f / m.tilt_dz : 0.f;
     dm.anisotropy = m.anisotropy; dm.pre_renorm = m.pre_renorm; dm.post_renorm = m.post_renorm;
     for (int i = 0; i < 3; ++i) { dm.l[i] = m.l[i]; dm.rl[i] = m.rl[i]; }
     dm.azx = m.azx; dm.azy = m.azy; dm.neg_azy = m.neg_azy; dm.B2 = m.B2;

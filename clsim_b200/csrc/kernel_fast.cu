@@ -154,7 +154,7 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 
 // Shared-memory plan, carved out of the dynamic allocation.
 struct SmemLayout {
-    uint32_t off_layers, off_bounds, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near;
+    uint32_t off_layers, off_bounds, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_tilt_dist, off_tilt_corr;
     uint32_t off_state;   // per-thread arrays: state | birth tag | segment counter | propagation-stream tag (save-all only)
     uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
     uint32_t cell_offset[kMaxSubdetectors];
@@ -177,6 +177,8 @@ struct SmemPlan {
     uint16_t *layer_to_dom;  // [layer_table_size]
     uint16_t *cells;         // concatenated grids
     uint32_t *near;          // xy pixel map, see device_scene.h
+    float2 *tilt_dist;       // [tilt_nd] (distance along the tilt direction, 1 / (this - previous)); ice tilt only
+    float *tilt_corr;        // [tilt_nd][tilt_nz] z corrections
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -199,6 +201,8 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     }
     at = align16(at + cells * 2);
     L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
+    L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 32);   // + 8 search keys
+    L.off_tilt_corr = at; at = align16(at + s.medium.tilt_nd * s.medium.tilt_nz * 4);
     L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kPopTagWords : 0)) * kThreads * 4);
     L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
     L.total = at;
@@ -223,6 +227,8 @@ __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
     sp.layer_to_dom = reinterpret_cast<uint16_t *>(smem + lay.off_layer_to_dom);
     sp.cells = reinterpret_cast<uint16_t *>(smem + lay.off_cells);
     sp.near = reinterpret_cast<uint32_t *>(smem + lay.off_near);
+    sp.tilt_dist = reinterpret_cast<float2 *>(smem + lay.off_tilt_dist);
+    sp.tilt_corr = reinterpret_cast<float *>(smem + lay.off_tilt_corr);
     return sp;
 }
 
@@ -336,23 +342,34 @@ __device__ __forceinline__ void dom_centre(const DevGeometry &g, int string, int
     z = __ldg(g.tmpl_z + at);
 }
 
-// R4a (I3CLSimScalarFieldIceTiltZShift.cxx:145-216)
-__device__ float tilt_shift(const DevMedium &m, float x, float y, float z)
+// R4a (I3CLSimScalarFieldIceTiltZShift.cxx:145-216); both tables in shared memory, the reciprocal of every
+// distance interval precomputed, the interval found without a data-dependent loop
+__device__ __forceinline__ float tilt_shift(const DevMedium &m, const float2 *dist, const float *corr, float x, float y, float z)
 {
-    const float zr = (z - m.tilt_z0) * mufu_rcp(m.tilt_dz);
+    const float zr = (z - m.tilt_z0) * m.tilt_inv_dz;
     const int k = min(max(__float2int_rd(zr), 0), m.tilt_nz - 2);
     const float above = zr - static_cast<float>(k);
     const float below = 1.f - above;
     const float nr = m.tilt_lnx * x + m.tilt_lny * y;
+    // j = first interval end in [1, nd-1] with nr < dist[j], or nd-1 (the reference's scan, :178-186).  The
+    // distances ascend, so j = 1 + the number of interior nodes not above nr; up to 8 nodes (the ice models have 6)
+    // sit in two float4 behind the table, padded with +inf
     int j = 1;
-    while (j < m.tilt_nd - 1 && !(nr < __ldg(m.tilt_dist + j))) ++j;
-    const float here = __ldg(m.tilt_dist + j), prev = __ldg(m.tilt_dist + j - 1);
-    const float w_lo = (here - nr) * mufu_rcp(here - prev);
+    if (m.tilt_nd <= 8) {
+        const float4 *keys = reinterpret_cast<const float4 *>(dist + m.tilt_nd + (m.tilt_nd & 1));
+        const float4 k0 = keys[0], k1 = keys[1];
+        j += ((nr < k0.y) ? 0 : 1) + ((nr < k0.z) ? 0 : 1) + ((nr < k0.w) ? 0 : 1) + ((nr < k1.x) ? 0 : 1) + ((nr < k1.y) ? 0 : 1) + ((nr < k1.z) ? 0 : 1);
+    } else {
+#pragma unroll 1
+        for (int i = 1; i < m.tilt_nd - 1; ++i) j += (nr < dist[i].x) ? 0 : 1;
+    }
+    const float2 here = dist[j];
+    const float w_lo = (here.x - nr) * here.y;
     const float w_hi = 1.f - w_lo;
-    const float *lo_row = m.tilt_corr + (j - 1) * m.tilt_nz + k;
-    const float *hi_row = m.tilt_corr + j * m.tilt_nz + k;
-    const float v_lo = __ldg(lo_row + 1) * above + __ldg(lo_row) * below;
-    const float v_hi = __ldg(hi_row + 1) * above + __ldg(hi_row) * below;
+    const float *lo_row = corr + (j - 1) * m.tilt_nz + k;
+    const float *hi_row = lo_row + m.tilt_nz;
+    const float v_lo = lo_row[1] * above + lo_row[0] * below;
+    const float v_hi = hi_row[1] * above + hi_row[0] * below;
     return v_hi * w_hi + v_lo * w_lo;
 }
 
@@ -765,8 +782,8 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
 // exactly this leg through.
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
-                                               const float2 *bounds, const float4 *strings, const uint32_t *near, uint32_t rng_a, float *st,
-                                               bool renormalize)
+                                               const float2 *bounds, const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
+                                               const float *tilt_corr, uint32_t rng_a, float *st, bool renormalize)
 {
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
@@ -775,7 +792,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
     if (L.sca_left <= 0.f) {
         // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
-            L.z_eff = L.pos.z - tilt_shift(m, L.pos.x, L.pos.y, L.pos.z);
+            L.z_eff = L.pos.z - tilt_shift(m, tilt_dist, tilt_corr, L.pos.x, L.pos.y, L.pos.z);
             L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
         }
         if (ANISO) {
@@ -1094,6 +1111,17 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         sp.bounds[i] = make_float2((i == 0) ? -1e30f : m.z0 + m.h * static_cast<float>(i),
                                    (i == m.num_layers - 1) ? 1e30f : m.z0 + m.h * static_cast<float>(i + 1));
     }
+    if (TILT) {
+        for (int i = tid; i < m.tilt_nd; i += kThreads) {
+            const float here = __ldg(m.tilt_dist + i);
+            sp.tilt_dist[i] = make_float2(here, (i > 0) ? 1.f / (here - __ldg(m.tilt_dist + i - 1)) : 0.f);
+        }
+        if (tid < 8) {
+            float *keys = reinterpret_cast<float *>(sp.tilt_dist + m.tilt_nd + (m.tilt_nd & 1));
+            keys[tid] = (tid >= 1 && tid <= m.tilt_nd - 2) ? __ldg(m.tilt_dist + tid) : __int_as_float(0x7f800000);
+        }
+        for (int i = tid; i < m.tilt_nd * m.tilt_nz; i += kThreads) sp.tilt_corr[i] = __ldg(m.tilt_corr + i);
+    }
     if (!SAVE_ALL) {
         for (int i = tid; i < geo.num_strings; i += kThreads) {
             sp.strings[i] = make_float4(__ldg(geo.string_x + i), __ldg(geo.string_y + i), __ldg(geo.string_max_z + i) + geo.om_radius,
@@ -1176,7 +1204,8 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                 }
             }
             if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, rng_a, st,
+                advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, sp.tilt_dist,
+                                                             sp.tilt_corr, rng_a, st,
                                                              kRenormEvery != 0u && (iteration & (kRenormEvery - 1u)) == 0u);
             if (kRenormEvery != 0u) ++iteration;
         }
