@@ -431,6 +431,12 @@ bool I3CLSimStepToPhotonConverterCUDA::MorePhotonsAvailable() const
 
 I3CLSimStepToPhotonConverter::ConversionResult_t I3CLSimStepToPhotonConverterCUDA::GetConversionResult()
 {
+    std::vector<clsimcu_mcpe> unused;
+    return GetConversionResultWithMCPEs(unused);
+}
+
+I3CLSimStepToPhotonConverter::ConversionResult_t I3CLSimStepToPhotonConverterCUDA::GetConversionResultWithMCPEs(std::vector<clsimcu_mcpe> &mcpes)
+{
     ThrowIfNotInitialized();
     clsimcu_result r;
     std::memset(&r, 0, sizeof(r));
@@ -450,6 +456,7 @@ I3CLSimStepToPhotonConverter::ConversionResult_t I3CLSimStepToPhotonConverterCUD
         }
         out.photonHistories = hs;
     }
+    mcpes.assign(r.mcpes, r.mcpes + r.num_mcpes);
     clsimcu_release_result(engine_, &r);
     return out;
 }

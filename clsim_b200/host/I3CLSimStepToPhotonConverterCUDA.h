@@ -30,6 +30,7 @@
 #include <vector>
 
 struct clsimcu_engine;
+struct clsimcu_mcpe;
 
 class I3CLSimStepToPhotonConverterCUDA : public I3CLSimStepToPhotonConverter {
 public:
@@ -82,6 +83,11 @@ public:
 
     // The flattened description (what Compile() produced), for tests: JSON text of the device tables.
     std::string DescribeTables() const;
+
+    // the neighbours on the device (I3CLSimNeighboursCUDA.h) attach to the engine behind this converter
+    clsimcu_engine *GetEngine() { return engine_; }
+    // GetConversionResult plus the photo-electrons of an attached I3CLSimPhotonToMCPEConverterCUDA
+    ConversionResult_t GetConversionResultWithMCPEs(std::vector<clsimcu_mcpe> &mcpes);
 
 private:
     struct Flat;  // POD arrays behind the clsimcu_config pointers

@@ -106,6 +106,7 @@ struct I3CLSimPhoton {
     float GetCherenkovDist() const { return cherenkovDist; }
     uint32_t GetNumScatters() const { return numScatters; }
     float GetWeight() const { return weight; }
+    void SetWeight(const float &val) { weight = val; }   // public/clsim/I3CLSimPhoton.h:119
     uint32_t GetID() const { return identifier; }
     int16_t GetStringID() const { return stringID; }
     uint16_t GetOMID() const { return omID; }

@@ -127,3 +127,26 @@ def test_server_seam_on_devices(binary):
     print(res.stdout)
     assert res.returncode == 0, res.stdout
     assert "0 failed" in res.stdout
+
+
+NEIGHBOURS_BINARY = os.path.join(ROOT, "clsim_b200", "host", "build", "test_neighbours_cuda")
+
+
+def test_cxx_neighbour_classes_contract(binary, has_gpu):
+    """I3CLSimPhotonToMCPEConverterCUDA / I3CLSimStepGeneratorCUDA (C++): argument errors with the reference's messages,
+    and no construction without a device."""
+    res = subprocess.run([NEIGHBOURS_BINARY, "--gpu-args-only" if has_gpu else "--no-gpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=120)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout
+    assert "0 failed" in res.stdout
+
+
+@pytest.mark.gpu
+def test_cxx_neighbour_classes_on_the_device(binary):
+    """Photon -> MCPE against a C++ restatement of the reference's Convert (explicit uniforms: every survivor), the
+    conversion attached to a converter, steps made on the device, bunches generated in place."""
+    res = subprocess.run([NEIGHBOURS_BINARY, "--gpu"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout
+    assert "0 failed" in res.stdout
