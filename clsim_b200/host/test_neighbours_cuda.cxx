@@ -101,7 +101,7 @@ static void test_on_device()
     auto conv = make_conv(11);
     conv->EnqueueSteps(make_steps(bunch, 200, 5, 5), 5);
     I3CLSimPhotonSeriesPtr photons = conv->GetConversionResult().photons;
-    CHECK(photons && photons->size() > 500);
+    CHECK(photons && photons->size() > 150);
     I3CLSimPhotonToMCPEConverterCUDA mcpe(21, acc, angular, 0, 2700000);
     std::mt19937 rng(3);
     std::uniform_real_distribution<float> uni(0.f, 1.f);
@@ -139,7 +139,7 @@ static void test_on_device()
     conv2->EnqueueSteps(make_steps(bunch, 200, 6, 6), 6);
     std::vector<clsimcu_mcpe> pes;
     I3CLSimStepToPhotonConverter::ConversionResult_t res = conv2->GetConversionResultWithMCPEs(pes);
-    CHECK(res.identifier == 6 && res.photons && res.photons->size() > 500);
+    CHECK(res.identifier == 6 && res.photons && res.photons->size() > 150);
     CHECK(!pes.empty() && pes.size() < res.photons->size());
     std::multiset<Key> photon_keys;
     for (const I3CLSimPhoton &p : *res.photons) photon_keys.insert(Key(p.GetStringID(), p.GetOMID(), p.GetTime(), p.GetID()));
