@@ -27,6 +27,8 @@ SYMBOLS = [
     "clsimcu_sizeof_config", "clsimcu_device_count",
     "clsimcu_mcpe_create", "clsimcu_mcpe_destroy", "clsimcu_mcpe_convert", "clsimcu_mcpe_rng_get", "clsimcu_attach_mcpe_converter",
     "clsimcu_stepgen_create", "clsimcu_stepgen_destroy", "clsimcu_stepgen_generate", "clsimcu_stepgen_rng_get", "clsimcu_enqueue_sources",
+    "clsimcu_tabulator_create", "clsimcu_tabulator_destroy", "clsimcu_tabulator_enqueue", "clsimcu_tabulator_finish", "clsimcu_tabulator_info",
+    "clsimcu_tabulator_get_table",
 ]
 
 STAT_KEYS = ["TotalDeviceTime", "TotalHostTime", "NumKernelCalls", "TotalNumPhotonsGenerated", "TotalNumPhotonsAtDOMs",

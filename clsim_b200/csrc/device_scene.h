@@ -93,6 +93,27 @@ struct DevScene {
 };
 
 // Per-launch arguments.
+// Table-maker variant of the reference-order kernel (-DTABULATE, propagation_kernel.c.cl:226-304): the binning
+// code the reference generates from its Axes (private/clsim/tabulator/Axes.cxx:71-93, Axis.cxx:44-60) as data.
+struct DevAxis {
+    float scale, offset;   // index = clamp(floor(scale * inverse_transform(x) - offset), -1, n_bins) + 1
+    int n_bins;
+    int inverse;           // 0: x (linear, power 1)   1: constant 1 (power 0)   2: sqrt   3: cbrt   4: pow(x, inv_power)
+    float inv_power;
+    uint32_t stride;
+};
+struct TabulateArgs {
+    int geometry, ndim, full_azimuth;
+    DevAxis axes[5];
+    float max0, max3;                    // isOutOfBounds (Axes.cxx:113-123, 151-159)
+    float step_length;                   // VOLUME_MODE_STEP
+    float min_inv_group_vel, tan_theta_c;
+    int num_angular;
+    float angular[24];                   // getAngularAcceptance, Horner form of I3CLSimFunctionPolynomial.cxx:139-153
+    float ref_pos[4], ref_dir[4], ref_perp[4];   // I3CLSimReferenceParticle
+    float *table, *squared;              // HBM, added to atomically
+};
+
 struct LaunchArgs {
     const void *steps;         // clsimcu_step[num_steps]
     uint32_t num_steps;
@@ -109,6 +130,7 @@ struct LaunchArgs {
     uint64_t *rng_tag_x;       // optional (save-all replay): per record, creation and propagation RNG states
     uint32_t *rng_tag_a;
     int count_stats;
+    const TabulateArgs *tabulate;  // reference-order kernel only: table-maker variant (device pointer) or nullptr
 };
 
 // kernel launchers (defined in kernel_reference.cu / kernel_fast.cu)

@@ -35,6 +35,7 @@
 #include "device_scene.h"
 #include "mcpe.h"
 #include "stepgen.h"
+#include "tabulate.h"
 #include "tables.h"
 
 namespace clsimcu {
@@ -221,6 +222,7 @@ struct clsimcu_engine {
     uint64_t *d_tag_x = nullptr;
     uint32_t *d_tag_a = nullptr;
     uint8_t *d_l2_flush = nullptr;   // written between timed launches (larger than the 126 MB L2)
+    clsimcu_step *d_tab_steps = nullptr;   // table-maker variant: the bunch being tabulated
     size_t res_steps = 0, res_cap = 0;
     uint64_t res_generated_per_run = 0;
     uint32_t res_last_hits = 0;
@@ -625,13 +627,57 @@ void free_engine(clsimcu_engine *e)
     for (size_t i = 0; i < e->staging_count; ++i) cudaFreeHost(e->staging[i]);
     cudaFree(e->d_arena); cudaFree(e->d_scene); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
     cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
-    cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush);
+    cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush); cudaFree(e->d_tab_steps);
     cudaFreeHost(e->h_res_counters); cudaFreeHost(e->h_res_stats);
     if (e->compute) cudaStreamDestroy(e->compute);
     delete e;
 }
 
 } // namespace
+} // namespace clsimcu
+
+// ---- seam for the table-maker variant (tabulate.cu) -----------------------------------------------------
+namespace clsimcu {
+
+int engine_device(const clsimcu_engine *e) { return e->device; }
+size_t engine_max_items(const clsimcu_engine *e) { return e->max_items; }
+
+std::string engine_launch_tabulate(clsimcu_engine *e, const clsimcu_step *steps, size_t n, const TabulateArgs *d_tab)
+{
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        if (!e->d_tab_steps) CUDA_OK(cudaMalloc(&e->d_tab_steps, e->max_items * sizeof(clsimcu_step)));
+        // pageable source: the copy has returned from the host buffer when this call returns; stream order keeps
+        // the previous launch from being overwritten
+        CUDA_OK(cudaMemcpyAsync(e->d_tab_steps, steps, n * sizeof(clsimcu_step), cudaMemcpyHostToDevice, e->compute));
+        LaunchArgs a{};
+        a.steps = e->d_tab_steps;
+        a.num_steps = static_cast<uint32_t>(n);
+        a.rng_x = e->d_rng_x;
+        a.rng_a = e->d_rng_a;
+        a.scene_dev = e->d_scene;
+        a.tabulate = d_tab;
+        if (launch_reference_kernel(e->scene, a, e->compute) != 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    } catch (const std::exception &ex) {
+        return ex.what();
+    }
+    return std::string();
+}
+
+std::string engine_copy_on_stream(clsimcu_engine *e, void *dst, const void *src, size_t bytes, bool to_device, bool wait)
+{
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        if (bytes) CUDA_OK(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, e->compute));
+        if (wait) CUDA_OK(cudaStreamSynchronize(e->compute));
+    } catch (const std::exception &ex) {
+        return ex.what();
+    }
+    return std::string();
+}
+
 } // namespace clsimcu
 
 extern "C" {

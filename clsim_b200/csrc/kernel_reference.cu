@@ -390,6 +390,110 @@ __device__ bool find_collision(const Output &o, const Flight &f, float &length, 
     return false;
 }
 
+// ---- table-maker variant (-DTABULATE) -------------------------------------------------------------------
+// Coordinates of a point of the photon's path relative to the reference particle
+// (resources/kernels/spherical_coordinates.c.cl, cylindrical_coordinates.c.cl).  OpenCL's dot() of two float4
+// includes the fourth components: zero for the reference vectors, but wavelength x delay time in the impact-angle
+// product (a quirk of the reference, kept).
+__device__ void table_coordinates(const TabulateArgs &tb, const V3 &p, float t, V3 dir, float wlen, Stream &rng, float c[5])
+{
+    const float px = p.x - tb.ref_pos[0], py = p.y - tb.ref_pos[1], pz = p.z - tb.ref_pos[2], pw = t - tb.ref_pos[3];
+    const float l = ((px * tb.ref_dir[0] + py * tb.ref_dir[1]) + pz * tb.ref_dir[2]) + pw * tb.ref_dir[3];
+    const float rx = px - l * tb.ref_dir[0], ry = py - l * tb.ref_dir[1], rz = pz - l * tb.ref_dir[2], rw = pw - l * tb.ref_dir[3];
+    const float n_rho = sqrtf(rx * rx + ry * ry + rz * rz);
+    const float rho_perp = ((rx * tb.ref_perp[0] + ry * tb.ref_perp[1]) + rz * tb.ref_perp[2]) + rw * tb.ref_perp[3];
+    if (tb.geometry == 0) {
+        c[0] = sqrtf(px * px + py * py + pz * pz);
+        const float azimuth = (n_rho > 0) ? acosf(rho_perp / n_rho) / (kPi / 180) : 0;
+        if (tb.full_azimuth) {
+            // cross(rho, perpDir) . dir
+            const float cx = ry * tb.ref_perp[2] - rz * tb.ref_perp[1], cy = rz * tb.ref_perp[0] - rx * tb.ref_perp[2],
+                        cz = rx * tb.ref_perp[1] - ry * tb.ref_perp[0];
+            const float sign = (cx * tb.ref_dir[0] + cy * tb.ref_dir[1]) + cz * tb.ref_dir[2];
+            c[1] = (sign > 0) ? 360.f - azimuth : azimuth;
+        } else {
+            c[1] = azimuth;
+        }
+        c[2] = (c[0] > 0) ? (l / c[0]) : 0;
+        c[3] = pw - c[0] * tb.min_inv_group_vel;
+        if (tb.ndim > 4) {
+            const float sina = sqrtf(rng.co());
+            rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
+            c[4] = (c[0] > 0) ? ((((dir.x * px + dir.y * py) + dir.z * pz) + wlen * pw) / c[0]) : 1;
+        }
+    } else {
+        c[0] = n_rho;
+        c[1] = (c[0] > 0) ? acosf(rho_perp / c[0]) : 0;
+        c[2] = tb.ref_pos[2] + l * tb.ref_dir[2];
+        c[3] = pw - (l + c[0] * tb.tan_theta_c) * 3.33564095f;   // recip_speedOfLight, propagation_kernel.h.cl:149
+        if (tb.ndim > 4) {
+            const float sina = sqrtf(rng.co());
+            rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
+            // vector from the nominal Cherenkov emission point; (l - rho/tan_thetaC) is a float4 in the reference, component-wise
+            const float k = 1.f / tb.tan_theta_c;
+            const float qx = p.x - (tb.ref_pos[0] + (l - rx * k) * tb.ref_dir[0]), qy = p.y - (tb.ref_pos[1] + (l - ry * k) * tb.ref_dir[1]),
+                        qz = p.z - (tb.ref_pos[2] + (l - rz * k) * tb.ref_dir[2]), qw = t - (tb.ref_pos[3] + (l - rw * k) * tb.ref_dir[3]);
+            const float cdist = sqrtf(qx * qx + qy * qy + qz * qz);
+            c[4] = (cdist > 0) ? ((((dir.x * qx + dir.y * qy) + dir.z * qz) + wlen * qw) / cdist) : 1;
+        }
+    }
+}
+
+// getBinIndex (Axes.cxx:71-93) with Axis::GetIndexCode (Axis.cxx:44-60): convert_int_sat_rtn = floor with saturation
+__device__ uint32_t table_bin_index(const TabulateArgs &tb, const float c[5])
+{
+    uint32_t index = 0;
+    for (int i = 0; i < tb.ndim; ++i) {
+        const DevAxis &ax = tb.axes[i];
+        float v = c[i];
+        if (ax.inverse == 1) v = 1.f;
+        else if (ax.inverse == 2) v = sqrtf(v);
+        else if (ax.inverse == 3) v = cbrtf(v);
+        else if (ax.inverse == 4) v = powf(v, ax.inv_power);
+        const float f = floorf(ax.scale * v - ax.offset);
+        int k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f)));
+        k = min(max(k, -1), ax.n_bins) + 1;
+        index += ax.stride * static_cast<uint32_t>(k);
+    }
+    return index;
+}
+
+__device__ float table_angular_acceptance(const TabulateArgs &tb, float x)
+{
+    if (tb.num_angular == 0) return 0.f;
+    float v = tb.angular[tb.num_angular - 1];
+    for (int i = tb.num_angular - 2; i >= 0; --i) v = tb.angular[i] + x * v;
+    return v;
+}
+
+// savePath (propagation_kernel.c.cl:226-304).  The entries go straight into the table in HBM; there is no entry
+// buffer to run out of, so the reference's "return false, restart the photon" branch does not exist.
+__device__ void save_path(const TabulateArgs &tb, const clsimcu_step &step, const Flight &f, float travel, float &prev_remainder, float depth,
+                          float step_depth, bool &stop, Stream &rng)
+{
+    const float impact_weight = (tb.ndim > 4) ? step.weight : step.weight * table_angular_acceptance(tb, f.dir.z);
+    float d = prev_remainder;
+    for (; d < travel; d += tb.step_length) {
+        V3 p;
+        p.x = f.pos.x + d * f.dir.x;
+        p.y = f.pos.y + d * f.dir.y;
+        p.z = f.pos.z + d * f.dir.z;
+        const float t = f.t + d * f.inv_vg;
+        float c[5];
+        table_coordinates(tb, p, t, f.dir, f.wlen, rng, c);
+        const bool out = (tb.geometry == 0) ? ((c[3] > tb.max3) || (c[0] > tb.max0)) : (c[3] > tb.max3);
+        if (out) {
+            stop = true;
+            break;
+        }
+        const uint32_t index = table_bin_index(tb, c);
+        const float w = impact_weight * expf(-(depth + (d / travel) * step_depth));
+        atomicAdd(tb.table + index, w);
+        if (tb.squared) atomicAdd(tb.squared + index, w * w);
+    }
+    prev_remainder = d - travel;
+}
+
 __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_constant__ DevScene scene, const __grid_constant__ LaunchArgs args)
 {
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -420,6 +524,8 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
     f.abs_initial = 0.f;
     const bool flat_ice = (m.tilt_nd == 0); // getTiltZShift_IS_CONSTANT
     int layer = 0;
+    const TabulateArgs *tab = args.tabulate;   // table-maker variant
+    float depth = 0.f, prev_remainder = 0.f;
     unsigned long long n_created = 0, n_segments = 0;
 
     while (left > 0) {
@@ -446,6 +552,11 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
             f.start_dir = f.dir;
             f.scatters = 0;
             f.path = 0.f;
+            if (tab) {
+                // randomise the first sub-step (propagation_kernel.c.cl:566-569); depth restarts (:590-592)
+                prev_remainder = tab->step_length * rng.oc();
+                depth = 0.f;
+            }
             if (flat_ice) layer = clampi(layer_of(m, f.pos.z), 0, m.num_layers - 1);
             f.inv_vg = 1.f / group_velocity(m, f.wlen);
             f.abs_initial = scene.fixed_abs ? scene.fixed_abs_lens : -logf(rng.oc());
@@ -516,6 +627,13 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
             const bool caught = find_collision(out, f, travel, f.abs_initial - abs_left);
             if (scene.stop_detected && caught) abs_left = 0.f;
         }
+        if (tab) {
+            // propagation_kernel.c.cl:755-785
+            bool stop = false;
+            save_path(*tab, step, f, travel, prev_remainder, depth, f.abs_initial - abs_left - depth, stop, rng);
+            if (stop) abs_left = 0.f;   // the photon ran off the end of the table
+            depth = f.abs_initial - abs_left;
+        }
 
         f.pos.x += f.dir.x * travel;
         f.pos.y += f.dir.y * travel;
@@ -525,7 +643,7 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
 
         if (abs_left < kEpsilon) {
             --left;
-            if (scene.save_all) {
+            if (scene.save_all && !tab) {   // #if defined(SAVE_ALL_PHOTONS) && !defined(TABULATE), :800
                 if (rng.co() < scene.prescale) record_hit(out, f, 0.f, f.abs_initial, 0, 0);
             }
         } else {

@@ -422,6 +422,74 @@ int clsimcu_stepgen_rng_get(clsimcu_step_generator *generator, uint64_t *x, uint
 int clsimcu_enqueue_sources(clsimcu_engine *engine, clsimcu_step_generator *generator, const clsimcu_step_source *sources,
                             size_t n, uint32_t identifier);
 
+/* ---- table-maker variant -------------------------------------- */
+
+/* The -DTABULATE build of the reference kernel (resources/kernels/propagation_kernel.c.cl:226-304, 755-785)
+ * behind I3CLSimStepToTableConverter (private/clsim/tabulator/I3CLSimStepToTableConverter.cxx): photons are
+ * propagated for a fixed 42 absorption lengths through DOM-free ice, and every `step_length` metres along
+ * their path the detection probability exp(-absorption lengths so far) * angular acceptance is added to the
+ * bin of a photon-density table around a reference particle.
+ * Re-designed for the B200: the table lives in HBM and the kernel adds to it with float atomics.  The
+ * reference's per-work-item entry buffers, its "out of space, restart the photon" protocol and the host loop
+ * that sums the entries (…StepToTableConverter.cxx:375-520) have no counterpart: the result is the same sum
+ * in a different order. */
+#define CLSIMCU_AXIS_LINEAR 0     /* clsim::tabulator::LinearAxis (private/clsim/tabulator/Axis.cxx:80-111) */
+#define CLSIMCU_AXIS_POWER  1     /* clsim::tabulator::PowerAxis  (…Axis.cxx:113-171) */
+typedef struct clsimcu_axis {
+    int32_t kind;
+    uint32_t power;               /* POWER */
+    double min, max;
+    uint32_t n_bins;
+    uint32_t reserved0;
+} clsimcu_axis;
+
+#define CLSIMCU_TABLE_SPHERICAL   0   /* SphericalAxes: radius, azimuth [deg], cos(polar), delay time (+ impact cos) */
+#define CLSIMCU_TABLE_CYLINDRICAL 1   /* CylindricalAxes: perpendicular distance, azimuth [rad], depth, delay time (+ impact cos) */
+typedef struct clsimcu_tabulator_config {
+    int32_t struct_size;          /* sizeof(clsimcu_tabulator_config) */
+    int32_t geometry;             /* CLSIMCU_TABLE_* */
+    int32_t num_axes;             /* 4, or 5 to tabulate the impact angle as well (TABULATE_IMPACT_ANGLE) */
+    int32_t store_squared_weights;
+    clsimcu_axis axes[5];
+    double step_length;           /* VOLUME_MODE_STEP, 1 m in the reference (stepLength_) */
+    double reference_area;        /* domArea_, used by the normalisation */
+    int32_t num_angular_coefficients;   /* getAngularAcceptance: I3CLSimFunctionPolynomial (4-axis tables) */
+    int32_t reserved0;
+    const double *angular_coefficients;
+    double min_wavelength, max_wavelength;   /* mediumProperties->GetMin/MaxWavelength(); 0 = 265 nm / 675 nm */
+} clsimcu_tabulator_config;
+
+/* I3CLSimReferenceParticle(source) (…StepToTableConverter.cxx:65-93): position, time and direction of the
+ * particle the coordinates refer to */
+typedef struct clsimcu_reference_particle {
+    double x, y, z, t;
+    double dir_x, dir_y, dir_z;
+} clsimcu_reference_particle;
+
+typedef struct clsimcu_tabulator clsimcu_tabulator;
+
+/* `scene`: wavelength generators, wavelength acceptance (wlen_bias), medium, RNG and device as for
+ * clsimcu_create; geometry and the photon options are ignored (the tabulator sets SAVE_ALL_PHOTONS,
+ * prescale 1 and 42 fixed absorption lengths like the reference's preamble, …cxx:177-183). */
+int clsimcu_tabulator_create(const clsimcu_config *scene, const clsimcu_tabulator_config *config, clsimcu_tabulator **tabulator);
+int clsimcu_tabulator_destroy(clsimcu_tabulator *tabulator);
+
+/* Replaces: EnqueueSteps(steps, reference) (…cxx:290-302) + the harvester thread's launch: propagates the
+ * bunch and adds its photons to the table.  n <= scene->max_num_workitems.  Returns when the launch is queued;
+ * clsimcu_tabulator_finish (Finish, …cxx:304-312) waits for everything. */
+int clsimcu_tabulator_enqueue(clsimcu_tabulator *tabulator, const clsimcu_step *steps, size_t n, const clsimcu_reference_particle *reference);
+int clsimcu_tabulator_finish(clsimcu_tabulator *tabulator);
+
+/* Table geometry and header values: out[0] = number of bins (over-/underflow included), out[1..5] = shape,
+ * out[6..10] = strides, out[11] = n_photons (spectralBiasFactor * sum of photon weights), out[12] = n_group,
+ * out[13] = n_phase (minimum refractive indices, …cxx:96-121), out[14] = spectralBiasFactor, out[15] = photons
+ * propagated so far. */
+int clsimcu_tabulator_info(clsimcu_tabulator *tabulator, double out[16]);
+
+/* Copies the table (and the squared weights, if stored and asked for) to the host after Finish.  normalize != 0
+ * applies Normalize() (…cxx:522-556) to the copy: bin volume / (step_length * reference_area). */
+int clsimcu_tabulator_get_table(clsimcu_tabulator *tabulator, int normalize, float *bins, float *squared_weights, size_t cap);
+
 /* Number of usable CUDA devices (reference: I3CLSimOpenCLDevice::GetAllDevices,
  * private/opencl/I3CLSimOpenCLDevice.cxx, as used by python/traysegments/common.py:10-77).
  * 0 devices is an error: there is no CPU fallback. */

@@ -1171,11 +1171,138 @@ struct WorkItemStats {
     uint64_t photons = 0, segments = 0, crossings = 0;
 };
 
+// ---- table-maker variant (-DTABULATE) --------------------------------------------------------------------
+// The binning code Axes::GenerateBinningCode prints (private/clsim/tabulator/Axes.cxx:71-123, Axis.cxx:44-60),
+// as data, and the table the host loop of I3CLSimStepToTableConverter sums the entries into (…cxx:484-497).
+struct TableAxis {
+    float scale, offset;
+    int nBins;
+    int kind;      // 0 linear, 1 power
+    unsigned power;
+    float invPower;
+    uint64_t stride;
+};
+struct TableSink {
+    int geometry;  // 0 spherical_coordinates.c.cl, 1 cylindrical_coordinates.c.cl
+    int ndim;
+    bool fullAzimuth;
+    TableAxis axes[5];
+    float max0, max3, stepLength, minInvGroupVel, tanThetaC;
+    std::vector<float> angular;   // getAngularAcceptance literals
+    Vec4 refPos, refDir, refPerp; // I3CLSimReferenceParticle
+    double *bins;                 // summed in double: the checker's "exact" sum
+    double *squared;
+    uint64_t entries;
+};
+
+inline float dot4(const Vec4 &a, const Vec4 &b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + a.w * b.w; }   // OpenCL dot(float4, float4)
+inline float magnitude3(const Vec4 &v) { return std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z); }
+
+// getAngularAcceptance as I3CLSimFunctionPolynomial::GetOpenCLFunction nests it (…Polynomial.cxx:139-153)
+float table_angular(const TableSink &t, float x)
+{
+    if (t.angular.empty()) return 0.f;
+    float v = t.angular.back();
+    for (int i = static_cast<int>(t.angular.size()) - 2; i >= 0; --i) v = t.angular[i] + x * v;
+    return v;
+}
+
+void table_coords(const TableSink &t, const Vec4 &absPos, Vec4 dirAndWlen, Rng &rng, float c[5])
+{
+    Vec4 pos{absPos.x - t.refPos.x, absPos.y - t.refPos.y, absPos.z - t.refPos.z, absPos.w - t.refPos.w};
+    const float l = dot4(pos, t.refDir);
+    Vec4 rho{pos.x - l * t.refDir.x, pos.y - l * t.refDir.y, pos.z - l * t.refDir.z, pos.w - l * t.refDir.w};
+    if (t.geometry == 0) {
+        const float n_rho = magnitude3(rho);
+        c[0] = magnitude3(pos);
+        const float azimuth = (n_rho > 0) ? std::acos(dot4(rho, t.refPerp) / n_rho) / (kPI / 180) : 0;
+        if (t.fullAzimuth) {
+            const float cx = rho.y * t.refPerp.z - rho.z * t.refPerp.y, cy = rho.z * t.refPerp.x - rho.x * t.refPerp.z,
+                        cz = rho.x * t.refPerp.y - rho.y * t.refPerp.x;
+            const float azisign = (cx * t.refDir.x + cy * t.refDir.y) + cz * t.refDir.z;
+            c[1] = (azisign > 0) ? 360.f - azimuth : azimuth;
+        } else {
+            c[1] = azimuth;
+        }
+        c[2] = (c[0] > 0) ? (l / c[0]) : 0;
+        c[3] = pos.w - c[0] * t.minInvGroupVel;
+        if (t.ndim > 4) {
+            const float sina = std::sqrt(rand_co(rng));
+            scatter_direction_by_angle(std::sqrt(1 - sina * sina), sina, dirAndWlen, rand_co(rng));
+            c[4] = (c[0] > 0) ? (dot4(dirAndWlen, pos) / c[0]) : 1;
+        }
+    } else {
+        c[0] = magnitude3(rho);
+        c[1] = (c[0] > 0) ? std::acos(dot4(rho, t.refPerp) / c[0]) : 0;
+        c[2] = t.refPos.z + l * t.refDir.z;
+        c[3] = pos.w - (l + c[0] * t.tanThetaC) * 3.33564095f;
+        if (t.ndim > 4) {
+            const float sina = std::sqrt(rand_co(rng));
+            scatter_direction_by_angle(std::sqrt(1 - sina * sina), sina, dirAndWlen, rand_co(rng));
+            const float k = 1.f / t.tanThetaC;
+            Vec4 cpos{absPos.x - (t.refPos.x + (l - rho.x * k) * t.refDir.x), absPos.y - (t.refPos.y + (l - rho.y * k) * t.refDir.y),
+                      absPos.z - (t.refPos.z + (l - rho.z * k) * t.refDir.z), absPos.w - (t.refPos.w + (l - rho.w * k) * t.refDir.w)};
+            const float cdist = magnitude3(cpos);
+            c[4] = (cdist > 0) ? (dot4(dirAndWlen, cpos) / cdist) : 1;
+        }
+    }
+}
+
+uint64_t table_index(const TableSink &t, const float c[5])
+{
+    uint64_t index = 0;
+    for (int i = 0; i < t.ndim; ++i) {
+        const TableAxis &ax = t.axes[i];
+        float v = c[i];
+        if (ax.kind == 1) {
+            if (ax.power == 0) v = 1.f;
+            else if (ax.power == 2) v = std::sqrt(v);
+            else if (ax.power == 3) v = std::cbrt(v);
+            else if (ax.power != 1) v = std::pow(v, ax.invPower);
+        }
+        const float f = std::floor(ax.scale * v - ax.offset);   // convert_int_sat_rtn
+        long long k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647ll : ((f <= -2147483648.f) ? -2147483648ll : static_cast<long long>(f)));
+        k = std::min<long long>(std::max<long long>(k, -1), ax.nBins) + 1;
+        index += ax.stride * static_cast<uint64_t>(k);
+    }
+    return index;
+}
+
+// savePath (propagation_kernel.c.cl:226-304) with an entry buffer that never runs out
+void save_path(TableSink &t, const oracle_step &step, const PhotonState &ph, float thisStepLength, float *prevStepLength, float depth,
+               float thisStepDepth, bool *stop, Rng &rng)
+{
+    const float impactWeight = (t.ndim > 4) ? step.weight : step.weight * table_angular(t, ph.dir.z);
+    float d = *prevStepLength;
+    for (; d < thisStepLength; d += t.stepLength) {
+        Vec4 pos = ph.pos;
+        pos.x = ph.pos.x + d * ph.dir.x;
+        pos.y = ph.pos.y + d * ph.dir.y;
+        pos.z = ph.pos.z + d * ph.dir.z;
+        pos.w = ph.pos.w + d * ph.invGroupVel;
+        float c[5];
+        table_coords(t, pos, ph.dir, rng, c);
+        const bool out = (t.geometry == 0) ? ((c[3] > t.max3) || (c[0] > t.max0)) : (c[3] > t.max3);
+        if (out) {
+            *stop = true;
+            break;
+        }
+        const uint64_t index = table_index(t, c);
+        const float weight = impactWeight * std::exp(-(depth + (d / thisStepLength) * thisStepDepth));
+        t.bins[index] += weight;
+        if (t.squared) t.squared[index] += static_cast<double>(weight) * weight;
+        ++t.entries;
+    }
+    *prevStepLength = d - thisStepLength;
+}
+
 // One work-item of propKernel (propagation_kernel.c.cl:406-913).  max_photons limits the
 // photons taken from the step (single-photon replay uses 1).
 void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, HitSink &sink, WorkItemStats &st,
-                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr, uint32_t aAfterCreation = 0)
+                   uint32_t maxPhotons, TrajSink *traj, const uint64_t *xAfterCreation = nullptr, uint32_t aAfterCreation = 0,
+                   TableSink *table = nullptr)
 {
+    float depthPropagated = 0.f, prevStepRemainder = 0.f;   // TABULATE
     const Medium &m = sc.med;
     Vec4 stepDir;
     {
@@ -1200,11 +1327,13 @@ void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, Hi
             ph.startDir = ph.dir;
             ph.numScatters = 0;
             ph.totalPath = 0.f;
+            if (table) prevStepRemainder = table->stepLength * rand_oc(rng);   // propagation_kernel.c.cl:566-569
             if (tiltConstant) currentPhotonLayer = std::min(std::max(find_layer(m, ph.pos.z), 0), m.L - 1);
             ph.invGroupVel = 1.f / group_velocity(m, ph.dir.w);
             if (sc.fixedAbs) ph.absLensInitial = sc.fixedAbsLens;
             else ph.absLensInitial = -std::log(rand_oc(rng));
             abs_lens_left = ph.absLensInitial;
+            if (table) depthPropagated = 0.f;   // :590-592
             // replay of a photon that was created from one stream and propagated from another
             // (the B200 fast kernel keeps a creation stream and a propagation stream per lane)
             if (xAfterCreation) {
@@ -1285,6 +1414,15 @@ void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, Hi
             if (sc.stop && collided) abs_lens_left = 0.f;
         }
 
+        if (table) {
+            // :755-785
+            bool stop = false;
+            save_path(*table, step, ph, distancePropagated, &prevStepRemainder, depthPropagated,
+                      ph.absLensInitial - abs_lens_left - depthPropagated, &stop, rng);
+            if (stop) abs_lens_left = 0.f;
+            depthPropagated = ph.absLensInitial - abs_lens_left;
+        }
+
         ph.pos.x += ph.dir.x * distancePropagated;
         ph.pos.y += ph.dir.y * distancePropagated;
         ph.pos.z += ph.dir.z * distancePropagated;
@@ -1293,7 +1431,7 @@ void run_work_item(const oracle_scene &sc, const oracle_step &step, Rng &rng, Hi
 
         if (abs_lens_left < kEpsilon) {
             --photonsLeft;
-            if (sc.saveAll) {
+            if (sc.saveAll && !table) {   // #if defined(SAVE_ALL_PHOTONS) && !defined(TABULATE)
                 if (rand_co(rng) < sc.prescale) {
                     save_hit(sc, sink, ph.pos, ph.dir, 0.f, ph.invGroupVel, ph.totalPath, ph.numScatters, ph.absLensInitial,
                              ph.startPos, ph.startDir, step, 0, 0, curHistory.data());
@@ -1515,6 +1653,66 @@ uint64_t oracle_propagate(const oracle_scene *scene, const oracle_step *steps, s
     }
     if (stats) { stats[0] = totPhot; stats[1] = totSeg; stats[2] = totCross; stats[3] = totDraws; }
     return count;
+}
+
+uint64_t oracle_tabulate(const oracle_scene *scene, const oracle_table_config *tc, const oracle_step *steps, size_t n, uint64_t *rng_x,
+                         const uint32_t *rng_a, const double reference[7], double *bins, double *squared)
+{
+    if (!scene->saveAll || !scene->fixedAbs) {
+        g_last_error = "the table-maker variant needs save_all_photons and a fixed number of absorption lengths";
+        return 0;
+    }
+    TableSink t;
+    t.geometry = tc->geometry;
+    t.ndim = tc->num_axes;
+    t.fullAzimuth = (tc->geometry == 0 && tc->axis_max[1] > 180.);
+    uint64_t stride = 1;
+    for (int i = tc->num_axes - 1; i >= 0; --i) {
+        TableAxis &ax = t.axes[i];
+        ax.kind = tc->axis_kind[i];
+        ax.power = tc->axis_power[i];
+        ax.nBins = static_cast<int>(tc->axis_bins[i]);
+        auto inverse = [&](double v) { return ax.kind == 1 ? std::pow(v, 1. / ax.power) : v; };
+        // Axis::GetIndexCode (Axis.cxx:44-60)
+        const double scale = ax.nBins / (inverse(tc->axis_max[i]) - inverse(tc->axis_min[i]));
+        ax.scale = lit(scale);
+        ax.offset = lit(scale * inverse(tc->axis_min[i]));
+        ax.invPower = (ax.kind == 1 && ax.power > 0) ? lit(1. / ax.power) : 0.f;
+        ax.stride = stride;
+        stride *= static_cast<uint64_t>(ax.nBins) + 2;
+    }
+    t.max0 = lit(tc->axis_max[0]);
+    t.max3 = lit(tc->axis_max[3]);
+    t.stepLength = lit(tc->step_length);
+    t.minInvGroupVel = lit(tc->n_group / 0.299792458);
+    t.tanThetaC = lit(std::sqrt(tc->n_phase * tc->n_phase - 1.));
+    for (int i = 0; i < tc->num_angular_coefficients; ++i) t.angular.push_back(lit(tc->angular_coefficients[i]));
+    // I3CLSimReferenceParticle (…StepToTableConverter.cxx:65-93)
+    t.refPos = Vec4{static_cast<float>(reference[0]), static_cast<float>(reference[1]), static_cast<float>(reference[2]), static_cast<float>(reference[3])};
+    t.refDir = Vec4{static_cast<float>(reference[4]), static_cast<float>(reference[5]), static_cast<float>(reference[6]), 0.f};
+    {
+        const double perpz = std::hypot(reference[4], reference[5]);
+        double px = 1., py = 0., pz = 0.;
+        if (perpz > 0.) {
+            px = -reference[4] * reference[6] / perpz;
+            py = -reference[5] * reference[6] / perpz;
+            pz = perpz;
+            const double norm = std::sqrt(px * px + py * py + pz * pz);
+            px /= norm; py /= norm; pz /= norm;
+        }
+        t.refPerp = Vec4{static_cast<float>(px), static_cast<float>(py), static_cast<float>(pz), 0.f};
+    }
+    t.bins = bins;
+    t.squared = squared;
+    t.entries = 0;
+    HitSink sink{nullptr, 0, nullptr, 0, {}, {}, false};
+    for (size_t i = 0; i < n; ++i) {
+        Rng rng{rng_x[i], rng_a[i], 0};
+        WorkItemStats st;
+        run_work_item(*scene, steps[i], rng, sink, st, 0xffffffffu, nullptr, nullptr, 0, &t);
+        rng_x[i] = rng.x;
+    }
+    return t.entries;
 }
 
 int oracle_propagate_single_photon(const oracle_scene *scene, const oracle_step *step, uint64_t *x, uint32_t a, oracle_photon *out,

@@ -157,6 +157,26 @@ uint64_t oracle_propagate(const oracle_scene *scene, const oracle_step *steps, s
                           oracle_photon *out, size_t cap, float *history,
                           int num_threads, uint64_t stats[4]);
 
+/* Table-maker variant (-DTABULATE, propagation_kernel.c.cl:226-304, 755-785): propKernel over n work-items with
+ * savePath instead of the DOMs; every (index, weight) entry is added to bins[] (and weight^2 to squared[], if not
+ * NULL) in double precision.  The scene must have been created with save_all_photons and a fixed number of
+ * absorption lengths.  reference = {x, y, z, t, dir_x, dir_y, dir_z} of the reference particle.  Returns the
+ * number of entries. */
+typedef struct oracle_table_config {
+    int32_t geometry;            /* 0 spherical, 1 cylindrical */
+    int32_t num_axes;            /* 4 or 5 */
+    int32_t axis_kind[5];        /* 0 linear, 1 power */
+    uint32_t axis_power[5];
+    uint32_t axis_bins[5];
+    int32_t num_angular_coefficients;
+    double axis_min[5], axis_max[5];
+    double step_length;
+    double n_group, n_phase;     /* minimum refractive indices (…StepToTableConverter.cxx:96-121) */
+    const double *angular_coefficients;
+} oracle_table_config;
+uint64_t oracle_tabulate(const oracle_scene *scene, const oracle_table_config *config, const oracle_step *steps, size_t n,
+                         uint64_t *rng_x, const uint32_t *rng_a, const double reference[7], double *bins, double *squared);
+
 /* One photon of `step` from RNG state (*x, a).  traj: NULL or room for
  * max_points * 8 floats {x,y,z,t,dx,dy,dz,abs_lens_left} recorded at creation
  * and after every segment.  Returns 1 if a record was written to *out (hit, or

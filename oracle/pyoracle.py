@@ -115,6 +115,40 @@ class Scene(object):
         st = {"photons": int(stats[0]), "segments": int(stats[1]), "crossings": int(stats[2]), "draws": int(stats[3])}
         return out[:k], int(cnt), st, x, (hist[:k] if hist is not None else None)
 
+    def tabulate(self, axes, steps, rng_x, rng_a, reference, n_group, n_phase, angular_coefficients=None, step_length=1.0, squared=False):
+        """Table-maker variant: -> (bins[float64], squared or None, entries, new rng_x).  `axes`: an object with
+        .geometry and .axes (kind, power, min, max, n_bins), e.g. clsim_b200.tabulator.SphericalAxes."""
+        class TableConfig(C.Structure):
+            _fields_ = [("geometry", C.c_int32), ("num_axes", C.c_int32), ("axis_kind", C.c_int32 * 5), ("axis_power", C.c_uint32 * 5),
+                        ("axis_bins", C.c_uint32 * 5), ("num_angular_coefficients", C.c_int32), ("axis_min", C.c_double * 5),
+                        ("axis_max", C.c_double * 5), ("step_length", C.c_double), ("n_group", C.c_double), ("n_phase", C.c_double),
+                        ("angular_coefficients", C.POINTER(C.c_double))]
+        tc = TableConfig()
+        tc.geometry, tc.num_axes = int(axes.geometry), len(axes.axes)
+        for i, ax in enumerate(axes.axes):
+            tc.axis_kind[i], tc.axis_power[i], tc.axis_bins[i], tc.axis_min[i], tc.axis_max[i] = ax.kind, ax.power, ax.n_bins, ax.min, ax.max
+        tc.step_length, tc.n_group, tc.n_phase = float(step_length), float(n_group), float(n_phase)
+        coef = np.ascontiguousarray(angular_coefficients if angular_coefficients is not None else [], dtype=np.float64)
+        tc.num_angular_coefficients = len(coef)
+        tc.angular_coefficients = coef.ctypes.data_as(C.POINTER(C.c_double))
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        n = len(steps)
+        x = np.array(rng_x[:n], dtype=np.uint64, copy=True)
+        a = np.ascontiguousarray(rng_a[:n], dtype=np.uint32)
+        nb = 1
+        for ax in axes.axes:
+            nb *= ax.n_bins + 2
+        bins = np.zeros(nb, dtype=np.float64)
+        sq = np.zeros(nb, dtype=np.float64) if squared else None
+        ref = (C.c_double * 7)(*[float(v) for v in reference])
+        fn = lib().oracle_tabulate
+        fn.restype = C.c_uint64
+        fn.argtypes = [C.c_void_p, C.POINTER(TableConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+        entries = fn(self._h, C.byref(tc), steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, ref, bins.ctypes.data, sq.ctypes.data if squared else None)
+        if entries == 0 and lib().oracle_last_error():
+            pass
+        return bins, sq, int(entries), x
+
     def single_photon(self, step, x, a, max_points=0):
         step = np.ascontiguousarray(step, dtype=STEP_DTYPE).reshape(1)
         out = np.zeros(1, dtype=PHOTON_DTYPE)

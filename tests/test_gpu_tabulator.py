@@ -1,0 +1,131 @@
+"""Table-maker variant on the device against the oracle: same RNG streams, same photons, the same
+table up to the order of the float additions and the last bits of libm."""
+import math
+
+import numpy as np
+import pytest
+
+from clsim_b200 import capi, ice, mcpe, stepgen, steps, tabulator
+from clsim_b200.description import ConverterOptions
+from oracle import pyoracle
+from tests.scenes import rng_streams
+
+pytestmark = pytest.mark.gpu
+
+DOM_AREA = math.pi * 0.1651 ** 2
+
+
+def make(name, axes, n_items, squared=False, seed=5):
+    medium = ice.MakeHomogeneousIceMediumProperties("spice_mie") if name == "homogeneous" else \
+        ice.MakeIceCubeMediumProperties(iceDataDirectory=name, useTiltIfAvailable=True)
+    acc = ice.GetIceCubeDOMAcceptance(domRadius=0.1651)
+    ang = mcpe.GetIceCubeDOMAngularSensitivity()
+    a, x = rng_streams(n_items, seed=seed)
+    conv = tabulator.I3CLSimStepToTableConverter(0, axes, 0, squared, medium, None, DOM_AREA, acc, ang, seed, maxNumWorkitems=n_items, rng_a=a, rng_x=x)
+    gen = ice.makeCherenkovWavelengthGenerator(acc, False, medium)
+    opt = ConverterOptions(stop_detected_photons=False, save_all_photons=True, save_all_photons_prescale=1.0, fixed_number_of_absorption_lengths=42.0)
+    scene = pyoracle.Scene(medium, None, [gen], acc, opt)
+    return conv, scene, ang, a, x, medium, acc
+
+
+def tables_agree(dev, ora, tol=2e-3):
+    """Same sum and the same distribution over the bins: an entry may land in the neighbouring bin when the last bit
+    of acosf/sqrtf/expf differs between CUDA and glibc."""
+    assert abs(dev.sum() / ora.sum() - 1) < 1e-4
+    assert np.abs(dev - ora).sum() / ora.sum() < tol
+    assert np.count_nonzero((dev > 0) != (ora > 0)) < 0.02 * np.count_nonzero(ora > 0) + 5
+
+
+def test_spherical_table_equals_the_oracle():
+    axes = tabulator.SphericalAxes([tabulator.PowerAxis(0, 580, 40, 2), tabulator.LinearAxis(0, 180, 9), tabulator.LinearAxis(-1, 1, 20),
+                                    tabulator.PowerAxis(0, 7e3, 30, 2)])
+    n = 256
+    conv, scene, ang, a, x, medium, acc = make("spice_mie", axes, n, squared=True)
+    info = conv.info()
+    assert info["n_bins"] == axes.GetNBins() and info["shape"] == axes.GetShape() and info["strides"] == axes.GetStrides()
+    # GetMinimumRefractiveIndex (…StepToTableConverter.cxx:96-121), sampling quirk included
+    best = (math.inf, math.inf)
+    for i in range(1000):
+        w = 265e-9 + i * (675e-9 - 265e-9)
+        ng, npv = medium.GetGroupRefractiveIndex(w), medium.GetPhaseRefractiveIndex(w)
+        if ng > 1 and ng < best[0]:
+            best = (ng, npv)
+    assert abs(info["n_group"] - best[0]) < 1e-12 and abs(info["n_phase"] - best[1]) < 1e-12
+    from clsim_b200.description import WlenBias
+    want_bias = stepgen.NumberOfPhotonsPerMeter(medium, WlenBias(constant=1.0), 300e-9, 600e-9) / stepgen.NumberOfPhotonsPerMeter(medium, acc, 265e-9, 675e-9)
+    assert abs(info["spectral_bias_factor"] / want_bias - 1) < 1e-4
+
+    reference = (10.0, -20.0, 30.0, 5.0, math.sin(0.4) * math.cos(1.0), math.sin(0.4) * math.sin(1.0), math.cos(0.4))
+    bunch = steps.cascade_steps(n, photons_per_step=20, energy_gev=1e3, pos=reference[:3], zenith_deg=180 - math.degrees(0.4), azimuth_deg=math.degrees(1.0) + 180, seed=7)
+    bunch["t"] += 5.0
+    conv.EnqueueSteps(bunch, reference)
+    conv.Finish()
+    dev, dev_sq = conv.GetTable()
+    ora, ora_sq, entries, x1 = scene.tabulate(axes, bunch, x, a, reference, info["n_group"], info["n_phase"], angular_coefficients=ang.coefficients, squared=True)
+    assert entries > 1e5 and dev.sum() > 0
+    tables_agree(dev, ora)
+    tables_agree(dev_sq, ora_sq, tol=4e-3)
+    info = conv.info()
+    assert info["photons"] == n * 20 and abs(info["n_photons"] - info["spectral_bias_factor"] * n * 20) < 1e-6 * info["n_photons"]
+    # light is where the cascade points: more in the forward hemisphere (cos polar > 0) than behind
+    full = dev.reshape(axes.GetShape())
+    assert full[:, :, 12:, :].sum() > 2 * full[:, :, :10, :].sum()
+
+    # Normalize() (…cxx:522-556) of the same table
+    norm, norm_sq = conv.GetTable(normalize=True)
+    want = dev.astype(np.float64).reshape(axes.GetShape()).copy()
+    shape = axes.GetShape()
+    for i in range(shape[0]):
+        for j in range(shape[1]):
+            for k in range(shape[2]):
+                idx = [min(max(v - 1, 0), s - 3) for v, s in zip((i, j, k), shape)]
+                want[i, j, k] /= axes.GetBinVolume(idx) / (1.0 * DOM_AREA)
+    assert np.allclose(norm.reshape(shape), want, rtol=1e-6, atol=0)
+
+    # a second bunch adds to the table; the RNG streams continue
+    conv.EnqueueSteps(bunch, reference)
+    conv.Finish()
+    dev2, _ = conv.GetTable()
+    ora2, _, _, _ = scene.tabulate(axes, bunch, x1, a, reference, info["n_group"], info["n_phase"], angular_coefficients=ang.coefficients)
+    tables_agree(dev2, ora + ora2)
+    conv.close()
+
+
+def test_cylindrical_table_with_impact_angle_on_tilted_anisotropic_ice():
+    axes = tabulator.CylindricalAxes([tabulator.PowerAxis(0, 580, 30, 2), tabulator.LinearAxis(0, math.pi, 9), tabulator.LinearAxis(-8e2, 8e2, 20),
+                                      tabulator.PowerAxis(0, 7e3, 30, 2), tabulator.LinearAxis(-1, 1, 10)])
+    n = 256
+    conv, scene, ang, a, x, medium, acc = make("spice_lea", axes, n, seed=9)
+    info = conv.info()
+    reference = (0.0, 0.0, -100.0, 0.0, 0.0, 0.6, 0.8)
+    bunch = steps.muon_track_steps(n, photons_per_step=20, track_length=400.0, zenith_deg=math.degrees(math.acos(-0.8)), azimuth_deg=270.0,
+                                   center=(0.0, 0.0, -100.0), seed=8)
+    conv.EnqueueSteps(bunch, reference)
+    conv.Finish()
+    dev, none = conv.GetTable()
+    assert none is None
+    ora, _, entries, _ = scene.tabulate(axes, bunch, x, a, reference, info["n_group"], info["n_phase"])
+    assert entries > 1e5
+    tables_agree(dev, ora, tol=4e-3)
+    conv.close()
+
+
+def test_full_azimuth_table_and_limits():
+    axes = tabulator.SphericalAxes([tabulator.PowerAxis(0, 200, 20, 2), tabulator.LinearAxis(0, 360, 12), tabulator.LinearAxis(-1, 1, 10),
+                                    tabulator.PowerAxis(0, 1500, 20, 2)])
+    n = 128
+    conv, scene, ang, a, x, medium, acc = make("homogeneous", axes, n, seed=11)
+    info = conv.info()
+    reference = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0)
+    bunch = steps.point_source_steps(n, 20, seed=12)
+    conv.EnqueueSteps(bunch, reference)
+    conv.EnqueueSteps(None, reference)          # ignored like the reference does (…cxx:293-294)
+    conv.Finish()
+    dev, _ = conv.GetTable()
+    ora, _, _, _ = scene.tabulate(axes, bunch, x, a, reference, info["n_group"], info["n_phase"], angular_coefficients=ang.coefficients)
+    tables_agree(dev, ora)
+    full = dev.reshape(axes.GetShape())
+    assert full[:, 7:13].sum() > 0.3 * dev.sum() and full[-1].sum() == 0    # both azimuth halves are used; nothing beyond the radius bound
+    with pytest.raises(capi.ClsimCudaError, match="greater than maximum number of work items"):
+        conv.EnqueueSteps(steps.point_source_steps(n + 1, 20, seed=13), reference)
+    conv.close()

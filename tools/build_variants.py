@@ -31,7 +31,7 @@ def main():
             if "ILb0ELb0ELb0" in line:
                 idx = log.stdout.splitlines().index(line)
                 print(tag, " | ".join(l.strip() for l in log.stdout.splitlines()[idx + 1: idx + 3]))
-        objs = [obj] + [os.path.join(g.BUILD, o) for o in ("kernel_reference.o", "engine.o", "mcpe.o", "stepgen.o", "tables.o")]
+        objs = [obj] + [os.path.join(g.BUILD, o) for o in ("kernel_reference.o", "engine.o", "mcpe.o", "stepgen.o", "tabulate.o", "tables.o")]
         lib = os.path.join(out_dir, "libclsimcuda_%s.so" % tag)
         subprocess.check_call([g._nvcc(), "-ccbin", g._host_cxx()] + g.ARCH + ["-shared", "-o", lib] + objs + ["-lpthread", "-ldl"])
         print("built", lib)
