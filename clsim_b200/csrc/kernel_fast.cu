@@ -1078,6 +1078,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
         __syncwarp();
     }
     st[kStatus * kThreads] = __uint_as_float(status);
+    __syncwarp();   // every lane has read the control block before lane 0 rewrites it
     if (lane == 0) wctl[kWQueued] = queued;
 
     const int n_idle = __popc(__ballot_sync(0xffffffffu, status == kDead));
@@ -1211,6 +1212,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         }
         if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
+        __syncwarp();   // every lane has read the control block before lane 0 rewrites it
         if (lane == 0) wctl[kWQueued] = queued;
         __syncwarp();
     }
