@@ -21,6 +21,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -47,6 +48,26 @@ int fail(int code, const std::string &msg)
 {
     t_last_error = msg;
     return code;
+}
+
+// Large host-to-host copies (a 48 MiB bunch into pinned staging, 18 MB of hits out of the pinned mirror) are on the
+// latency path of the first and the last bunch of a run: split them over a few threads.
+void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kPerThread = size_t(4) << 20;
+    const unsigned parts = static_cast<unsigned>(std::min<size_t>(4, bytes / kPerThread));
+    if (parts < 2) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t chunk = ((bytes / parts) + 63) & ~size_t(63);
+    std::vector<std::thread> pool;
+    for (unsigned p = 1; p < parts; ++p) {
+        const size_t at = p * chunk, len = (p + 1 == parts) ? bytes - at : chunk;
+        pool.emplace_back([=] { std::memcpy(static_cast<char *>(dst) + at, static_cast<const char *>(src) + at, len); });
+    }
+    std::memcpy(dst, src, chunk);
+    for (std::thread &t : pool) t.join();
 }
 
 struct CudaError : std::runtime_error {
@@ -129,7 +150,8 @@ struct Bunch {
 
 struct HostResult {
     uint32_t identifier = 0;
-    std::vector<clsimcu_photon> photons;
+    std::unique_ptr<clsimcu_photon[]> photons;   // not a vector: no zero-fill of 18 MB before it is overwritten
+    size_t num_photons = 0;
     std::vector<float> history;
     std::vector<clsimcu_mcpe> mcpes;
     uint64_t generated = 0, counted = 0;
@@ -510,7 +532,6 @@ void submit_loop(clsimcu_engine *e)
                 a.rng_a = e->d_rng_a;
                 a.count_stats = 0;
                 a.scene_dev = e->d_scene;
-            a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
                 a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
                 launch(*e, a, e->compute);
                 CUDA_OK(cudaEventRecord(s.k_stop, e->compute));
@@ -588,7 +609,9 @@ void drain_loop(clsimcu_engine *e)
                 if (e->history_entries > 0)
                     CUDA_OK(cudaMemcpyAsync(s.h_history, s.d_history, n * e->history_entries * 4 * sizeof(float), cudaMemcpyDeviceToHost, s.xfer));
                 CUDA_OK(cudaStreamSynchronize(s.xfer));
-                res->photons.assign(s.h_photons, s.h_photons + n);
+                res->photons.reset(new clsimcu_photon[n]);
+                res->num_photons = n;
+                parallel_copy(res->photons.get(), s.h_photons, n * sizeof(clsimcu_photon));
                 if (e->history_entries > 0) unroll_history(s.h_history, s.h_photons, n, e->history_entries, res->history);
             }
             {
@@ -901,7 +924,7 @@ int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint
     b.identifier = identifier;
     b.num_steps = n;
     if (int rc = acquire_staging(e, b.staging)) return rc;
-    std::memcpy(e->staging[b.staging], steps, n * sizeof(clsimcu_step));
+    parallel_copy(e->staging[b.staging], steps, n * sizeof(clsimcu_step));
     for (size_t i = 0; i < n; ++i) b.generated += steps[i].num_photons;
     if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
     return CLSIMCU_OK;
@@ -921,8 +944,8 @@ int clsimcu_get_result(clsimcu_engine *e, clsimcu_result *r)
     static clsimcu_photon empty_photon;
     r->identifier = res->identifier;
     r->reserved0 = 0;
-    r->num_photons = res->photons.size();
-    r->photons = res->photons.empty() ? &empty_photon : res->photons.data();
+    r->num_photons = res->num_photons;
+    r->photons = res->num_photons == 0 ? &empty_photon : res->photons.get();
     r->history = (e->history_entries > 0 && !res->history.empty()) ? res->history.data() : nullptr;
     r->num_photons_generated = res->generated;
     r->num_hits_counted = res->counted;
