@@ -1,6 +1,6 @@
 """First-contact GPU script: reference-order kernel vs oracle, fast kernel rate, OpenCL ICD probe."""
 import ctypes, os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from clsim_b200 import capi, geometry, ice, steps
 from clsim_b200.description import ConverterOptions, KERNEL_FAST, KERNEL_REFERENCE

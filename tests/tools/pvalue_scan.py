@@ -1,8 +1,8 @@
 """Repeat the fast-kernel vs reference-order-kernel comparison with different seeds and print the p-values:
 a check that a borderline p-value in one run of a statistical test is a fluctuation and not a bias.
-usage (on the GPU box): python tools/pvalue_scan.py [scene] [n_steps] [repeats]"""
+usage (on the GPU box): python tests/tools/pvalue_scan.py [scene] [n_steps] [repeats]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from clsim_b200 import steps
 from clsim_b200.description import KERNEL_FAST, KERNEL_REFERENCE
