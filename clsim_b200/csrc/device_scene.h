@@ -33,6 +33,11 @@ struct DevMedium {
     int scat_kind;
     float f_sl, one_minus_f_sl, g, g2, sl_beta;
     float inv_f_sl, inv_one_minus_f_sl, inv_2g; // fast kernel: reciprocals (0 where undefined)
+    // fast kernel, SL + HG mix folded into constants (computed in double on the host, see upload_tables):
+    //   cos_sl = ex2(sl_beta * lg2(u) + sl_off) - 1            == 2 (u / f_sl)^beta - 1
+    //   cos_hg = hg_c - hg_w * r^2,  r = 1 / (hg_h0 + hg_h1 u) == ((1 + g^2) - ((1 - g^2) / (1 + g s))^2) / 2g,  s = 2 (1 - u) / (1 - f_sl) - 1
+    float sl_off, hg_h0, hg_h1, hg_c, hg_w;
+    int mix_folded; // the five constants above are set (f_sl in (0,1), g != 0)
     int tilt_nd, tilt_nz;
     float tilt_z0, tilt_dz, tilt_inv_dz, tilt_lnx, tilt_lny;
     int anisotropy, pre_renorm, post_renorm;
@@ -63,8 +68,8 @@ struct DevGeometry {
     const float *tmpl_z;
     const uint32_t *string_tmpl_start;
     const float *string_mean_x, *string_mean_y;
-    // Fast kernel only: pixel map over the xy plane.  near_info[pixel] = index of the string
-    // nearest to the pixel centre (low 16 bits) | the RANGE of the pixel, stored as the upper 16
+    // Fast kernel only: pixel map over the xy plane.  near_info[pixel] = 16 x the index of the string
+    // nearest to the pixel centre (low 16 bits: at most 4095 strings) | the RANGE of the pixel, stored as the upper 16
     // bits of an fp32 (rounded down): a photon anywhere in the pixel can fly that far before any
     // OTHER string can come within string_max_radius of it.  The fast kernel cuts flights at that
     // range, so a segment only ever has to be tested against the one named string (exactly, from

@@ -286,6 +286,15 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     dm.inv_f_sl = (m.f_sl > 0.f) ? 1.f / m.f_sl : 0.f;
     dm.inv_one_minus_f_sl = (m.one_minus_f_sl > 0.f) ? 1.f / m.one_minus_f_sl : 0.f;
     dm.inv_2g = (m.g != 0.f) ? 1.f / (2.f * m.g) : 0.f;
+    if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && m.f_sl > 0.f && m.one_minus_f_sl > 0.f && m.g != 0.f) {
+        const double f = m.f_sl, omf = m.one_minus_f_sl, g = m.g;
+        dm.sl_off = static_cast<float>(static_cast<double>(m.sl_beta) * std::log2(1.0 / f) + 1.0);
+        dm.hg_h0 = static_cast<float>(1.0 + g * (2.0 / omf - 1.0));
+        dm.hg_h1 = static_cast<float>(-2.0 * g / omf);
+        dm.hg_c = static_cast<float>((1.0 + g * g) / (2.0 * g));
+        dm.hg_w = static_cast<float>((1.0 - g * g) * (1.0 - g * g) / (2.0 * g));
+        dm.mix_folded = 1;
+    }
     dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
     dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
     dm.tilt_inv_dz = (m.tilt_nd > 0 && m.tilt_dz != 0.f) ? 1.f / m.tilt_dz : 0.f;
@@ -410,7 +419,7 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
                     uint32_t bits;
                     std::memcpy(&bits, &rf, 4);
                     bits &= 0xffff0000u; // truncation of a positive float rounds down: the bound stays a lower bound
-                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = static_cast<uint32_t>(who) | bits;
+                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = (static_cast<uint32_t>(who) << 4) | bits; // byte offset of the string's 16-byte record
                 }
             }
             o_near_info = arena.add(info);

@@ -68,16 +68,15 @@ namespace {
 #ifndef CLSIMCU_IDLE_LIMIT_SAVE_ALL
 #define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
 #endif
-#ifndef CLSIMCU_RENORM_EVERY
-#define CLSIMCU_RENORM_EVERY 0
+#ifndef CLSIMCU_HOT_UNROLL
+#define CLSIMCU_HOT_UNROLL 2
 #endif
 #ifndef CLSIMCU_REFILL_BATCH
 #define CLSIMCU_REFILL_BATCH 4
 #endif
 constexpr int kThreads = CLSIMCU_THREADS;
-// Direction renormalisation in the hot loop: 0 = only when a fast phase starts (every few dozen iterations, the
-// drift of the unit length is a few 1e-7 per scatter); N (power of two) = on every N-th iteration as well
-constexpr uint32_t kRenormEvery = CLSIMCU_RENORM_EVERY;
+// legs a lane flies between two looks at the warp's state (ballots, refill decisions) in the hot loop
+constexpr int kHotUnroll = CLSIMCU_HOT_UNROLL;
 constexpr int kRefillBatch = CLSIMCU_REFILL_BATCH;            // lanes without a photon that make the warp stop for a refill
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
@@ -131,18 +130,19 @@ __device__ __forceinline__ float fast_ln(float x) { return kLn2 * mufu_lg2(x); }
 struct Mwc {
     uint64_t x;
     uint32_t a;
-    // mwcrng_kernel.cl:12-28; the conversion rounds toward zero so 1.0 is never returned
-    __device__ __forceinline__ float co()
+    // mwcrng_kernel.cl:12-28
+    // (written as one mad.wide on the two halves: ptxas then emits IMAD.WIDE + a two-instruction carry chain instead
+    // of shuffling the state through an aligned register pair)
+    __device__ __forceinline__ uint32_t next()
     {
-        x = static_cast<uint64_t>(static_cast<uint32_t>(x)) * a + (x >> 32);
-        return __uint2float_rz(static_cast<uint32_t>(x)) * 2.3283064365386963e-10f;
+        const uint32_t lo = static_cast<uint32_t>(x), hi = static_cast<uint32_t>(x >> 32);
+        asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(x) : "r"(lo), "r"(a), "l"(static_cast<uint64_t>(hi)));
+        return static_cast<uint32_t>(x);
     }
+    // the conversion rounds toward zero so 1.0 is never returned
+    __device__ __forceinline__ float co() { return __uint2float_rz(next()) * 2.3283064365386963e-10f; }
     // 1 - u/2^32 in one FMA (the scaling is exact, so this equals the two-step form)
-    __device__ __forceinline__ float oc()
-    {
-        x = static_cast<uint64_t>(static_cast<uint32_t>(x)) * a + (x >> 32);
-        return __fmaf_rn(__uint2float_rz(static_cast<uint32_t>(x)), -2.3283064365386963e-10f, 1.0f);
-    }
+    __device__ __forceinline__ float oc() { return __fmaf_rn(__uint2float_rz(next()), -2.3283064365386963e-10f, 1.0f); }
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -154,7 +154,7 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 
 // Shared-memory plan, carved out of the dynamic allocation.
 struct SmemLayout {
-    uint32_t off_layers, off_bounds, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_tilt_dist, off_tilt_corr;
+    uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_tilt_dist, off_tilt_corr;
     uint32_t off_state;   // per-thread arrays: state | birth tag | segment counter | propagation-stream tag (save-all only)
     uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
     uint32_t cell_offset[kMaxSubdetectors];
@@ -169,8 +169,8 @@ struct SmemHeader {
 };
 
 struct SmemPlan {
-    float4 *layers;          // [num_layers] (b400, D*aDust+E, 1+0.01*dTau, 0)
-    float2 *bounds;          // [num_layers] (lower, upper) boundary z; -/+1e30 where there is no layer beyond
+    float4 *layers;          // [num_layers + 1] (b400, 1+0.01*dTau, D*aDust+E, lower boundary z); the upper boundary of a
+                             // layer is the lower one of the next entry; -/+1e30 where there is no layer beyond
     float4 *strings;         // [num_strings] (x, y, zmax+R, zmin-R)
     float4 *sets;            // [num_sets] (start_z, 1/height, num_layers, row offset)
     uint8_t *string_set;     // [num_strings]
@@ -187,8 +187,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
 {
     SmemLayout L{};
     uint32_t at = align16(sizeof(SmemHeader));
-    L.off_layers = at; at = align16(at + s.medium.num_layers * 16);
-    L.off_bounds = at; at = align16(at + s.medium.num_layers * 8);
+    L.off_layers = at; at = align16(at + (s.medium.num_layers + 1) * 16);
     L.off_strings = at; at = align16(at + s.geo.num_strings * 16);
     L.off_sets = at; at = align16(at + s.geo.num_sets * 16);
     L.off_string_set = at; at = align16(at + s.geo.num_strings);
@@ -220,7 +219,6 @@ __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
     uint8_t *smem = smem_base();
     SmemPlan sp;
     sp.layers = reinterpret_cast<float4 *>(smem + lay.off_layers);
-    sp.bounds = reinterpret_cast<float2 *>(smem + lay.off_bounds);
     sp.strings = reinterpret_cast<float4 *>(smem + lay.off_strings);
     sp.sets = reinterpret_cast<float4 *>(smem + lay.off_sets);
     sp.string_set = smem + lay.off_string_set;
@@ -260,7 +258,7 @@ __device__ __forceinline__ void rotate_by(float cosa, float sina, V3 &d, float r
     }
     // the rotation preserves the length up to rounding (a few 1e-7 per scatter with the approximate sine and
     // cosine), so one Newton step of 1/sqrt about 1 is exact to fp32 here and keeps the special-function unit
-    // free; the hot loop leaves it to the start of each fast phase (kRenormEvery)
+    // free; the hot loop leaves it to the start of each fast phase
     if (renormalize) {
         const float inv = fmaf(nx * nx + ny * ny + nz * nz, -0.5f, 1.5f);
         nx *= inv; ny *= inv; nz *= inv;
@@ -380,12 +378,6 @@ __device__ __forceinline__ void apply_matrix(const float *M, V3 &d)
     const float nz = M[6] * d.x + M[7] * d.y + M[8] * d.z;
     const float inv = mufu_rsqrt(nx * nx + ny * ny + nz * nz);
     d.x = nx * inv; d.y = ny * inv; d.z = nz * inv;
-}
-
-__device__ __forceinline__ float safe_inv_dz(float dz)
-{
-    // the reference treats |dz| < 1e-5 as "stays in its layer" (propagation_kernel.c.cl:669)
-    return (fabsf(dz) < kEpsilon) ? ((dz < 0.f) ? -1e30f : 1e30f) : mufu_rcp(dz);
 }
 
 // ---- R6: DOM collision, restated for SIMT -----------------------------------------------------
@@ -530,7 +522,7 @@ __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint
     slot[kQx * 32] = b.pos.x; slot[kQy * 32] = b.pos.y; slot[kQz * 32] = b.pos.z;
     slot[kQDx * 32] = b.dir.x; slot[kQDy * 32] = b.dir.y; slot[kQDz * 32] = b.dir.z;
     // derived here, where all 32 lanes work, rather than when a lane takes the photon
-    slot[kQInvDz * 32] = safe_inv_dz(b.dir.z);
+    slot[kQInvDz * 32] = mufu_rcp(b.dir.z);
     slot[kQLayer * 32] = __int_as_float(min(max(__float2int_rz((b.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1));
     slot[kQLife * 32] = b.life;
     const float nm = b.wlen * 1e9f;
@@ -627,7 +619,7 @@ __device__ __noinline__ float abs_left_at_end_of_flight(const float4 *layers, fl
     const bool up = !(dz < 0.f);
     for (;;) {
         const float4 c = layers[layer];
-        const float b = c.x * f_scat, a = c.y * f_dust + c.z * f_pure;
+        const float b = c.x * f_scat, a = c.z * f_dust + c.y * f_pure;
         const float zb = z0 + h * static_cast<float>(layer + (up ? 1 : 0));
         const float d_b = fmaxf((zb - z) * inv_dz, 0.f);
         const bool can_cross = up ? (layer < num_layers - 1) : (layer > 0);
@@ -642,11 +634,19 @@ __device__ __noinline__ float abs_left_at_end_of_flight(const float4 *layers, fl
 }
 
 // ---- the photon in flight ---------------------------------------------------------------------
+// Quantities that are always used together sit in register PAIRS (float2): sm_100a has packed fp32 instructions
+// (FFMA2 / FMUL2 / FADD2: two independent fp32 operations per issue slot, with scalar-broadcast, swap and per-half
+// negation of the operands for free), and this kernel is bound by instruction issue, not by the fp32 pipes.
 struct Lane {
-    V3 pos, dir;
-    float inv_dz;                     // 1/dir.z (guarded), refreshed whenever the direction changes
-    float abs_left, sca_left, path;   // sca_left == 0 marks "draw a new flight"
-    float f_scat, f_dust, f_pure;
+    float2 pxy;                       // position x, y
+    float pz;
+    float2 dxy;                       // direction x, y
+    float dz;
+    float inv_dz;                     // 1/dz (+-inf for dz == 0), refreshed whenever the direction changes
+    float2 bud;                       // (abs_left, sca_left): budgets in absorption / scattering lengths; sca_left == 0 marks "draw a new flight"
+    float path;
+    float2 f_sp;                      // (f_scat, f_pure): wavelength-only factors of the ice model
+    float f_dust;
     float z_eff;                      // TILT only: z in the untilted layer frame, carried along the flight
     float inv_aniso;                  // ANISO only: abs_left is held scaled by 1/inv_aniso during a flight
     uint32_t scatters;
@@ -655,13 +655,17 @@ struct Lane {
     uint64_t rng_x;
 };
 
+// 1/dz without a guard: dz == 0 gives +-inf, and a leg then never reaches the boundary ahead (the reference treats
+// |dz| < 1e-5 as "stays in its layer", propagation_kernel.c.cl:669; a photon that flat flies > 1e5 layer heights per layer)
+__device__ __forceinline__ float raw_inv_dz(float dz) { return mufu_rcp(dz); }
+
 template <bool TILT, bool ANISO> __device__ __forceinline__ void load_lane(Lane &L, const float *st)
 {
-    L.pos.x = st[kPx * kThreads]; L.pos.y = st[kPy * kThreads]; L.pos.z = st[kPz * kThreads];
-    L.dir.x = st[kDx * kThreads]; L.dir.y = st[kDy * kThreads]; L.dir.z = st[kDz * kThreads];
-    L.inv_dz = safe_inv_dz(L.dir.z);
-    L.abs_left = st[kAbsLeft * kThreads]; L.sca_left = st[kScaLeft * kThreads]; L.path = st[kPath * kThreads];
-    L.f_scat = st[kFScat * kThreads]; L.f_dust = st[kFDust * kThreads]; L.f_pure = st[kFPure * kThreads];
+    L.pxy = make_float2(st[kPx * kThreads], st[kPy * kThreads]); L.pz = st[kPz * kThreads];
+    L.dxy = make_float2(st[kDx * kThreads], st[kDy * kThreads]); L.dz = st[kDz * kThreads];
+    L.inv_dz = raw_inv_dz(L.dz);
+    L.bud = make_float2(st[kAbsLeft * kThreads], st[kScaLeft * kThreads]); L.path = st[kPath * kThreads];
+    L.f_sp = make_float2(st[kFScat * kThreads], st[kFPure * kThreads]); L.f_dust = st[kFDust * kThreads];
     L.scatters = __float_as_uint(st[kScatters * kThreads]);
     L.layer = __float_as_int(st[kLayer * kThreads]);
     L.status = __float_as_uint(st[kStatus * kThreads]);
@@ -672,10 +676,10 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void load_lane(Lane 
 
 template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(const Lane &L, float *st)
 {
-    st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
-    st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
-    st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = L.sca_left; st[kPath * kThreads] = L.path;
-    st[kFScat * kThreads] = L.f_scat; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_pure; // lanes change photons inside a fast phase
+    st[kPx * kThreads] = L.pxy.x; st[kPy * kThreads] = L.pxy.y; st[kPz * kThreads] = L.pz;
+    st[kDx * kThreads] = L.dxy.x; st[kDy * kThreads] = L.dxy.y; st[kDz * kThreads] = L.dz;
+    st[kAbsLeft * kThreads] = L.bud.x; st[kScaLeft * kThreads] = L.bud.y; st[kPath * kThreads] = L.path;
+    st[kFScat * kThreads] = L.f_sp.x; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_sp.y; // lanes change photons inside a fast phase
     st[kScatters * kThreads] = __uint_as_float(L.scatters);
     st[kLayer * kThreads] = __int_as_float(L.layer);
     st[kStatus * kThreads] = __uint_as_float(L.status);
@@ -723,56 +727,84 @@ __device__ __noinline__ bool dom_within_reach(const DevScene *scene, int who, fl
 // of the flight (scatter / absorption inside the current ice layer, the layer boundary, or the
 // range limit of the collision map) and what is left of the two budgets afterwards.
 struct Leg {
-    float a, b;               // 1/absorption length, 1/scattering length in the current layer
+    float2 q;                 // (b, a): 1/scattering length, 1/absorption length in the current layer
     float zb, zc;             // boundary ahead, current z (both in the layer frame)
     float travel;
-    float rem_abs, rem_sca;   // budgets left at the end of the leg
-    float ox, oy;             // from the photon to the axis of the nearest string (xy)
-    int who;                  // that string
-    bool up, absorbed, limited, cross, walk;
+    float2 rem;               // budgets (abs, sca) left at the end of the leg
+    float2 o;                 // from the photon to the axis of the nearest string (xy)
+    float d_b, cap;           // distance to the layer boundary ahead; range limit of the collision map (+inf: none)
+    uint32_t cell;            // pixel-map word: byte offset of that string's record | range bits
+    bool absorbed, limited;
 };
 
+// +1 for a photon going up (or flat), -1 for one going down, from the sign of 1/dz
+__device__ __forceinline__ int layer_step(float inv_dz) { return (__float_as_int(inv_dz) >> 31) | 1; }
+// pixel-map word -> string index / "the strings are too dense here for the map: the reference's cell walk instead"
+__device__ __forceinline__ int cell_string(uint32_t cell) { return static_cast<int>((cell & 0xffffu) >> 4); }
+__device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff0000u) == 0u; }
+
 template <bool TILT, bool SAVE_ALL>
-__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float2 *bounds,
-                                        const float4 *strings, const uint32_t *near)
+__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float4 *strings, const uint32_t *near)
 {
     const DevGeometry &geo = scene.geo;
     Leg g;
     const float4 c = layers[L.layer];
-    const float2 zz = bounds[L.layer];
-    g.b = c.x * L.f_scat;
-    g.a = fmaf(c.y, L.f_dust, c.z * L.f_pure);
-    g.up = !(L.dir.z < 0.f);
-    g.zb = g.up ? zz.y : zz.x;                               // +-1e30 when there is no layer beyond
-    g.zc = TILT ? L.z_eff : L.pos.z;
-    const float d_b = fmaxf((g.zb - g.zc) * L.inv_dz, 0.f);
-    g.absorbed = L.abs_left * g.b < L.sca_left * g.a;        // d_absorb < d_scatter inside this layer
-    const float d_sa = (g.absorbed ? L.abs_left : L.sca_left) * mufu_rcp(g.absorbed ? g.a : g.b);
+    const float z_up = layers[L.layer + 1].w;
+    g.q = __fmul2_rn(make_float2(c.x, c.y), L.f_sp);         // (b400 * f_scat, (1 + 0.01 dTau) * f_pure)
+    g.q.y = fmaf(c.z, L.f_dust, g.q.y);
+    g.zb = (L.inv_dz < 0.f) ? c.w : z_up;                    // +-1e30 when there is no layer beyond
+    g.zc = TILT ? L.z_eff : L.pz;
+    g.d_b = fmaxf((g.zb - g.zc) * L.inv_dz, 0.f);            // (0 * inf = NaN -> 0: a flat photon on a boundary steps over it)
+    const float2 cmp = __fmul2_rn(L.bud, g.q);               // (abs_left * b, sca_left * a)
+    g.absorbed = cmp.x < cmp.y;                              // d_absorb < d_scatter inside this layer
+    const float d_sa = (g.absorbed ? L.bud.x : L.bud.y) * mufu_rcp(g.absorbed ? g.q.y : g.q.x);
     // pixel map: nearest string and the range within which no other string can be touched
-    g.who = -1;
-    float cap = __int_as_float(0x7f800000);
-    g.ox = g.oy = 0.f;
-    g.walk = false;
+    g.cell = 0u;
+    g.cap = __int_as_float(0x7f800000);
+    g.o = make_float2(0.f, 0.f);
     if (!SAVE_ALL) {
         // (float -> unsigned conversion saturates below at 0)
-        const uint32_t px = min(__float2uint_rz(fmaf(L.pos.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
-        const uint32_t py = min(__float2uint_rz(fmaf(L.pos.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
-        const uint32_t cell = near[py * geo.near_nx + px];
-        g.who = static_cast<int>(cell & 0xffffu);
-        const float range = __uint_as_float(cell & 0xffff0000u);
-        g.walk = !(range > 0.f);        // strings too dense here for the map: no range limit, cell walk instead
-        if (!g.walk) cap = range;
-        const float2 sxy = *reinterpret_cast<const float2 *>(strings + g.who);
-        g.ox = sxy.x - L.pos.x;
-        g.oy = sxy.y - L.pos.y;
+        const uint32_t px = min(__float2uint_rz(fmaf(L.pxy.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
+        const uint32_t py = min(__float2uint_rz(fmaf(L.pxy.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
+        g.cell = near[py * geo.near_nx + px];
+        const float range = __uint_as_float(g.cell & 0xffff0000u);
+        if (range > 0.f) g.cap = range;    // range 0: no limit (and every leg takes the reference's cell walk, see cell_walk)
+        const float2 sxy = *reinterpret_cast<const float2 *>(reinterpret_cast<const uint8_t *>(strings) + (g.cell & 0xffffu));
+        g.o = __fadd2_rn(sxy, make_float2(-L.pxy.x, -L.pxy.y));
     }
-    const float d_geo = fminf(d_b, cap);
+    const float d_geo = fminf(g.d_b, g.cap);
     g.limited = d_geo < d_sa;                                // the flight goes on after this leg
-    g.cross = g.limited && (d_b <= cap);
-    g.travel = g.limited ? d_geo : d_sa;
-    g.rem_abs = fmaf(-g.travel, g.a, L.abs_left);
-    g.rem_sca = fmaxf(fmaf(-g.travel, g.b, L.sca_left), 1e-30f);
+    g.travel = fminf(d_geo, d_sa);
+    g.rem = __ffma2_rn(make_float2(-g.travel, -g.travel), make_float2(g.q.y, g.q.x), L.bud);
+    g.rem.y = fmaxf(g.rem.y, 1e-30f);
     return g;
+}
+
+// R8 (propagation_kernel.c.cl:83-129) on a direction held as (xy pair, z); the azimuth comes as the raw 32-bit
+// draw, so that its scaling to [0, 2 pi) is one multiplication (bit-identical to 2 pi * (draw * 2^-32): the power of
+// two is exact).  With k = sin(a)/sin(theta), u = cos(b) k, w = cos(a) - z sin(b) k:
+//     (x, y)' = (x, y) w + (-y, x) u        z' = z cos(a) + sin(a) sin(b) sin(theta)
+// sin^2(theta) is taken from x and y, not as 1 - z^2: for a direction whose length is off by eps the rotation then
+// gives a length off by at most eps again (with 1 - z^2 the error is amplified by sin^2(a)/sin^2(theta) near the
+// poles), so the length only random-walks by rounding and is restored once per fast phase, not per scatter.
+__device__ __forceinline__ void rotate_packed(float cosa, float sina, float2 &dxy, float &dz, uint32_t draw)
+{
+    float sinb, cosb;
+    __sincosf(__uint2float_rz(draw) * (2.0f * kPi * 2.3283064365386963e-10f), &sinb, &cosb);
+    const float s2 = fmaf(dxy.x, dxy.x, dxy.y * dxy.y);
+    if (s2 > 0.f) {
+        const float inv_s = mufu_rsqrt(s2);
+        const float2 ks = __fmul2_rn(make_float2(sina, s2), make_float2(inv_s, inv_s));   // (k, sin(theta))
+        const float u = cosb * ks.x;
+        const float w = fmaf(-dz * sinb, ks.x, cosa);
+        const float nz = fmaf(sina * sinb, ks.y, dz * cosa);
+        const float2 along = __fmul2_rn(dxy, make_float2(w, w));
+        dxy = __ffma2_rn(make_float2(-dxy.y, dxy.x), make_float2(u, u), along);
+        dz = nz;
+    } else {
+        dxy = make_float2(sina * cosb, sina * sinb);
+        dz = (dz > 0.f) ? cosa : ((dz < 0.f) ? -cosa : cosa * dz);
+    }
 }
 
 // One iteration of the hot loop: move the photon to its next event.  A leg that might touch a DOM
@@ -782,95 +814,110 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
 // exactly this leg through.
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
-                                               const float2 *bounds, const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
-                                               const float *tilt_corr, uint32_t rng_a, float *st, bool renormalize)
+                                               const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
+                                               const float *tilt_corr, uint32_t rng_a, float *st)
 {
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
 
     // ------------------------------------------------------------------ R5: next event of the flight
-    if (L.sca_left <= 0.f) {
+    if (L.bud.y <= 0.f) {
         // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
-            L.z_eff = L.pos.z - tilt_shift(m, tilt_dist, tilt_corr, L.pos.x, L.pos.y, L.pos.z);
+            L.z_eff = L.pz - tilt_shift(m, tilt_dist, tilt_corr, L.pxy.x, L.pxy.y, L.pz);
             L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
         }
         if (ANISO) {
             // R4b: 1/f = (B2-nB)*An/2 (I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx:92-134)
-            const float n0 = m.azx * L.dir.x + m.azy * L.dir.y, n1 = m.neg_azy * L.dir.x + m.azx * L.dir.y;
-            const float s0 = n0 * n0, s1 = n1 * n1, s2 = L.dir.z * L.dir.z;
+            const float n0 = m.azx * L.dxy.x + m.azy * L.dxy.y, n1 = m.neg_azy * L.dxy.x + m.azx * L.dxy.y;
+            const float s0 = n0 * n0, s1 = n1 * n1, s2 = L.dz * L.dz;
             const float nB = s0 * m.rl[0] + s1 * m.rl[1] + s2 * m.rl[2];
             const float An = s0 * m.l[0] + s1 * m.l[1] + s2 * m.l[2];
             L.inv_aniso = (m.B2 - nB) * An * 0.5f;
-            L.abs_left *= mufu_rcp(L.inv_aniso);
+            L.bud.x *= mufu_rcp(L.inv_aniso);
         }
-        L.sca_left = -fast_ln(rng.oc());
+        L.bud.y = -fast_ln(rng.oc());
         L.rng_x = rng.x;
     }
-    const Leg g = plan_leg<TILT, SAVE_ALL>(L, scene, layers, bounds, strings, near);
+    const Leg g = plan_leg<TILT, SAVE_ALL>(L, scene, layers, strings, near);
 
     // ------------------------------------------------------------------ R6: DOM collision, cheap part
     if (!SAVE_ALL) {
-        // 2-D segment / cylinder test against the one string in range
+        // is the one string in range within reach of this leg at all?  (a few legs in a thousand; where the map
+        // has no range every leg is)
         const float R = scene.geo.string_max_radius;
-        const float o2 = g.ox * g.ox + g.oy * g.oy;
-        const float t = g.ox * L.dir.x + g.oy * L.dir.y;
-        const float dxy2 = L.dir.x * L.dir.x + L.dir.y * L.dir.y;
+        const float o2 = fmaf(g.o.x, g.o.x, g.o.y * g.o.y);
         const float reach = g.travel + R;
-        const float out2 = o2 - R * R;                       // > 0: the photon starts outside the cylinder
-        const bool miss = (o2 > reach * reach) || ((t <= 0.f) && (out2 > 0.f)) || (out2 * dxy2 > t * t);
-        if ((!miss || g.walk) && !cleared) {
+        const float reach2 = (g.cap == __int_as_float(0x7f800000)) ? g.cap : reach * reach;
+        if (!(o2 > reach2) && !cleared) {
+            // 2-D segment / cylinder test
+            const bool walk = cell_walk(g.cell);
+            const float t = fmaf(g.o.x, L.dxy.x, g.o.y * L.dxy.y);
+            const float dxy2 = fmaf(L.dxy.x, L.dxy.x, L.dxy.y * L.dxy.y);
+            const float out2 = o2 - R * R;                       // > 0: the photon starts outside the cylinder
+            const bool miss = (o2 > reach * reach) || ((t <= 0.f) && (out2 > 0.f)) || (out2 * dxy2 > t * t);
+            if (!miss || walk) {
 #ifdef CLSIMCU_DEBUG_COUNTERS
-            {
-                const LaunchArgs &dbg = reinterpret_cast<const SmemHeader *>(smem_base())->args;
-                atomicAdd(dbg.stats + 2, 1ull);                                  // legs parked
-                if (g.walk) atomicAdd(dbg.stats + 3, 1ull);                      // ... in a dense-string pixel
-                if (out2 <= 0.f) atomicAdd(dbg.stats + 4, 1ull);                 // ... starting inside the cylinder
-                if (L.scatters == 0u) atomicAdd(dbg.stats + 5, 1ull);            // ... before the first scatter
-                if (g.travel > 20.f) atomicAdd(dbg.stats + 6, 1ull);             // ... long legs
-            }
+                {
+                    const LaunchArgs &dbg = reinterpret_cast<const SmemHeader *>(smem_base())->args;
+                    atomicAdd(dbg.stats + 2, 1ull);                                  // legs parked
+                    if (walk) atomicAdd(dbg.stats + 3, 1ull);                        // ... in a dense-string pixel
+                    if (out2 <= 0.f) atomicAdd(dbg.stats + 4, 1ull);                 // ... starting inside the cylinder
+                    if (L.scatters == 0u) atomicAdd(dbg.stats + 5, 1ull);            // ... before the first scatter
+                    if (g.travel > 20.f) atomicAdd(dbg.stats + 6, 1ull);             // ... long legs
+                }
 #endif
 #ifndef CLSIMCU_NO_Z_PRETEST
-            if (g.walk || dom_within_reach(scene_dev, g.who, L.pos.z, L.dir.z, g.travel, t, dxy2, out2))
+                if (walk || dom_within_reach(scene_dev, cell_string(g.cell), L.pz, L.dz, g.travel, t, dxy2, out2))
 #endif
-            {
-                L.status = kFrozen;
-                st[kPendTravel * kThreads] = g.travel;
-                st[kPendWho * kThreads] = __int_as_float(g.walk ? -1 : g.who);
-                return;
+                {
+                    L.status = kFrozen;
+                    st[kPendTravel * kThreads] = g.travel;
+                    st[kPendWho * kThreads] = __int_as_float(walk ? -1 : cell_string(g.cell));
+                    return;
+                }
             }
         }
         cleared = false;
     }
 
     // ------------------------------------------------------------------ advance
-    L.pos.x = fmaf(L.dir.x, g.travel, L.pos.x);
-    L.pos.y = fmaf(L.dir.y, g.travel, L.pos.y);
-    L.pos.z = fmaf(L.dir.z, g.travel, L.pos.z);
+    L.pxy = __ffma2_rn(L.dxy, make_float2(g.travel, g.travel), L.pxy);
+    L.pz = fmaf(L.dz, g.travel, L.pz);
     L.path += g.travel;
 
     if (g.limited) {
         // the flight goes on (in the neighbouring layer, or past the range limit of the collision
         // map) with what is left of both budgets
-        if (g.cross) L.layer += g.up ? 1 : -1;
-        L.abs_left = g.rem_abs;
-        L.sca_left = g.rem_sca;
-        if (TILT) L.z_eff = g.cross ? g.zb : fmaf(L.dir.z, g.travel, L.z_eff);
+        const bool cross = g.d_b <= g.cap;
+        if (cross) L.layer += layer_step(L.inv_dz);
+        L.bud = g.rem;
+        if (TILT) L.z_eff = cross ? g.zb : fmaf(L.dz, g.travel, L.z_eff);
         return;
     }
-    L.abs_left = g.absorbed ? 0.f : g.rem_abs;
-    if (ANISO) L.abs_left *= L.inv_aniso;
-    if (L.abs_left < kEpsilon) {
+    L.bud.x = g.absorbed ? 0.f : g.rem.x;
+    if (ANISO) L.bud.x *= L.inv_aniso;
+    if (L.bud.x < kEpsilon) {
         L.status = SAVE_ALL ? kDying : kDead;
         return;
     }
     // ------------------------------------------------------------------ R9 + R8: scatter
-    if (ANISO) apply_matrix(m.pre, L.dir);
+    if (ANISO) {
+        V3 d{L.dxy.x, L.dxy.y, L.dz};
+        apply_matrix(m.pre, d);
+        L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+    }
     const float rr = rng.co();
     float cs;
     const int scat_kind = MIXED ? CLSIMCU_SCAT_MIXED_SL_HG : m.scat_kind;   // the IceCube models' mix is compiled in
-    if (scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
-        // both samplers are evaluated and one is selected: no divergent branch
+    if (MIXED) {
+        // both samplers are evaluated and one is selected (no divergent branch); the constants of
+        // I3CLSimRandomValueMixed / ...SimplifiedLiu / ...HenyeyGreenstein are folded on the host (DevMedium)
+        const float cos_sl = mufu_ex2(fmaf(m.sl_beta, mufu_lg2(rr), m.sl_off)) - 1.f;
+        const float r = mufu_rcp(fmaf(m.hg_h1, rr, m.hg_h0));
+        const float cos_hg = fmaf(-m.hg_w, r * r, m.hg_c);
+        cs = (rr < m.f_sl) ? cos_sl : cos_hg;
+    } else if (scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
         const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
         const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
         const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
@@ -883,12 +930,16 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
     } else {
         cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
     }
-    cs = fminf(fmaxf(cs, -1.f), 1.f);
-    const float sn = mufu_sqrt(1.f - cs * cs);
-    rotate_by(cs, sn, L.dir, rng.co(), ANISO ? false : renormalize);   // apply_matrix renormalises
-    if (ANISO) apply_matrix(m.post, L.dir);
-    L.inv_dz = safe_inv_dz(L.dir.z);
-    L.sca_left = 0.f;
+    // (the samplers stay within [-1, 1] up to the rounding of the approximate exp2 / reciprocal; only the root needs a guard)
+    const float sn = mufu_sqrt(fmaxf(fmaf(-cs, cs, 1.f), 0.f));
+    rotate_packed(cs, sn, L.dxy, L.dz, rng.next());
+    if (ANISO) {
+        V3 d{L.dxy.x, L.dxy.y, L.dz};
+        apply_matrix(m.post, d);
+        L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+    }
+    L.inv_dz = raw_inv_dz(L.dz);
+    L.bud.y = 0.f;
     ++L.scatters;
     L.rng_x = rng.x;
 }
@@ -909,12 +960,13 @@ __device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st
     const SmemPlan sp = table_plan(lay);
     Lane L;
     load_lane<TILT, ANISO>(L, st);
-    const Leg g = plan_leg<TILT, false>(L, *scene, sp.layers, sp.bounds, sp.strings, sp.near);
-    float at_end = g.absorbed ? 0.f : g.rem_abs;
+    const Leg g = plan_leg<TILT, false>(L, *scene, sp.layers, sp.strings, sp.near);
+    float at_end = g.absorbed ? 0.f : g.rem.x;
+    const bool cross = g.limited && (g.d_b <= g.cap);
     if (g.limited)
         at_end = abs_left_at_end_of_flight(sp.layers, scene->medium.z0, scene->medium.h, scene->medium.num_layers,
-                                           g.cross ? L.layer + (g.up ? 1 : -1) : L.layer, g.cross ? g.zb : fmaf(L.dir.z, g.travel, g.zc),
-                                           L.dir.z, L.inv_dz, g.rem_sca, g.rem_abs, L.f_scat, L.f_dust, L.f_pure);
+                                           cross ? L.layer + layer_step(L.inv_dz) : L.layer, cross ? g.zb : fmaf(L.dz, g.travel, g.zc),
+                                           L.dz, L.inv_dz, g.rem.y, g.rem.x, L.f_sp.x, L.f_dust, L.f_sp.y);
     if (ANISO) at_end *= L.inv_aniso;
     const V3 end{fmaf(dir.x, col.travel, pos.x), fmaf(dir.y, col.travel, pos.y), fmaf(dir.z, col.travel, pos.z)};
     emit_record(scene, st, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, at_end, false, rng_a);
@@ -990,13 +1042,12 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
 template <bool SAVE_ALL>
 __device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *st)
 {
-    L.pos.x = slot[kQx * 32]; L.pos.y = slot[kQy * 32]; L.pos.z = slot[kQz * 32];
-    L.dir.x = slot[kQDx * 32]; L.dir.y = slot[kQDy * 32]; L.dir.z = slot[kQDz * 32];
+    L.pxy = make_float2(slot[kQx * 32], slot[kQy * 32]); L.pz = slot[kQz * 32];
+    L.dxy = make_float2(slot[kQDx * 32], slot[kQDy * 32]); L.dz = slot[kQDz * 32];
     L.inv_dz = slot[kQInvDz * 32];
-    L.abs_left = slot[kQLife * 32];
-    L.sca_left = 0.f;
+    L.bud = make_float2(slot[kQLife * 32], 0.f);
     L.path = 0.f;
-    L.f_scat = slot[kQFScat * 32]; L.f_dust = slot[kQFDust * 32]; L.f_pure = slot[kQFPure * 32];
+    L.f_sp = make_float2(slot[kQFScat * 32], slot[kQFPure * 32]); L.f_dust = slot[kQFDust * 32];
     L.scatters = 0u;
     L.layer = __float_as_int(slot[kQLayer * 32]);
     L.status = kActive;
@@ -1066,10 +1117,10 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
             Lane L;
             L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
             take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
-            st[kPx * kThreads] = L.pos.x; st[kPy * kThreads] = L.pos.y; st[kPz * kThreads] = L.pos.z;
-            st[kDx * kThreads] = L.dir.x; st[kDy * kThreads] = L.dir.y; st[kDz * kThreads] = L.dir.z;
-            st[kAbsLeft * kThreads] = L.abs_left; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
-            st[kFScat * kThreads] = L.f_scat; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_pure;
+            st[kPx * kThreads] = L.pxy.x; st[kPy * kThreads] = L.pxy.y; st[kPz * kThreads] = L.pz;
+            st[kDx * kThreads] = L.dxy.x; st[kDy * kThreads] = L.dxy.y; st[kDz * kThreads] = L.dz;
+            st[kAbsLeft * kThreads] = L.bud.x; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
+            st[kFScat * kThreads] = L.f_sp.x; st[kFDust * kThreads] = L.f_dust; st[kFPure * kThreads] = L.f_sp.y;
             st[kScatters * kThreads] = __uint_as_float(0u);
             st[kLayer * kThreads] = __int_as_float(L.layer);
             status = kActive;
@@ -1106,11 +1157,10 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     const SmemPlan sp = table_plan(lay);
 
     // ---- stage the hot tables into shared memory (coalesced reads, once per CTA)
-    for (int i = tid; i < m.num_layers; i += kThreads)
-    {
-        sp.layers[i] = make_float4(__ldg(m.b400 + i), __ldg(m.abs_dust + i), __ldg(m.abs_tau + i), 0.f);
-        sp.bounds[i] = make_float2((i == 0) ? -1e30f : m.z0 + m.h * static_cast<float>(i),
-                                   (i == m.num_layers - 1) ? 1e30f : m.z0 + m.h * static_cast<float>(i + 1));
+    for (int i = tid; i <= m.num_layers; i += kThreads) {
+        const float z_low = (i == 0) ? -1e30f : ((i == m.num_layers) ? 1e30f : m.z0 + m.h * static_cast<float>(i));
+        sp.layers[i] = (i < m.num_layers) ? make_float4(__ldg(m.b400 + i), __ldg(m.abs_tau + i), __ldg(m.abs_dust + i), z_low)
+                                          : make_float4(0.f, 0.f, 0.f, z_low);
     }
     if (TILT) {
         for (int i = tid; i < m.tilt_nd; i += kThreads) {
@@ -1171,15 +1221,14 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         load_lane<TILT, ANISO>(L, st);
         if (!ANISO) {
             // the unit length of the direction, restored once per fast phase (see rotate_by)
-            const float inv = fmaf(L.dir.x * L.dir.x + L.dir.y * L.dir.y + L.dir.z * L.dir.z, -0.5f, 1.5f);
-            L.dir.x *= inv; L.dir.y *= inv; L.dir.z *= inv;
-            L.inv_dz = safe_inv_dz(L.dir.z);
+            const float inv = fmaf(L.dxy.x * L.dxy.x + L.dxy.y * L.dxy.y + L.dz * L.dz, -0.5f, 1.5f);
+            L.dxy.x *= inv; L.dxy.y *= inv; L.dz *= inv;
+            L.inv_dz = raw_inv_dz(L.dz);
         }
         bool cleared = (L.status == kCleared);
         if (cleared) L.status = kActive;
         uint32_t queued = wctl[kWQueued];
         const bool more = (wctl[kWMore] != 0u) || (wctl[kWLeft] > 0u);
-        uint32_t iteration = 0u;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.status != kActive);
             if (idle != 0u) {
@@ -1204,11 +1253,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                     if (n_waiting + static_cast<int>(n_dead) >= limit) break;
                 }
             }
-            if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.bounds, sp.strings, sp.near, sp.tilt_dist,
-                                                             sp.tilt_corr, rng_a, st,
-                                                             kRenormEvery != 0u && (iteration & (kRenormEvery - 1u)) == 0u);
-            if (kRenormEvery != 0u) ++iteration;
+#pragma unroll
+            for (int leg = 0; leg < kHotUnroll; ++leg)
+                if (L.status == kActive)
+                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
+                                                                 sp.tilt_corr, rng_a, st);
         }
         if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
@@ -1249,7 +1298,7 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
 {
     // the save-all variants are checkers' tools: no need to specialise them further
     if constexpr (!SAVE_ALL) {
-        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) return launch_mix<TILT, ANISO, SAVE_ALL, true>(scene, args, blocks, stream);
+        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, SAVE_ALL, true>(scene, args, blocks, stream);
     }
     return launch_mix<TILT, ANISO, SAVE_ALL, false>(scene, args, blocks, stream);
 }
@@ -1262,9 +1311,11 @@ bool fast_kernel_supports(const DevScene &scene, const char **why)
     static const char *k_nonstop = "StopDetectedPhotons=false is only implemented by the reference-order kernel";
     static const char *k_renorm = "non-renormalising direction transforms are only implemented by the reference-order kernel";
     static const char *k_smem = "geometry/medium tables do not fit into shared memory";
+    static const char *k_strings = "more than 4095 strings";
     if (scene.history_entries > 0) { *why = k_history; return false; }
     if (!scene.save_all && !scene.stop_detected) { *why = k_nonstop; return false; }
     if (scene.medium.anisotropy && (!scene.medium.pre_renorm || !scene.medium.post_renorm)) { *why = k_renorm; return false; }
+    if (scene.geo.num_strings > 4095) { *why = k_strings; return false; }
     if (plan_smem(scene).total + 1024u > kSmemBudget / kBlocksPerSM) { *why = k_smem; return false; }
     return true;
 }
