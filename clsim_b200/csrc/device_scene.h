@@ -69,12 +69,12 @@ struct DevGeometry {
     const uint32_t *string_tmpl_start;
     const float *string_mean_x, *string_mean_y;
     // Fast kernel only: pixel map over the xy plane.  near_info[pixel] = 16 x the index of the string
-    // nearest to the pixel centre (low 16 bits: at most 4095 strings) | the RANGE of the pixel, stored as the upper 16
+    // nearest to the pixel centre (low 16 bits: at most 4094 strings) | the RANGE of the pixel, stored as the upper 16
     // bits of an fp32 (rounded down): a photon anywhere in the pixel can fly that far before any
     // OTHER string can come within string_max_radius of it.  The fast kernel cuts flights at that
     // range, so a segment only ever has to be tested against the one named string (exactly, from
-    // the photon's own position).  Range 0 marks pixels where the strings are too dense for the
-    // pixel size: there every segment takes the reference's cell walk.  Points outside the map
+    // the photon's own position).  Range +inf with string index num_strings marks pixels where the strings
+    // are too dense for the pixel size: there every segment takes the reference's cell walk.  Points outside the map
     // clamp to the border pixels (the bound stays valid: projection onto the map rectangle is
     // non-expansive and every string lies inside it).
     int near_nx, near_ny;

@@ -414,12 +414,18 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
                     // how far a photon anywhere in this pixel may fly before a string other than
                     // `who` can come within the collision radius
                     double range = std::min(second, 1e9) - half_diag - g.string_max_radius - 1e-2;
-                    if (range < min_range) range = 0.0;
                     const float rf = static_cast<float>(range);
                     uint32_t bits;
                     std::memcpy(&bits, &rf, 4);
                     bits &= 0xffff0000u; // truncation of a positive float rounds down: the bound stays a lower bound
-                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = (static_cast<uint32_t>(who) << 4) | bits; // byte offset of the string's 16-byte record
+                    uint32_t low = static_cast<uint32_t>(who) << 4; // byte offset of the string's 16-byte record
+                    if (range < min_range) {
+                        // strings too dense for the pixel size: no range (+inf) and no string (the record behind the
+                        // last one, which the kernel fills with NaN): every leg takes the reference's cell walk
+                        bits = 0x7f800000u;
+                        low = static_cast<uint32_t>(g.num_strings) << 4;
+                    }
+                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = low | bits;
                 }
             }
             o_near_info = arena.add(info);

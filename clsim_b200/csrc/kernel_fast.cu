@@ -69,10 +69,10 @@ namespace {
 #define CLSIMCU_IDLE_LIMIT_SAVE_ALL 8
 #endif
 #ifndef CLSIMCU_HOT_UNROLL
-#define CLSIMCU_HOT_UNROLL 2
+#define CLSIMCU_HOT_UNROLL 3
 #endif
 #ifndef CLSIMCU_REFILL_BATCH
-#define CLSIMCU_REFILL_BATCH 4
+#define CLSIMCU_REFILL_BATCH 3
 #endif
 constexpr int kThreads = CLSIMCU_THREADS;
 // legs a lane flies between two looks at the warp's state (ballots, refill decisions) in the hot loop
@@ -88,12 +88,14 @@ constexpr float kEpsilon = 0.00001f;
 constexpr float kLn2 = 0.69314718056f;
 constexpr uint32_t kSmemBudget = 227u * 1024u;
 
-// queue slot (one photon waiting for a lane): where it starts, what is left of its life, the three
-// wavelength-only ice factors, and its BIRTH TAG: the state of the creation stream it was made from and
-// the step it belongs to.  The start-of-flight record a hit needs (start point, direction, time,
+// queue slot (one photon waiting for a lane), four 16-byte chunks so that a lane takes a photon with four loads:
+//   0: (x, y, dx, dy)   1: (z, dz, lifetime in absorption lengths, ice layer)   2: (f_scat, f_pure, f_dust, -)
+//   3: BIRTH TAG (creation-stream state lo, hi, step index | creating lane << 27, -)
+// f_*: the three wavelength-only ice factors.  The start-of-flight record a hit needs (start point, direction, time,
 // wavelength, lifetime) is not carried along: one photon in a thousand is detected, and for those the
 // record is re-created from the tag (creation is deterministic).
-enum QueueWord { kQx = 0, kQy, kQz, kQDx, kQDy, kQDz, kQInvDz, kQLayer, kQLife, kQFScat, kQFDust, kQFPure, kQTagLo, kQTagHi, kQTagStep, kQueueWords };
+constexpr int kQueueChunks = 4;
+constexpr int kQueueWords = 4 * kQueueChunks;
 constexpr uint32_t kStepIndexBits = kFastKernelStepIndexBits; // tag word kQTagStep = step index | (creating lane << 27)
 // per-lane running state, parked in shared memory between fast phases
 enum StateWord {
@@ -102,21 +104,19 @@ enum StateWord {
 };
 // per-lane birth tag of the photon in flight (3 words) and, in the save-all variants, the state of the
 // propagation stream when it started (2 words): what a checker needs to replay the photon
-constexpr int kBirthTagWords = 3;
+constexpr int kTagRecordWords = 4;   // per thread, 16 bytes: birth tag (3 words) | flights of the photons the lane finished in slow phases
 constexpr int kPopTagWords = 2;
 // per-warp control block
 enum WarpCtl { kWLeft = 0, kWStepIndex, kWMore, kWQueued, kWCreated, kWarpCtlWords = 8 };
 constexpr int kWarpStepWords = 16; // the warp's step record (12 words) + its direction (3)
 // compile-time offsets (in words) inside the per-thread and per-warp regions of shared memory
 constexpr int kOffBirthTag = kStateWords * kThreads;
-constexpr int kOffNSeg = kOffBirthTag + kBirthTagWords * kThreads;
-constexpr int kOffPopTag = kOffNSeg + kThreads;
-constexpr int kPerThreadWords = kStateWords + kBirthTagWords + 1;
+constexpr int kOffPopTag = kOffBirthTag + kTagRecordWords * kThreads;
+constexpr int kPerThreadWords = kStateWords + kTagRecordWords;
 constexpr int kOffWarpStep = kWarpsPerBlock * kQueueWords * 32;
 constexpr int kOffWarpCtl = kOffWarpStep + kWarpsPerBlock * kWarpStepWords;
 
-// kCleared = active, and the collision test of the segment it is about to fly has already come back negative
-enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3, kCleared = 4 };
+enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3 };
 
 // ---- approximate MUFU wrappers ---------------------------------------------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -188,7 +188,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     SmemLayout L{};
     uint32_t at = align16(sizeof(SmemHeader));
     L.off_layers = at; at = align16(at + (s.medium.num_layers + 1) * 16);
-    L.off_strings = at; at = align16(at + s.geo.num_strings * 16);
+    L.off_strings = at; at = align16(at + (s.geo.num_strings + 1) * 16);
     L.off_sets = at; at = align16(at + s.geo.num_sets * 16);
     L.off_string_set = at; at = align16(at + s.geo.num_strings);
     L.off_layer_to_dom = at; at = align16(at + s.geo.layer_table_size * 2);
@@ -213,6 +213,9 @@ __device__ __forceinline__ uint8_t *smem_base()
     extern __shared__ __align__(16) uint8_t smem[];
     return smem;
 }
+
+// the calling thread's tag record; `st` is its column of the per-thread state arrays
+__device__ __forceinline__ uint32_t *tag_record(float *st) { return reinterpret_cast<uint32_t *>(st + kOffBirthTag + (kTagRecordWords - 1) * threadIdx.x); }
 
 __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
 {
@@ -508,7 +511,7 @@ __device__ __forceinline__ Born create_core(const DevScene *scene, const StepVie
 // Queue fill: one photon of the warp's current step into queue slot `slot` (word stride 32), together
 // with the wavelength-only factors of the ice model (R4, …_Optimizers.cxx:123-250).  The scene is read
 // from its copy in global memory (uniform addresses).  Returns the advanced creation-stream state.
-__device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float *slot, uint64_t rng_x, uint32_t rng_a,
+__device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float4 *slot, uint64_t rng_x, uint32_t rng_a,
                                                uint32_t tag_step)
 {
     const DevMedium &m = scene->medium;
@@ -519,19 +522,16 @@ __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint
     s.source = wstep[11] & 0xffu;
     s.axis = V3{__uint_as_float(wstep[12]), __uint_as_float(wstep[13]), __uint_as_float(wstep[14])};
     const Born b = create_core(scene, s, rng);
-    slot[kQx * 32] = b.pos.x; slot[kQy * 32] = b.pos.y; slot[kQz * 32] = b.pos.z;
-    slot[kQDx * 32] = b.dir.x; slot[kQDy * 32] = b.dir.y; slot[kQDz * 32] = b.dir.z;
     // derived here, where all 32 lanes work, rather than when a lane takes the photon
-    slot[kQInvDz * 32] = mufu_rcp(b.dir.z);
-    slot[kQLayer * 32] = __int_as_float(min(max(__float2int_rz((b.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1));
-    slot[kQLife * 32] = b.life;
+    const int layer = min(max(__float2int_rz((b.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1);
     const float nm = b.wlen * 1e9f;
-    slot[kQFScat * 32] = fast_pow(b.wlen * m.inv_ref_wlen, -m.alpha);              // 1/scatLen = b400 * this
-    slot[kQFDust * 32] = fast_pow(nm, -m.kappa);                                  // dust term factor
-    slot[kQFPure * 32] = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
-    slot[kQTagLo * 32] = __uint_as_float(static_cast<uint32_t>(rng_x));
-    slot[kQTagHi * 32] = __uint_as_float(static_cast<uint32_t>(rng_x >> 32));
-    slot[kQTagStep * 32] = __uint_as_float(tag_step);
+    const float f_scat = fast_pow(b.wlen * m.inv_ref_wlen, -m.alpha);              // 1/scatLen = b400 * this
+    const float f_dust = fast_pow(nm, -m.kappa);                                  // dust term factor
+    const float f_pure = m.A * mufu_ex2(-m.B * mufu_rcp(nm) * 1.44269504089f);    // pure-ice term
+    slot[0] = make_float4(b.pos.x, b.pos.y, b.dir.x, b.dir.y);
+    slot[1] = make_float4(b.pos.z, b.dir.z, b.life, __int_as_float(layer));
+    slot[2] = make_float4(f_scat, f_pure, f_dust, 0.f);
+    slot[3] = make_float4(__uint_as_float(static_cast<uint32_t>(rng_x)), __uint_as_float(static_cast<uint32_t>(rng_x >> 32)), __uint_as_float(tag_step), 0.f);
     return rng.x;
 }
 
@@ -555,11 +555,11 @@ __device__ __noinline__ void emit_record(const DevScene *scene_dev, float *st, V
     if (slot >= args.max_hits) return; // counted but dropped (quirk 10)
 
     // birth tag -> start-of-flight record
-    const uint32_t *btag = reinterpret_cast<const uint32_t *>(st + kOffBirthTag);
-    const uint32_t tag_step = btag[2 * kThreads];
+    const uint32_t *btag = tag_record(st);
+    const uint32_t tag_step = btag[2];
     const uint32_t step_index = tag_step & ((1u << kStepIndexBits) - 1u);
     const uint32_t made_by = (blockIdx.x * kThreads + (threadIdx.x & ~31u)) + (tag_step >> kStepIndexBits);
-    const uint64_t birth_x = static_cast<uint64_t>(btag[0 * kThreads]) | (static_cast<uint64_t>(btag[1 * kThreads]) << 32);
+    const uint64_t birth_x = static_cast<uint64_t>(btag[0]) | (static_cast<uint64_t>(btag[1]) << 32);
     const uint32_t birth_a = __ldg(args.rng_a + args.rng_creation_offset + made_by);
     const clsimcu_step *step = static_cast<const clsimcu_step *>(args.steps) + step_index;
     StepView sv;
@@ -741,7 +741,7 @@ struct Leg {
 __device__ __forceinline__ int layer_step(float inv_dz) { return (__float_as_int(inv_dz) >> 31) | 1; }
 // pixel-map word -> string index / "the strings are too dense here for the map: the reference's cell walk instead"
 __device__ __forceinline__ int cell_string(uint32_t cell) { return static_cast<int>((cell & 0xffffu) >> 4); }
-__device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff0000u) == 0u; }
+__device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff0000u) == 0x7f800000u; }
 
 template <bool TILT, bool SAVE_ALL>
 __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float4 *strings, const uint32_t *near)
@@ -767,8 +767,7 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
         const uint32_t px = min(__float2uint_rz(fmaf(L.pxy.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
         const uint32_t py = min(__float2uint_rz(fmaf(L.pxy.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
         g.cell = near[py * geo.near_nx + px];
-        const float range = __uint_as_float(g.cell & 0xffff0000u);
-        if (range > 0.f) g.cap = range;    // range 0: no limit (and every leg takes the reference's cell walk, see cell_walk)
+        g.cap = __uint_as_float(g.cell & 0xffff0000u);       // +inf: no limit (and every leg takes the reference's cell walk, see cell_walk)
         const float2 sxy = *reinterpret_cast<const float2 *>(reinterpret_cast<const uint8_t *>(strings) + (g.cell & 0xffffu));
         g.o = __fadd2_rn(sxy, make_float2(-L.pxy.x, -L.pxy.y));
     }
@@ -810,18 +809,20 @@ __device__ __forceinline__ void rotate_packed(float cosa, float sina, float2 &dx
 // One iteration of the hot loop: move the photon to its next event.  A leg that might touch a DOM
 // parks the lane (status kFrozen, the leg's length and string in the state words kPend*) with
 // nothing but the scattering-length draw applied; the slow phase runs the full collision test
-// and either ends the photon there or sends the lane back with status kCleared, which lets
-// exactly this leg through.
+// and either ends the photon there or flies this leg itself (finish_leg) and sends the lane back.
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
-__device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
+__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a);
+
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+__device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
                                                const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
                                                const float *tilt_corr, uint32_t rng_a, float *st)
 {
     const DevMedium &m = scene.medium;
-    Mwc rng{L.rng_x, rng_a};
 
     // ------------------------------------------------------------------ R5: next event of the flight
     if (L.bud.y <= 0.f) {
+        Mwc rng{L.rng_x, rng_a};
         // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
             L.z_eff = L.pz - tilt_shift(m, tilt_dist, tilt_corr, L.pxy.x, L.pxy.y, L.pz);
@@ -848,8 +849,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
         const float R = scene.geo.string_max_radius;
         const float o2 = fmaf(g.o.x, g.o.x, g.o.y * g.o.y);
         const float reach = g.travel + R;
-        const float reach2 = (g.cap == __int_as_float(0x7f800000)) ? g.cap : reach * reach;
-        if (!(o2 > reach2) && !cleared) {
+        if (!(o2 > reach * reach)) {                             // (o2 is NaN where the map has no range)
             // 2-D segment / cylinder test
             const bool walk = cell_walk(g.cell);
             const float t = fmaf(g.o.x, L.dxy.x, g.o.y * L.dxy.y);
@@ -878,9 +878,16 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
                 }
             }
         }
-        cleared = false;
     }
+    finish_leg<TILT, ANISO, SAVE_ALL, MIXED>(L, g, scene, rng_a);
+}
 
+// The rest of the iteration, once the leg is known to be free of DOMs: fly it, then scatter (or go on / end).
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a)
+{
+    const DevMedium &m = scene.medium;
+    Mwc rng{L.rng_x, rng_a};
     // ------------------------------------------------------------------ advance
     L.pxy = __ffma2_rn(L.dxy, make_float2(g.travel, g.travel), L.pxy);
     L.pz = fmaf(L.dz, g.travel, L.pz);
@@ -945,22 +952,27 @@ __device__ __forceinline__ void advance_photon(Lane &L, bool &cleared, const Dev
 }
 
 // Slow phase, for a parked lane: the reference's collision test over the pending leg.  No hit:
-// the lane goes back to the hot loop (kCleared).  Hit: the photon ends at the DOM and is
-// written out.
-template <bool TILT, bool ANISO>
+// the leg is flown here (the same code as in the hot loop) and the lane goes back.  Hit: the photon
+// ends at the DOM and is written out.
+template <bool TILT, bool ANISO, bool MIXED>
 __device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, uint32_t rng_a)
 {
     const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
     const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
     const V3 dir{st[kDx * kThreads], st[kDy * kThreads], st[kDz * kThreads]};
     const Collision col = collide(scene, __float_as_int(st[kPendWho * kThreads]), pos, dir, st[kPendTravel * kThreads]);
-    if (!col.hit) return kCleared;
-    // the leg again, for the budgets: distInAbsLens is taken for the unshortened flight
-    // (propagation_kernel.c.cl:718)
+    // the leg again (the plan is a function of the parked state alone)
     const SmemPlan sp = table_plan(lay);
     Lane L;
     load_lane<TILT, ANISO>(L, st);
     const Leg g = plan_leg<TILT, false>(L, *scene, sp.layers, sp.strings, sp.near);
+    if (!col.hit) {
+        L.status = kActive;
+        finish_leg<TILT, ANISO, false, MIXED>(L, g, *scene, rng_a);
+        store_lane<TILT, ANISO>(L, st);
+        return L.status;
+    }
+    // the budgets: distInAbsLens is taken for the unshortened flight (propagation_kernel.c.cl:718)
     float at_end = g.absorbed ? 0.f : g.rem.x;
     const bool cross = g.limited && (g.d_b <= g.cap);
     if (g.limited)
@@ -983,7 +995,7 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lane_bit = 1u << lane;
-    float *queue = warp_region + warp * (kQueueWords * 32);
+    float4 *queue = reinterpret_cast<float4 *>(warp_region) + warp * (kQueueChunks * 32);
     uint32_t *wstep = reinterpret_cast<uint32_t *>(warp_region + kOffWarpStep) + warp * kWarpStepWords;
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
@@ -1020,7 +1032,7 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
         const int rank = __popc(need_mask & (lane_bit - 1u));
         const bool take = need && (static_cast<uint32_t>(rank) < w_left);
         if (take) {
-            crng.x = create_photon(scene, wstep, queue + lane, crng.x, crng.a, w_step_index | (static_cast<uint32_t>(lane) << kStepIndexBits));
+            crng.x = create_photon(scene, wstep, queue + kQueueChunks * lane, crng.x, crng.a, w_step_index | (static_cast<uint32_t>(lane) << kStepIndexBits));
             need = false;
         }
         const uint32_t took = __popc(__ballot_sync(0xffffffffu, take));
@@ -1040,19 +1052,21 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
 // A lane takes the photon in queue slot `slot` (word stride 32): running state into `L`, birth tag (and,
 // save-all, the propagation-stream state) into the lane's tag words.
 template <bool SAVE_ALL>
-__device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *st)
+__device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *st)
 {
-    L.pxy = make_float2(slot[kQx * 32], slot[kQy * 32]); L.pz = slot[kQz * 32];
-    L.dxy = make_float2(slot[kQDx * 32], slot[kQDy * 32]); L.dz = slot[kQDz * 32];
-    L.inv_dz = slot[kQInvDz * 32];
-    L.bud = make_float2(slot[kQLife * 32], 0.f);
+    const float4 c0 = slot[0], c1 = slot[1], c2 = slot[2], c3 = slot[3];
+    L.pxy = make_float2(c0.x, c0.y); L.pz = c1.x;
+    L.dxy = make_float2(c0.z, c0.w); L.dz = c1.y;
+    L.inv_dz = raw_inv_dz(c1.y);
+    L.bud = make_float2(c1.z, 0.f);
     L.path = 0.f;
-    L.f_sp = make_float2(slot[kQFScat * 32], slot[kQFPure * 32]); L.f_dust = slot[kQFDust * 32];
+    L.f_sp = make_float2(c2.x, c2.y); L.f_dust = c2.z;
     L.scatters = 0u;
-    L.layer = __float_as_int(slot[kQLayer * 32]);
+    L.layer = __float_as_int(c1.w);
     L.status = kActive;
-    float *btag = st + kOffBirthTag;
-    btag[0 * kThreads] = slot[kQTagLo * 32]; btag[1 * kThreads] = slot[kQTagHi * 32]; btag[2 * kThreads] = slot[kQTagStep * 32];
+    uint32_t *btag = tag_record(st);
+    *reinterpret_cast<float2 *>(btag) = make_float2(c3.x, c3.y);
+    btag[2] = __float_as_uint(c3.z);
     if (SAVE_ALL) {
         float *ptag = st + kOffPopTag;
         ptag[0 * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x));
@@ -1065,7 +1079,7 @@ __device__ __forceinline__ void take_photon(Lane &L, const float *slot, float *s
 // collision test (hits are written out), save-all photons that ended are recorded, the queue is
 // refilled, lanes without a photon take one.  Returns the number of idle lanes that ends the next fast
 // phase, or -1 when the warp is done.
-template <bool TILT, bool ANISO, bool SAVE_ALL>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *warp_region)
 {
     const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
@@ -1073,15 +1087,15 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lane_bit = 1u << lane;
-    uint32_t *nseg = reinterpret_cast<uint32_t *>(st + kOffNSeg);
-    const float *queue = warp_region + warp * (kQueueWords * 32);
+    uint32_t *nseg = tag_record(st) + 3;
+    const float4 *queue = reinterpret_cast<const float4 *>(warp_region) + warp * (kQueueChunks * 32);
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = __ldg(args.rng_a + gthread);
     uint32_t status = __float_as_uint(st[kStatus * kThreads]);
 
     // ---- photons whose next leg may touch a DOM: the full collision test
-    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO>(scene, st, rng_a);
+    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO, MIXED>(scene, st, rng_a);
     // ---- save-all: every photon that ended is recorded with probability `prescale`
     //      (propagation_kernel.c.cl:800-826)
     if (SAVE_ALL && status == kDying) {
@@ -1116,7 +1130,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
             *nseg += __float_as_uint(st[kScatters * kThreads]) + 1u;
             Lane L;
             L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
-            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
+            take_photon<SAVE_ALL>(L, queue + kQueueChunks * (queued - 1u - rank), st);
             st[kPx * kThreads] = L.pxy.x; st[kPy * kThreads] = L.pxy.y; st[kPz * kThreads] = L.pz;
             st[kDx * kThreads] = L.dxy.x; st[kDy * kThreads] = L.dxy.y; st[kDz * kThreads] = L.dz;
             st[kAbsLeft * kThreads] = L.bud.x; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
@@ -1179,6 +1193,8 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                                         __ldg(geo.string_min_z + i) - geo.om_radius);
             sp.string_set[i] = __ldg(geo.string_set + i);
         }
+        // the record the pixel map names where it cannot name a string (see cell_walk): a NaN axis fails every "farther than" test
+        if (tid == 0) sp.strings[geo.num_strings] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), 0.f, 0.f);
         for (int i = tid; i < geo.num_sets; i += kThreads)
             sp.sets[i] = make_float4(__ldg(geo.set_start_z + i), 1.f / __ldg(geo.set_layer_height + i),
                                      static_cast<float>(__ldg(geo.set_layer_count + i)), static_cast<float>(i * geo.max_layers));
@@ -1193,7 +1209,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     // ---- lane and warp state
     float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
     float *warp_region = reinterpret_cast<float *>(smem + lay.off_queue);
-    const float *queue = warp_region + warp * (kQueueWords * 32);
+    const float4 *queue = reinterpret_cast<const float4 *>(warp_region) + warp * (kQueueChunks * 32);
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = args.rng_a[gthread];
@@ -1204,7 +1220,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(x >> 32));
         st[kStatus * kThreads] = __uint_as_float(static_cast<uint32_t>(kDead));
         st[kScatters * kThreads] = __uint_as_float(0xffffffffu); // no photon yet: counts as 0 flights when replaced
-        reinterpret_cast<uint32_t *>(st + kOffNSeg)[0] = 0u;
+        tag_record(st)[3] = 0u;
         if (lane == 0) {
             wctl[kWLeft] = 0u; wctl[kWStepIndex] = 0xffffffffu; wctl[kWMore] = 1u; wctl[kWQueued] = 0u; wctl[kWCreated] = 0u;
         }
@@ -1212,7 +1228,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     __syncthreads();
 
     for (;;) {
-        const int limit = slow_phase<TILT, ANISO, SAVE_ALL>(args.scene_dev, st, warp_region);
+        const int limit = slow_phase<TILT, ANISO, SAVE_ALL, MIXED>(args.scene_dev, st, warp_region);
         if (limit < 0) break;
         // ---- fast phase: photon state in registers, no calls.  A lane whose photon ended takes the next
         //      one from the warp's queue right here; the phase ends when the queue runs dry, or when
@@ -1225,8 +1241,6 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             L.dxy.x *= inv; L.dxy.y *= inv; L.dz *= inv;
             L.inv_dz = raw_inv_dz(L.dz);
         }
-        bool cleared = (L.status == kCleared);
-        if (cleared) L.status = kActive;
         uint32_t queued = wctl[kWQueued];
         const bool more = (wctl[kWMore] != 0u) || (wctl[kWLeft] > 0u);
         for (;;) {
@@ -1242,7 +1256,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                         const uint32_t rank = __popc(dead & lanemask_lt());
                         if (L.status == kDead && rank < queued) {
                             flights += L.scatters + 1u;
-                            take_photon<SAVE_ALL>(L, queue + (queued - 1u - rank), st);
+                            take_photon<SAVE_ALL>(L, queue + kQueueChunks * (queued - 1u - rank), st);
                         }
                         const uint32_t taken = min(n_dead, queued);
                         queued -= taken;
@@ -1256,10 +1270,9 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
 #pragma unroll
             for (int leg = 0; leg < kHotUnroll; ++leg)
                 if (L.status == kActive)
-                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, cleared, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
+                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
                                                                  sp.tilt_corr, rng_a, st);
         }
-        if (cleared && L.status == kActive) L.status = kCleared; // the phase ended before the lane used its clearance
         store_lane<TILT, ANISO>(L, st);
         __syncwarp();   // every lane has read the control block before lane 0 rewrites it
         if (lane == 0) wctl[kWQueued] = queued;
@@ -1269,7 +1282,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     args.rng_x[gthread] = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
     if (args.count_stats) {
         // warp-level reduction, one atomic per warp; the lane's last photon has not been counted yet
-        unsigned long long segs = static_cast<unsigned long long>(reinterpret_cast<uint32_t *>(st + kOffNSeg)[0]) + flights +
+        unsigned long long segs = static_cast<unsigned long long>(tag_record(st)[3]) + flights +
                                   (__float_as_uint(st[kScatters * kThreads]) + 1u);
         for (int o = 16; o > 0; o >>= 1) segs += __shfl_down_sync(0xffffffffu, segs, o);
         if (lane == 0) {
@@ -1311,11 +1324,11 @@ bool fast_kernel_supports(const DevScene &scene, const char **why)
     static const char *k_nonstop = "StopDetectedPhotons=false is only implemented by the reference-order kernel";
     static const char *k_renorm = "non-renormalising direction transforms are only implemented by the reference-order kernel";
     static const char *k_smem = "geometry/medium tables do not fit into shared memory";
-    static const char *k_strings = "more than 4095 strings";
+    static const char *k_strings = "more than 4094 strings";
     if (scene.history_entries > 0) { *why = k_history; return false; }
     if (!scene.save_all && !scene.stop_detected) { *why = k_nonstop; return false; }
     if (scene.medium.anisotropy && (!scene.medium.pre_renorm || !scene.medium.post_renorm)) { *why = k_renorm; return false; }
-    if (scene.geo.num_strings > 4095) { *why = k_strings; return false; }
+    if (scene.geo.num_strings > 4094) { *why = k_strings; return false; }
     if (plan_smem(scene).total + 1024u > kSmemBudget / kBlocksPerSM) { *why = k_smem; return false; }
     return true;
 }
