@@ -77,6 +77,11 @@ namespace {
 constexpr int kThreads = CLSIMCU_THREADS;
 // legs a lane flies between two looks at the warp's state (ballots, refill decisions) in the hot loop
 constexpr int kHotUnroll = CLSIMCU_HOT_UNROLL;
+#ifdef CLSIMCU_LOOK_EVERY_LEG
+constexpr bool kLookEveryLeg = true;    // A/B knob: consult the collision map on every leg
+#else
+constexpr bool kLookEveryLeg = false;
+#endif
 constexpr int kRefillBatch = CLSIMCU_REFILL_BATCH;            // lanes without a photon that make the warp stop for a refill
 constexpr int kWarpsPerBlock = kThreads / 32;
 constexpr int kBlocksPerSM = CLSIMCU_BLOCKS_PER_SM;
@@ -735,6 +740,7 @@ struct Leg {
     float d_b, cap;           // distance to the layer boundary ahead; range limit of the collision map (+inf: none)
     uint32_t cell;            // pixel-map word: byte offset of that string's record | range bits
     bool absorbed, limited;
+    bool looked;              // the collision map was consulted for this leg (o, cap and cell are set)
 };
 
 // +1 for a photon going up (or flat), -1 for one going down, from the sign of 1/dz
@@ -743,8 +749,11 @@ __device__ __forceinline__ int layer_step(float inv_dz) { return (__float_as_int
 __device__ __forceinline__ int cell_string(uint32_t cell) { return static_cast<int>((cell & 0xffffu) >> 4); }
 __device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff0000u) == 0x7f800000u; }
 
-template <bool TILT, bool SAVE_ALL>
-__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float4 *strings, const uint32_t *near)
+// LOOK_ALWAYS legs consult the collision map; the others are planned without it (no range limit) and may only be
+// flown if they are shorter than the photon's clearance (see advance_photon).
+template <bool TILT, bool SAVE_ALL, bool LOOK_ALWAYS>
+__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float4 *strings,
+                                        const uint32_t *near)
 {
     const DevGeometry &geo = scene.geo;
     Leg g;
@@ -762,7 +771,8 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
     g.cell = 0u;
     g.cap = __int_as_float(0x7f800000);
     g.o = make_float2(0.f, 0.f);
-    if (!SAVE_ALL) {
+    g.looked = !SAVE_ALL && LOOK_ALWAYS;
+    if (g.looked) {
         // (float -> unsigned conversion saturates below at 0)
         const uint32_t px = min(__float2uint_rz(fmaf(L.pxy.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
         const uint32_t py = min(__float2uint_rz(fmaf(L.pxy.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
@@ -813,8 +823,8 @@ __device__ __forceinline__ void rotate_packed(float cosa, float sina, float2 &dx
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
 __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a);
 
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
-__device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS>
+__device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
                                                const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
                                                const float *tilt_corr, uint32_t rng_a, float *st)
 {
@@ -840,10 +850,16 @@ __device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, c
         L.bud.y = -fast_ln(rng.oc());
         L.rng_x = rng.x;
     }
-    const Leg g = plan_leg<TILT, SAVE_ALL>(L, scene, layers, strings, near);
+    const Leg g = plan_leg<TILT, SAVE_ALL, LOOK_ALWAYS>(L, scene, layers, strings, near);
+    // `clearance`: how far the photon may still fly before any string can come within the collision radius, as
+    // known from the lane's last look at the collision map minus what it has flown since.  The first leg after each
+    // look at the warp state consults the map and sets it; the legs after that one do not look: a leg shorter than
+    // the clearance needs neither the map nor a test nor a range limit, and a lane whose leg is not waits for the
+    // next leg that looks (a few lanes in a hundred; cheaper than a divergent look-up in most warp-legs).
+    if (!SAVE_ALL && !LOOK_ALWAYS && !(g.travel < clearance)) return;
 
     // ------------------------------------------------------------------ R6: DOM collision, cheap part
-    if (!SAVE_ALL) {
+    if (g.looked) {
         // is the one string in range within reach of this leg at all?  (a few legs in a thousand; where the map
         // has no range every leg is)
         const float R = scene.geo.string_max_radius;
@@ -863,8 +879,6 @@ __device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, c
                     atomicAdd(dbg.stats + 2, 1ull);                                  // legs parked
                     if (walk) atomicAdd(dbg.stats + 3, 1ull);                        // ... in a dense-string pixel
                     if (out2 <= 0.f) atomicAdd(dbg.stats + 4, 1ull);                 // ... starting inside the cylinder
-                    if (L.scatters == 0u) atomicAdd(dbg.stats + 5, 1ull);            // ... before the first scatter
-                    if (g.travel > 20.f) atomicAdd(dbg.stats + 6, 1ull);             // ... long legs
                 }
 #endif
 #ifndef CLSIMCU_NO_Z_PRETEST
@@ -878,7 +892,11 @@ __device__ __forceinline__ void advance_photon(Lane &L, const DevScene &scene, c
                 }
             }
         }
+        // from here: to the cylinder around the named string, or to where any other string comes into range (the
+        // comparison fails for the NaN of a pixel without a range: no clearance there)
+        clearance = (o2 > 0.f) ? fminf(mufu_sqrt(o2) - R, g.cap) - 0.01f : 0.f;
     }
+    clearance -= g.travel;
     finish_leg<TILT, ANISO, SAVE_ALL, MIXED>(L, g, scene, rng_a);
 }
 
@@ -965,7 +983,7 @@ __device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st
     const SmemPlan sp = table_plan(lay);
     Lane L;
     load_lane<TILT, ANISO>(L, st);
-    const Leg g = plan_leg<TILT, false>(L, *scene, sp.layers, sp.strings, sp.near);
+    const Leg g = plan_leg<TILT, false, true>(L, *scene, sp.layers, sp.strings, sp.near);
     if (!col.hit) {
         L.status = kActive;
         finish_leg<TILT, ANISO, false, MIXED>(L, g, *scene, rng_a);
@@ -1267,11 +1285,15 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                     if (n_waiting + static_cast<int>(n_dead) >= limit) break;
                 }
             }
+            float clearance = 0.f;   // set by the first leg, used by the others (see plan_leg)
+            if (L.status == kActive)
+                advance_photon<TILT, ANISO, SAVE_ALL, MIXED, true>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
+                                                                   sp.tilt_corr, rng_a, st);
 #pragma unroll
-            for (int leg = 0; leg < kHotUnroll; ++leg)
+            for (int leg = 1; leg < kHotUnroll; ++leg)
                 if (L.status == kActive)
-                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED>(L, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
-                                                                 sp.tilt_corr, rng_a, st);
+                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED, kLookEveryLeg>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near,
+                                                                                sp.tilt_dist, sp.tilt_corr, rng_a, st);
         }
         store_lane<TILT, ANISO>(L, st);
         __syncwarp();   // every lane has read the control block before lane 0 rewrites it
