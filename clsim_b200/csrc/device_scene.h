@@ -34,9 +34,11 @@ struct DevMedium {
     float f_sl, one_minus_f_sl, g, g2, sl_beta;
     float inv_f_sl, inv_one_minus_f_sl, inv_2g; // fast kernel: reciprocals (0 where undefined)
     // fast kernel, SL + HG mix folded into constants (computed in double on the host, see upload_tables):
-    //   cos_sl = ex2(sl_beta * lg2(u) + sl_off) - 1            == 2 (u / f_sl)^beta - 1
-    //   cos_hg = hg_c - hg_w * r^2,  r = 1 / (hg_h0 + hg_h1 u) == ((1 + g^2) - ((1 - g^2) / (1 + g s))^2) / 2g,  s = 2 (1 - u) / (1 - f_sl) - 1
-    float sl_off, hg_h0, hg_h1, hg_c, hg_w;
+    // with U = the 32-bit draw as a float (u = U 2^-32):
+    //   cos_sl = ex2(sl_beta * lg2(U) + sl_off) - 1            == 2 (u / f_sl)^beta - 1
+    //   cos_hg = hg_c - hg_w * r^2,  r = 1 / (hg_h0 + hg_h1 U) == ((1 + g^2) - ((1 - g^2) / (1 + g s))^2) / 2g,  s = 2 (1 - u) / (1 - f_sl) - 1
+    //   SL where U < mix_split == u < f_sl (both sides scaled by the exact 2^32)
+    float sl_off, hg_h0, hg_h1, hg_c, hg_w, mix_split;
     int mix_folded; // the five constants above are set (f_sl in (0,1), g != 0)
     int tilt_nd, tilt_nz;
     float tilt_z0, tilt_dz, tilt_inv_dz, tilt_lnx, tilt_lny;

@@ -288,9 +288,10 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     dm.inv_2g = (m.g != 0.f) ? 1.f / (2.f * m.g) : 0.f;
     if (m.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && m.f_sl > 0.f && m.one_minus_f_sl > 0.f && m.g != 0.f) {
         const double f = m.f_sl, omf = m.one_minus_f_sl, g = m.g;
-        dm.sl_off = static_cast<float>(static_cast<double>(m.sl_beta) * std::log2(1.0 / f) + 1.0);
+        dm.sl_off = static_cast<float>(static_cast<double>(m.sl_beta) * (std::log2(1.0 / f) - 32.0) + 1.0);
         dm.hg_h0 = static_cast<float>(1.0 + g * (2.0 / omf - 1.0));
-        dm.hg_h1 = static_cast<float>(-2.0 * g / omf);
+        dm.hg_h1 = static_cast<float>(-2.0 * g / omf / 4294967296.0);
+        dm.mix_split = m.f_sl * 4294967296.f;
         dm.hg_c = static_cast<float>((1.0 + g * g) / (2.0 * g));
         dm.hg_w = static_cast<float>((1.0 - g * g) * (1.0 - g * g) / (2.0 * g));
         dm.mix_folded = 1;

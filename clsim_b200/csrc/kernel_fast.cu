@@ -791,26 +791,33 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
 
 // R8 (propagation_kernel.c.cl:83-129) on a direction held as (xy pair, z); the azimuth comes as the raw 32-bit
 // draw, so that its scaling to [0, 2 pi) is one multiplication (bit-identical to 2 pi * (draw * 2^-32): the power of
-// two is exact).  With k = sin(a)/sin(theta), u = cos(b) k, w = cos(a) - z sin(b) k:
-//     (x, y)' = (x, y) w + (-y, x) u        z' = z cos(a) + sin(a) sin(b) sin(theta)
+// two is exact).  With k = sin(a)/sin(theta), u = cos(b) k, w = cos(a) - z sin(b) k, m = sin(a) sin(theta):
+//     (x, y)' = (x, y) w + (-y, x) u        z' = z cos(a) + m sin(b)
 // sin^2(theta) is taken from x and y, not as 1 - z^2: for a direction whose length is off by eps the rotation then
 // gives a length off by at most eps again (with 1 - z^2 the error is amplified by sin^2(a)/sin^2(theta) near the
 // poles), so the length only random-walks by rounding and is restored once per fast phase, not per scatter.
-__device__ __forceinline__ void rotate_packed(float cosa, float sina, float2 &dxy, float &dz, uint32_t draw)
+// The scattering angle comes as its cosine and sin^2 (in [0, 1]); k and m take ONE reciprocal root:
+//     r = 1/sqrt(sin^2(a) sin^2(theta)),   k = sin^2(a) r,   m = sin^2(a) sin^2(theta) r
+// (the special-function unit, 8 cycles per warp instruction and scheduler, is the next bound after issue).
+__device__ __forceinline__ void rotate_packed(float cosa, float sina2, float2 &dxy, float &dz, uint32_t draw)
 {
     float sinb, cosb;
     __sincosf(__uint2float_rz(draw) * (2.0f * kPi * 2.3283064365386963e-10f), &sinb, &cosb);
     const float s2 = fmaf(dxy.x, dxy.x, dxy.y * dxy.y);
-    if (s2 > 0.f) {
-        const float inv_s = mufu_rsqrt(s2);
-        const float2 ks = __fmul2_rn(make_float2(sina, s2), make_float2(inv_s, inv_s));   // (k, sin(theta))
-        const float u = cosb * ks.x;
-        const float w = fmaf(-dz * sinb, ks.x, cosa);
-        const float nz = fmaf(sina * sinb, ks.y, dz * cosa);
+    if (s2 > 1e-20f) {
+        // (sin^2(a) is 0 or at least an ulp of 1, so the product is 0 or a normal number; 0 gives k = m = 0)
+        const float x = sina2 * s2;
+        const float r = mufu_rsqrt(fmaxf(x, 1e-36f));
+        const float2 km = __fmul2_rn(make_float2(sina2, x), make_float2(r, r));   // (k, m)
+        const float u = cosb * km.x;
+        const float w = fmaf(-dz * sinb, km.x, cosa);
+        const float nz = fmaf(sinb, km.y, dz * cosa);
         const float2 along = __fmul2_rn(dxy, make_float2(w, w));
         dxy = __ffma2_rn(make_float2(-dxy.y, dxy.x), make_float2(u, u), along);
         dz = nz;
     } else {
+        // within 1e-10 rad of a pole
+        const float sina = mufu_sqrt(sina2);
         dxy = make_float2(sina * cosb, sina * sinb);
         dz = (dz > 0.f) ? cosa : ((dz < 0.f) ? -cosa : cosa * dz);
     }
@@ -932,32 +939,34 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
         apply_matrix(m.pre, d);
         L.dxy = make_float2(d.x, d.y); L.dz = d.z;
     }
-    const float rr = rng.co();
+    const float ru = __uint2float_rz(rng.next());   // the draw, not yet scaled by 2^-32 (the MIXED constants carry the scale)
     float cs;
     const int scat_kind = MIXED ? CLSIMCU_SCAT_MIXED_SL_HG : m.scat_kind;   // the IceCube models' mix is compiled in
     if (MIXED) {
         // both samplers are evaluated and one is selected (no divergent branch); the constants of
         // I3CLSimRandomValueMixed / ...SimplifiedLiu / ...HenyeyGreenstein are folded on the host (DevMedium)
-        const float cos_sl = mufu_ex2(fmaf(m.sl_beta, mufu_lg2(rr), m.sl_off)) - 1.f;
-        const float r = mufu_rcp(fmaf(m.hg_h1, rr, m.hg_h0));
+        const float cos_sl = mufu_ex2(fmaf(m.sl_beta, mufu_lg2(ru), m.sl_off)) - 1.f;
+        const float r = mufu_rcp(fmaf(m.hg_h1, ru, m.hg_h0));
         const float cos_hg = fmaf(-m.hg_w, r * r, m.hg_c);
-        cs = (rr < m.f_sl) ? cos_sl : cos_hg;
-    } else if (scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
-        const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
-        const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
-        const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-        const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
-        cs = (rr < m.f_sl) ? cos_sl : cos_hg;
-    } else if (scat_kind == CLSIMCU_SCAT_HG) {
-        const float s = 2.f * rr - 1.f;
-        const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
-        cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
+        cs = (ru < m.mix_split) ? cos_sl : cos_hg;
     } else {
-        cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
+        const float rr = ru * 2.3283064365386963e-10f;
+        if (scat_kind == CLSIMCU_SCAT_MIXED_SL_HG) {
+            const float cos_sl = 2.f * fast_pow(rr * m.inv_f_sl, m.sl_beta) - 1.f;
+            const float s = 2.f * ((1.f - rr) * m.inv_one_minus_f_sl) - 1.f;
+            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+            const float cos_hg = (1.f + m.g2 - ii * ii) * m.inv_2g;
+            cs = (rr < m.f_sl) ? cos_sl : cos_hg;
+        } else if (scat_kind == CLSIMCU_SCAT_HG) {
+            const float s = 2.f * rr - 1.f;
+            const float ii = (1.f - m.g2) * mufu_rcp(1.f + m.g * s);
+            cs = (1.f + m.g2 - ii * ii) * m.inv_2g;
+        } else {
+            cs = 2.f * fast_pow(rr, m.sl_beta) - 1.f;
+        }
     }
-    // (the samplers stay within [-1, 1] up to the rounding of the approximate exp2 / reciprocal; only the root needs a guard)
-    const float sn = mufu_sqrt(fmaxf(fmaf(-cs, cs, 1.f), 0.f));
-    rotate_packed(cs, sn, L.dxy, L.dz, rng.next());
+    // (the samplers stay within [-1, 1] up to the rounding of the approximate exp2 / reciprocal: sin^2 saturates at 0)
+    rotate_packed(cs, __saturatef(fmaf(-cs, cs, 1.f)), L.dxy, L.dz, rng.next());
     if (ANISO) {
         V3 d{L.dxy.x, L.dxy.y, L.dz};
         apply_matrix(m.post, d);
