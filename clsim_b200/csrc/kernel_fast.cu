@@ -764,8 +764,14 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
     g.zb = (L.inv_dz < 0.f) ? c.w : z_up;                    // +-1e30 when there is no layer beyond
     g.zc = TILT ? L.z_eff : L.pz;
     g.d_b = fmaxf((g.zb - g.zc) * L.inv_dz, 0.f);            // (0 * inf = NaN -> 0: a flat photon on a boundary steps over it)
+    // (the budgets are written by predicated code in several places; ptxas does not keep them in an aligned register
+    // pair, and packed instructions on them cost more in moves than they save -- measured)
+#ifdef CLSIMCU_PACKED_BUDGETS
     const float2 cmp = __fmul2_rn(L.bud, g.q);               // (abs_left * b, sca_left * a)
     g.absorbed = cmp.x < cmp.y;                              // d_absorb < d_scatter inside this layer
+#else
+    g.absorbed = L.bud.x * g.q.x < L.bud.y * g.q.y;          // d_absorb < d_scatter inside this layer
+#endif
     const float d_sa = (g.absorbed ? L.bud.x : L.bud.y) * mufu_rcp(g.absorbed ? g.q.y : g.q.x);
     // pixel map: nearest string and the range within which no other string can be touched
     g.cell = 0u;
@@ -781,11 +787,16 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
         const float2 sxy = *reinterpret_cast<const float2 *>(reinterpret_cast<const uint8_t *>(strings) + (g.cell & 0xffffu));
         g.o = __fadd2_rn(sxy, make_float2(-L.pxy.x, -L.pxy.y));
     }
-    const float d_geo = fminf(g.d_b, g.cap);
+    const float d_geo = g.looked ? fminf(g.d_b, g.cap) : g.d_b;
     g.limited = d_geo < d_sa;                                // the flight goes on after this leg
     g.travel = fminf(d_geo, d_sa);
+#ifdef CLSIMCU_PACKED_BUDGETS
     g.rem = __ffma2_rn(make_float2(-g.travel, -g.travel), make_float2(g.q.y, g.q.x), L.bud);
     g.rem.y = fmaxf(g.rem.y, 1e-30f);
+#else
+    g.rem.x = fmaf(-g.travel, g.q.y, L.bud.x);
+    g.rem.y = fmaxf(fmaf(-g.travel, g.q.x, L.bud.y), 1e-30f);
+#endif
     return g;
 }
 
