@@ -77,6 +77,11 @@ namespace {
 constexpr int kThreads = CLSIMCU_THREADS;
 // legs a lane flies between two looks at the warp's state (ballots, refill decisions) in the hot loop
 constexpr int kHotUnroll = CLSIMCU_HOT_UNROLL;
+// ... for the ice models with tilt or anisotropy, whose legs are twice as long in code (instruction cache)
+#ifndef CLSIMCU_HOT_UNROLL_TILTED
+#define CLSIMCU_HOT_UNROLL_TILTED 3
+#endif
+constexpr int kHotUnrollTilted = CLSIMCU_HOT_UNROLL_TILTED;
 #ifdef CLSIMCU_LOOK_EVERY_LEG
 constexpr bool kLookEveryLeg = true;    // A/B knob: consult the collision map on every leg
 #else
@@ -1310,7 +1315,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                 advance_photon<TILT, ANISO, SAVE_ALL, MIXED, true>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
                                                                    sp.tilt_corr, rng_a, st);
 #pragma unroll
-            for (int leg = 1; leg < kHotUnroll; ++leg)
+            for (int leg = 1; leg < ((TILT || ANISO) ? kHotUnrollTilted : kHotUnroll); ++leg)
                 if (L.status == kActive)
                     advance_photon<TILT, ANISO, SAVE_ALL, MIXED, kLookEveryLeg>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near,
                                                                                 sp.tilt_dist, sp.tilt_corr, rng_a, st);

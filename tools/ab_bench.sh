@@ -5,7 +5,7 @@ out=gpurun_out/ab_bench.txt
 : > $out
 for lib in clsim_b200/variants/*.so; do
   echo "== $lib" >> $out
-  CLSIMCU_LIB=$PWD/$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-variants 2>&1 | python -c "
+  CLSIMCU_LIB=$PWD/$lib timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-variants $AB_ARGS 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     l=l.strip()
