@@ -114,7 +114,7 @@ enum StateWord {
 };
 // per-lane birth tag of the photon in flight (3 words) and, in the save-all variants, the state of the
 // propagation stream when it started (2 words): what a checker needs to replay the photon
-constexpr int kTagRecordWords = 4;   // per thread, 16 bytes: birth tag (3 words) | flights of the photons the lane finished in slow phases
+constexpr int kTagRecordWords = 4;   // per thread: birth tag (3 words) | flights (reference: segments) of the photons the lane has finished
 constexpr int kPopTagWords = 2;
 // per-warp control block
 enum WarpCtl { kWLeft = 0, kWStepIndex, kWMore, kWQueued, kWCreated, kWarpCtlWords = 8 };
@@ -224,8 +224,9 @@ __device__ __forceinline__ uint8_t *smem_base()
     return smem;
 }
 
-// the calling thread's tag record; `st` is its column of the per-thread state arrays
-__device__ __forceinline__ uint32_t *tag_record(float *st) { return reinterpret_cast<uint32_t *>(st + kOffBirthTag + (kTagRecordWords - 1) * threadIdx.x); }
+// word `w` of the calling thread's tag record; `st` is its column of the per-thread state arrays (the record is laid out
+// like them, [word][thread]: every access is `st` + a compile-time offset, no second pointer to keep alive in the hot loop)
+__device__ __forceinline__ uint32_t &tag_word(float *st, int w) { return reinterpret_cast<uint32_t *>(st + kOffBirthTag)[w * kThreads]; }
 
 __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
 {
@@ -565,11 +566,10 @@ __device__ __noinline__ void emit_record(const DevScene *scene_dev, float *st, V
     if (slot >= args.max_hits) return; // counted but dropped (quirk 10)
 
     // birth tag -> start-of-flight record
-    const uint32_t *btag = tag_record(st);
-    const uint32_t tag_step = btag[2];
+    const uint32_t tag_step = tag_word(st, 2);
     const uint32_t step_index = tag_step & ((1u << kStepIndexBits) - 1u);
     const uint32_t made_by = (blockIdx.x * kThreads + (threadIdx.x & ~31u)) + (tag_step >> kStepIndexBits);
-    const uint64_t birth_x = static_cast<uint64_t>(btag[0]) | (static_cast<uint64_t>(btag[1]) << 32);
+    const uint64_t birth_x = static_cast<uint64_t>(tag_word(st, 0)) | (static_cast<uint64_t>(tag_word(st, 1)) << 32);
     const uint32_t birth_a = __ldg(args.rng_a + args.rng_creation_offset + made_by);
     const clsimcu_step *step = static_cast<const clsimcu_step *>(args.steps) + step_index;
     StepView sv;
@@ -1107,9 +1107,7 @@ __device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *
     L.scatters = 0u;
     L.layer = __float_as_int(c1.w);
     L.status = kActive;
-    uint32_t *btag = tag_record(st);
-    *reinterpret_cast<float2 *>(btag) = make_float2(c3.x, c3.y);
-    btag[2] = __float_as_uint(c3.z);
+    tag_word(st, 0) = __float_as_uint(c3.x); tag_word(st, 1) = __float_as_uint(c3.y); tag_word(st, 2) = __float_as_uint(c3.z);
     if (SAVE_ALL) {
         float *ptag = st + kOffPopTag;
         ptag[0 * kThreads] = __uint_as_float(static_cast<uint32_t>(L.rng_x));
@@ -1130,7 +1128,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const unsigned lane_bit = 1u << lane;
-    uint32_t *nseg = tag_record(st) + 3;
+    uint32_t *nseg = &tag_word(st, 3);
     const float4 *queue = reinterpret_cast<const float4 *>(warp_region) + warp * (kQueueChunks * 32);
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
@@ -1256,14 +1254,13 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = args.rng_a[gthread];
-    uint32_t flights = 0u; // statistics: flights (reference: segments) of the photons this lane finished in the hot loop
     {
         const uint64_t x = args.rng_x[gthread];
         st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(x));
         st[kRngHi * kThreads] = __uint_as_float(static_cast<uint32_t>(x >> 32));
         st[kStatus * kThreads] = __uint_as_float(static_cast<uint32_t>(kDead));
         st[kScatters * kThreads] = __uint_as_float(0xffffffffu); // no photon yet: counts as 0 flights when replaced
-        tag_record(st)[3] = 0u;
+        tag_word(st, 3) = 0u;
         if (lane == 0) {
             wctl[kWLeft] = 0u; wctl[kWStepIndex] = 0xffffffffu; wctl[kWMore] = 1u; wctl[kWQueued] = 0u; wctl[kWCreated] = 0u;
         }
@@ -1298,7 +1295,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                     if (n_dead > 0u && queued > 0u) {
                         const uint32_t rank = __popc(dead & lanemask_lt());
                         if (L.status == kDead && rank < queued) {
-                            flights += L.scatters + 1u;
+                            tag_word(st, 3) += L.scatters + 1u;   // statistics, kept in shared memory: a register here is a spill
                             take_photon<SAVE_ALL>(L, queue + kQueueChunks * (queued - 1u - rank), st);
                         }
                         const uint32_t taken = min(n_dead, queued);
@@ -1329,7 +1326,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     args.rng_x[gthread] = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
     if (args.count_stats) {
         // warp-level reduction, one atomic per warp; the lane's last photon has not been counted yet
-        unsigned long long segs = static_cast<unsigned long long>(tag_record(st)[3]) + flights +
+        unsigned long long segs = static_cast<unsigned long long>(tag_word(st, 3)) +
                                   (__float_as_uint(st[kScatters * kThreads]) + 1u);
         for (int o = 16; o > 0; o >>= 1) segs += __shfl_down_sync(0xffffffffu, segs, o);
         if (lane == 0) {
