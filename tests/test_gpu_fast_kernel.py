@@ -182,6 +182,36 @@ def test_fast_kernel_against_oracle_small_sample():
     _assert_same_distributions(attempt, 1e-2)
 
 
+def test_dense_strings_take_the_cell_walk(monkeypatch):
+    """Strings closer together than the pixels of the collision map are wide: the map has no range there, every
+    leg is parked and takes the reference's cell walk in the slow phase (sparse_collision_kernel.c.cl:194-460).
+    A cluster of three strings 6-7 m apart in its own subdetector next to the 24-DOM ring, a map forced coarse
+    (CLSIMCU_PIXEL_BUDGET), a point source inside the cluster: the fast kernel must see what the reference-order
+    kernel sees."""
+    from clsim_b200 import geometry
+    from clsim_b200.description import SimpleGeometry
+    sc = make_scene("homogeneous", geo_kind="ring")
+    ring = sc.geo
+    sid, did, xs, ys, zs = list(ring.stringIDs), list(ring.domIDs), list(ring.posX), list(ring.posY), list(ring.posZ)
+    sub = ["Ring"] * len(sid)
+    for k, (cx, cy) in enumerate(((0.0, 0.0), (6.0, 0.5), (-0.5, 7.0))):
+        for d in range(6):
+            sid.append(20 + k); did.append(d + 1); xs.append(cx + 0.1 * d); ys.append(cy - 0.05 * d); zs.append(25.0 - 10.0 * d)
+            sub.append("Cluster")
+    sc.geo = SimpleGeometry(sid, did, xs, ys, zs, ring.OMRadius, subdetectors=sub)
+    monkeypatch.setenv("CLSIMCU_PIXEL_BUDGET", "512")   # pixels of ~12 m over the 240 m ring
+    bunch = steps.point_source_steps(1 << 14, 200, pos=(3.0, 3.0, 2.0), seed=77)
+
+    def attempt(k):
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=11 + 1000 * k)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=12 + 1000 * k)
+        assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert len(ref) > 2e4 and set(np.unique(ref["string_id"])) >= {20, 21, 22}
+        return _compare_distributions(fast, ref, tot_f, tot_r)
+
+    _assert_same_distributions(attempt, 1e-2)
+
+
 def test_flasher_mode_statistics():
     sc = add_flasher_generator(make_scene("spice_lea", oversize=1.0))
     dom = dom_near(sc.geo, (0.0, 0.0, -200.0))
