@@ -62,8 +62,8 @@ def test_replay_parity_per_photon(name):
     assert worst < 1e-2
 
 
-def _run_resident(sc, bunch, mode, seed, repeat=1):
-    opt = sc.options(kernel_mode=mode, max_num_workitems=len(bunch), rng_seed=seed, output_photons_per_workitem=2)
+def _run_resident(sc, bunch, mode, seed, repeat=1, per_item=2):
+    opt = sc.options(kernel_mode=mode, max_num_workitems=len(bunch), rng_seed=seed, output_photons_per_workitem=per_item)
     hits = []
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         eng.upload_resident(bunch)
@@ -203,9 +203,11 @@ def test_dense_strings_take_the_cell_walk(monkeypatch):
     bunch = steps.point_source_steps(1 << 14, 200, pos=(3.0, 3.0, 2.0), seed=77)
 
     def attempt(k):
-        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=11 + 1000 * k)
-        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=12 + 1000 * k)
+        # (room for every photon: a full output buffer keeps the first hits written, a biased sample)
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=11 + 1000 * k, per_item=200)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=12 + 1000 * k, per_item=200)
         assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert tot_f["hits"] == len(fast) and tot_r["hits"] == len(ref)
         assert len(ref) > 2e4 and set(np.unique(ref["string_id"])) >= {20, 21, 22}
         return _compare_distributions(fast, ref, tot_f, tot_r)
 
