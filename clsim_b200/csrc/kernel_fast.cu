@@ -35,8 +35,14 @@
 //    too).  A 2-D segment/cylinder test against that one string rules out > 99.9 % of the
 //    segments in ~25 instructions; the rest run the reference's string / cell walk in the slow
 //    phase.
-//  * One reciprocal per iteration; SL and HG scattering angles are both evaluated and selected
-//    (no divergent branch); fast approximate MUFU intrinsics.
+//  * The kernel is bound by instruction issue, so the arithmetic is written for few instructions: sm_100a's packed
+//    fp32 instructions (FFMA2 / FMUL2 / FADD2, two operations per issue slot) on the (x, y) pairs of position and
+//    direction, the layer coefficients and the wavelength factors; the SL + HG scattering mix from constants folded
+//    on the host (both samplers evaluated, one selected: no divergent branch); one reciprocal root for the whole
+//    rotation; approximate MUFU intrinsics throughout.
+//  * The loop head (ballots, refill) runs every third leg, and only the first of the three legs consults the
+//    collision map: it leaves the lane a clearance (distance it may fly before any string can come into play) on
+//    which the other two fly without map, test or range limit.
 //  * Hits: warp-aggregated atomic reservation, five 16-byte stores per record, string/DOM IDs
 //    and the wavelength-bias weight applied on the device.
 //
