@@ -103,6 +103,8 @@ constexpr float kPi = 3.14159265359f;
 constexpr float kEpsilon = 0.00001f;
 constexpr float kLn2 = 0.69314718056f;
 constexpr uint32_t kSmemBudget = 227u * 1024u;
+constexpr int kGen0MaxEntries = 256;   // the Cherenkov generator of the IceCube setups has 43
+constexpr int kGen0Guide = 64;         // cells of the guide table over (0, 1]
 
 // queue slot (one photon waiting for a lane), four 16-byte chunks so that a lane takes a photon with four loads:
 //   0: (x, y, dx, dy)   1: (z, dz, lifetime in absorption lengths, ice layer)   2: (f_scat, f_pure, f_dust, -)
@@ -171,6 +173,8 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 // Shared-memory plan, carved out of the dynamic allocation.
 struct SmemLayout {
     uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_tilt_dist, off_tilt_corr;
+    uint32_t off_gen0;    // generator 0's cumulative | density | guide tables (gen0_n entries each, 64 guide bytes), see draw_wavelength
+    uint32_t gen0_n;      // 0: not staged
     uint32_t off_state;   // per-thread arrays: state | birth tag | segment counter | propagation-stream tag (save-all only)
     uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
     uint32_t cell_offset[kMaxSubdetectors];
@@ -218,6 +222,13 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
     L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 32);   // + 8 search keys
     L.off_tilt_corr = at; at = align16(at + s.medium.tilt_nd * s.medium.tilt_nz * 4);
+    L.off_gen0 = at;
+    L.gen0_n = 0;
+    if (s.num_generators >= 1 && (s.generators[0].kind == CLSIMCU_WLEN_INTERP_EQUAL || s.generators[0].kind == CLSIMCU_WLEN_INTERP_UNEQUAL) &&
+        s.generators[0].n >= 2 && s.generators[0].n <= kGen0MaxEntries) {
+        L.gen0_n = static_cast<uint32_t>(s.generators[0].n);
+        at = align16(at + 2 * L.gen0_n * 4 + kGen0Guide);
+    }
     L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kPopTagWords : 0)) * kThreads * 4);
     L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
     L.total = at;
@@ -299,29 +310,44 @@ __device__ __forceinline__ float inv_group_velocity(const DevMedium &m, float wl
     return np * corr * mufu_rcp(m.c_light);
 }
 
-// R3a: same bin as the reference's linear scan, found by bisection (cumulative is non-decreasing)
-__device__ float draw_wavelength(const DevWlenGenerator &g, Mwc &rng)
+// R3a: same bin as the reference's linear scan (cumulative is non-decreasing): smallest k in [0, n-2] with
+// cumulative[k+1] >= r.  `staged` != nullptr: the generator's cumulative and density tables sit in shared memory
+// behind a guide table (guide[c] = the bin of r = c/64, a lower bound for every r in that cell), and the bin is found
+// by a forward scan of a step or two from there; otherwise by bisection over the tables in global memory.
+__device__ float draw_wavelength(const DevWlenGenerator &g, Mwc &rng, const float *staged = nullptr)
 {
     if (g.kind == CLSIMCU_WLEN_CONSTANT) return g.value;
     const float r = rng.oc();
     if (g.kind == CLSIMCU_WLEN_NO_DISPERSION) return mufu_rcp(g.min_val + r * g.range);
-    // smallest k in [0, n-2] with cumulative[k+1] >= r
-    int lo = 0, hi = g.n - 2;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(g.cumulative + mid + 1) >= r) hi = mid;
-        else lo = mid + 1;
+    int k;
+    float below, b, b_next;
+    if (staged) {
+        const float *cum = staged, *dens = staged + g.n;
+        const uint8_t *guide = reinterpret_cast<const uint8_t *>(staged + 2 * g.n);
+        k = guide[min(__float2int_rz(r * static_cast<float>(kGen0Guide)), kGen0Guide - 1)];
+        while (k < g.n - 2 && cum[k + 1] < r) ++k;
+        below = (k == 0) ? 0.f : cum[k];
+        b = dens[k];
+        b_next = dens[k + 1];
+    } else {
+        int lo = 0, hi = g.n - 2;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(g.cumulative + mid + 1) >= r) hi = mid;
+            else lo = mid + 1;
+        }
+        k = lo;
+        below = (k == 0) ? 0.f : __ldg(g.cumulative + k);
+        b = __ldg(g.density + k);
+        b_next = __ldg(g.density + k + 1);
     }
-    const int k = lo;
-    const float below = (k == 0) ? 0.f : __ldg(g.cumulative + k);
-    const float b = __ldg(g.density + k);
     float x0, slope;
     if (g.kind == CLSIMCU_WLEN_INTERP_UNEQUAL) {
         x0 = __ldg(g.xs + k);
-        slope = (__ldg(g.density + k + 1) - b) / (__ldg(g.xs + k + 1) - x0);
+        slope = (b_next - b) / (__ldg(g.xs + k + 1) - x0);
     } else {
         x0 = static_cast<float>(k) * g.dx + g.x0;
-        slope = (__ldg(g.density + k + 1) - b) / g.dx;
+        slope = (b_next - b) / g.dx;
     }
     const float dy = r - below;
     if ((b == 0.f) && (slope == 0.f)) return x0;
@@ -512,7 +538,8 @@ __device__ __forceinline__ Born create_core(const DevScene *scene, const StepVie
     const float shift = s.length * rng.co();
     b.dir = s.axis;
     if (scene->num_generators <= 1 || s.source == 0) {
-        b.wlen = draw_wavelength(scene->generators[0], rng);
+        const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
+        b.wlen = draw_wavelength(scene->generators[0], rng, lay.gen0_n ? reinterpret_cast<const float *>(smem_base() + lay.off_gen0) : nullptr);
         const float cos_c = fminf(1.f, mufu_rcp(s.beta * phase_index(m, b.wlen)));
         const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
         rotate_by(cos_c, sin_c, b.dir, rng.co());
@@ -1233,6 +1260,22 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             keys[tid] = (tid >= 1 && tid <= m.tilt_nd - 2) ? __ldg(m.tilt_dist + tid) : __int_as_float(0x7f800000);
         }
         for (int i = tid; i < m.tilt_nd * m.tilt_nz; i += kThreads) sp.tilt_corr[i] = __ldg(m.tilt_corr + i);
+    }
+    if (lay.gen0_n) {
+        const DevWlenGenerator &g0 = scene.generators[0];
+        float *cum = reinterpret_cast<float *>(smem + lay.off_gen0), *dens = cum + g0.n;
+        uint8_t *guide = reinterpret_cast<uint8_t *>(dens + g0.n);
+        for (int i = tid; i < g0.n; i += kThreads) {
+            cum[i] = __ldg(g0.cumulative + i);
+            dens[i] = __ldg(g0.density + i);
+        }
+        if (tid < kGen0Guide) {
+            // the bin of r = tid/64, by the reference's linear scan
+            const float r = static_cast<float>(tid) * (1.f / static_cast<float>(kGen0Guide));
+            int k = 0;
+            while (k < g0.n - 2 && __ldg(g0.cumulative + k + 1) < r) ++k;
+            guide[tid] = static_cast<uint8_t>(k);
+        }
     }
     if (!SAVE_ALL) {
         for (int i = tid; i < geo.num_strings; i += kThreads) {
