@@ -62,8 +62,8 @@ def test_replay_parity_per_photon(name):
     assert worst < 1e-2
 
 
-def _run_resident(sc, bunch, mode, seed, repeat=1, per_item=2):
-    opt = sc.options(kernel_mode=mode, max_num_workitems=len(bunch), rng_seed=seed, output_photons_per_workitem=per_item)
+def _run_resident(sc, bunch, mode, seed, repeat=1, per_item=2, **more_options):
+    opt = sc.options(kernel_mode=mode, max_num_workitems=len(bunch), rng_seed=seed, output_photons_per_workitem=per_item, **more_options)
     hits = []
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         eng.upload_resident(bunch)
@@ -212,6 +212,25 @@ def test_dense_strings_take_the_cell_walk(monkeypatch):
         return _compare_distributions(fast, ref, tot_f, tot_r)
 
     _assert_same_distributions(attempt, 1e-2)
+
+
+def test_fixed_number_of_absorption_lengths():
+    """FixedNumberOfAbsorptionLengths (propagation_kernel.c.cl:582-585): every photon lives exactly that many
+    absorption lengths unless a DOM stops it.  Fast kernel against the reference-order kernel on SpiceLea with tilt
+    and anisotropy (the budget is rescaled at every scatter there), same statistics as the other tests."""
+    sc = make_scene("spice_lea")
+    bunch = steps.muon_track_steps(1 << 17, seed=55)
+
+    def attempt(k):
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=21 + 1000 * k, fixed_number_of_absorption_lengths=3.0)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=22 + 1000 * k, fixed_number_of_absorption_lengths=3.0)
+        assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert tot_f["hits"] == len(fast) and tot_r["hits"] == len(ref) and len(ref) > 2e4
+        for h in (fast, ref):
+            assert h["dist_in_abs_lens"].max() <= 3.0 + 1e-3
+        return _compare_distributions(fast, ref, tot_f, tot_r)
+
+    _assert_same_distributions(attempt, 2e-3)
 
 
 def test_flasher_mode_statistics():
