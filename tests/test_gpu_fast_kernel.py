@@ -214,6 +214,25 @@ def test_dense_strings_take_the_cell_walk(monkeypatch):
     _assert_same_distributions(attempt, 1e-2)
 
 
+@pytest.mark.parametrize("scat_kind", [1, 2])
+def test_single_scattering_angle_distributions(scat_kind):
+    """The ice models mix two scattering-angle samplers (R9), and that mix is compiled into the fast kernel; a
+    medium with Henyey-Greenstein (1) or simplified-Liu (2) alone takes the kernel's generic sampler code."""
+    sc = make_scene("homogeneous")
+    sc.medium.scat_kind = scat_kind
+    src = dom_near(sc.geo, (0.0, 0.0, 0.0)) + np.array([10.0, 5.0, 3.0])
+    bunch = steps.point_source_steps(1 << 16, 200, pos=tuple(src), seed=61)
+
+    def attempt(k):
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=31 + 1000 * k)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=32 + 1000 * k)
+        assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert tot_f["hits"] == len(fast) and tot_r["hits"] == len(ref) and len(ref) > 1e4
+        return _compare_distributions(fast, ref, tot_f, tot_r)
+
+    _assert_same_distributions(attempt, 2e-3)
+
+
 def test_fixed_number_of_absorption_lengths():
     """FixedNumberOfAbsorptionLengths (propagation_kernel.c.cl:582-585): every photon lives exactly that many
     absorption lengths unless a DOM stops it.  Fast kernel against the reference-order kernel on SpiceLea with tilt
