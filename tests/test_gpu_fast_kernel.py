@@ -233,6 +233,38 @@ def test_single_scattering_angle_distributions(scat_kind):
     _assert_same_distributions(attempt, 2e-3)
 
 
+@pytest.mark.parametrize("kind", ["unequal", "no_dispersion", "constant"])
+def test_other_wavelength_generators(kind):
+    """The wavelength generators besides the equally spaced table of the default setup (R3a): a table on unequal
+    abscissae (the staged path of the fast kernel with its abscissae in global memory), the analytic 1/lambda^2
+    spectrum (I3CLSimRandomValueWlenCherenkovNoDispersion) and a single wavelength (I3CLSimRandomValueConstant)."""
+    from clsim_b200.description import WlenGenerator
+    sc = make_scene("spice_mie")
+    g0 = sc.generators[0]
+    if kind == "unequal":
+        x = g0.x0 + g0.dx * np.arange(len(g0.y))
+        keep = np.ones(len(x), dtype=bool)
+        keep[3::4] = False                      # drop every fourth node: unequal spacing, a different spectrum for both kernels
+        keep[0] = keep[-1] = True
+        sc.generators = [WlenGenerator.interpolated_unequal(x[keep], g0.y[keep])]
+    elif kind == "no_dispersion":
+        sc.generators = [WlenGenerator.cherenkov_no_dispersion(sc.medium.GetMinWavelength(), sc.medium.GetMaxWavelength())]
+    else:
+        sc.generators = [WlenGenerator.constant(405e-9)]
+    bunch = steps.muon_track_steps(1 << 16, seed=71)
+
+    def attempt(k):
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=41 + 1000 * k)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=42 + 1000 * k)
+        assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert tot_f["hits"] == len(fast) and tot_r["hits"] == len(ref) and len(ref) > 5e3
+        if kind == "constant":
+            assert np.all(fast["wavelength"] == np.float32(405e-9)) and np.all(ref["wavelength"] == np.float32(405e-9))
+        return _compare_distributions(fast, ref, tot_f, tot_r)
+
+    _assert_same_distributions(attempt, 2e-3)
+
+
 def test_fixed_number_of_absorption_lengths():
     """FixedNumberOfAbsorptionLengths (propagation_kernel.c.cl:582-585): every photon lives exactly that many
     absorption lengths unless a DOM stops it.  Fast kernel against the reference-order kernel on SpiceLea with tilt
