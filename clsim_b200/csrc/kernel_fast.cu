@@ -114,7 +114,7 @@ constexpr int kGen0Guide = 64;         // cells of the guide table over (0, 1]
 // record is re-created from the tag (creation is deterministic).
 constexpr int kQueueChunks = 4;
 constexpr int kQueueWords = 4 * kQueueChunks;
-constexpr uint32_t kStepIndexBits = kFastKernelStepIndexBits; // tag word kQTagStep = step index | (creating lane << 27)
+constexpr uint32_t kStepIndexBits = kFastKernelStepIndexBits; // third tag word = step index | (creating lane << 27)
 // per-lane running state, parked in shared memory between fast phases
 enum StateWord {
     kPx = 0, kPy, kPz, kDx, kDy, kDz, kAbsLeft, kScaLeft, kPath, kFScat, kFDust, kFPure, kScatters, kLayer, kStatus, kRngLo, kRngHi,
@@ -554,7 +554,7 @@ __device__ __forceinline__ Born create_core(const DevScene *scene, const StepVie
     return b;
 }
 
-// Queue fill: one photon of the warp's current step into queue slot `slot` (word stride 32), together
+// Queue fill: one photon of the warp's current step into queue slot `slot` (four 16-byte chunks), together
 // with the wavelength-only factors of the ice model (R4, …_Optimizers.cxx:123-250).  The scene is read
 // from its copy in global memory (uniform addresses).  Returns the advanced creation-stream state.
 __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint32_t *wstep, float4 *slot, uint64_t rng_x, uint32_t rng_a,
@@ -1127,7 +1127,7 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
     __syncwarp();
 }
 
-// A lane takes the photon in queue slot `slot` (word stride 32): running state into `L`, birth tag (and,
+// A lane takes the photon in queue slot `slot` (four 16-byte chunks): running state into `L`, birth tag (and,
 // save-all, the propagation-stream state) into the lane's tag words.
 template <bool SAVE_ALL>
 __device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *st)
