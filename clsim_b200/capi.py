@@ -23,6 +23,7 @@ SYMBOLS = [
     "clsimcu_queue_size", "clsimcu_more_photons_available", "clsimcu_workgroup_size", "clsimcu_max_num_workitems",
     "clsimcu_get_statistics", "clsimcu_upload_resident", "clsimcu_run_resident", "clsimcu_download_resident",
     "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
+    "clsimcu_describe_collision_map_from_config",
     "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
     "clsimcu_sizeof_config", "clsimcu_device_count",
     "clsimcu_mcpe_create", "clsimcu_mcpe_destroy", "clsimcu_mcpe_convert", "clsimcu_mcpe_rng_get", "clsimcu_attach_mcpe_converter",
@@ -73,6 +74,7 @@ def lib():
         L.clsimcu_rng_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.clsimcu_describe_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_describe_tables_from_config.argtypes = [C.POINTER(ConfigStruct), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.clsimcu_describe_collision_map_from_config.argtypes = [C.POINTER(ConfigStruct), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_safeprime_multipliers.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
         if L.clsimcu_sizeof_config() != C.sizeof(ConfigStruct):
             raise ImportError("clsimcu_config layout mismatch between description.py and libclsimcuda.so")
@@ -105,6 +107,17 @@ def describe_tables(medium, geometry, wlen_generators, wlen_bias, options):
     _check(lib().clsimcu_describe_tables_from_config(C.byref(cfg), None, 0, C.byref(need)))
     buf = C.create_string_buffer(need.value)
     _check(lib().clsimcu_describe_tables_from_config(C.byref(cfg), buf, need.value, C.byref(need)))
+    del keep
+    return json.loads(buf.value.decode())
+
+
+def describe_collision_map(medium, geometry, wlen_generators, wlen_bias, options, pixel_budget=40000):
+    """The fast kernel's xy collision map for a pixel budget (host code, no GPU needed)."""
+    cfg, keep = build_config(medium, geometry, wlen_generators, wlen_bias, options)
+    need = C.c_size_t(0)
+    _check(lib().clsimcu_describe_collision_map_from_config(C.byref(cfg), int(pixel_budget), None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _check(lib().clsimcu_describe_collision_map_from_config(C.byref(cfg), int(pixel_budget), buf, need.value, C.byref(need)))
     del keep
     return json.loads(buf.value.decode())
 

@@ -379,57 +379,11 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
         // xy pixel map for the fast kernel (see device_scene.h); built for the pixel budget the
         // caller found to fit into shared memory
         {
-            float xlo = g.string_x[0], xhi = g.string_x[0], ylo = g.string_y[0], yhi = g.string_y[0];
-            for (int i = 0; i < g.num_strings; ++i) {
-                xlo = std::min(xlo, g.string_x[i]); xhi = std::max(xhi, g.string_x[i]);
-                ylo = std::min(ylo, g.string_y[i]); yhi = std::max(yhi, g.string_y[i]);
-            }
-            // one pixel of margin is enough: a point outside the map is farther from every string
-            // than its projection onto the map, so the border pixels' bounds hold for it
-            float pixel = 4.f;
-            for (;;) {
-                const double w = (xhi - xlo) + 2.0 * pixel, h = (yhi - ylo) + 2.0 * pixel;
-                if (std::ceil(w / pixel) * std::ceil(h / pixel) <= static_cast<double>(near_pixel_budget)) break;
-                pixel *= 1.05f;
-            }
-            dg.near_x0 = xlo - pixel;
-            dg.near_y0 = ylo - pixel;
-            dg.near_inv_pixel = 1.f / pixel;
-            dg.near_off_x = -dg.near_x0 * dg.near_inv_pixel;
-            dg.near_off_y = -dg.near_y0 * dg.near_inv_pixel;
-            dg.near_nx = static_cast<int>(std::ceil((xhi - xlo + 2 * pixel) / pixel));
-            dg.near_ny = static_cast<int>(std::ceil((yhi - ylo + 2 * pixel) / pixel));
-            const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-2; // + slack for fp32 pixel assignment
-            const double min_range = 1.0; // below this the map cannot limit flights sensibly: cell walk
-            std::vector<uint32_t> info(static_cast<size_t>(dg.near_nx) * dg.near_ny);
-            for (int iy = 0; iy < dg.near_ny; ++iy) {
-                for (int ix = 0; ix < dg.near_nx; ++ix) {
-                    const double cx = dg.near_x0 + (ix + 0.5) * pixel, cy = dg.near_y0 + (iy + 0.5) * pixel;
-                    double best = 1e30, second = 1e30;
-                    int who = 0;
-                    for (int k = 0; k < g.num_strings; ++k) {
-                        const double d = std::hypot(cx - g.string_x[k], cy - g.string_y[k]);
-                        if (d < best) { second = best; best = d; who = k; }
-                        else if (d < second) second = d;
-                    }
-                    // how far a photon anywhere in this pixel may fly before a string other than
-                    // `who` can come within the collision radius
-                    double range = std::min(second, 1e9) - half_diag - g.string_max_radius - 1e-2;
-                    const float rf = static_cast<float>(range);
-                    uint32_t bits;
-                    std::memcpy(&bits, &rf, 4);
-                    bits &= 0xffff0000u; // truncation of a positive float rounds down: the bound stays a lower bound
-                    uint32_t low = static_cast<uint32_t>(who) << 4; // byte offset of the string's 16-byte record
-                    if (range < min_range) {
-                        // strings too dense for the pixel size: no range (+inf) and no string (the record behind the
-                        // last one, which the kernel fills with NaN): every leg takes the reference's cell walk
-                        bits = 0x7f800000u;
-                        low = static_cast<uint32_t>(g.num_strings) << 4;
-                    }
-                    info[static_cast<size_t>(iy) * dg.near_nx + ix] = low | bits;
-                }
-            }
-            o_near_info = arena.add(info);
+            const CollisionMap map = build_collision_map(g, near_pixel_budget);
+            dg.near_x0 = map.x0; dg.near_y0 = map.y0; dg.near_inv_pixel = map.inv_pixel;
+            dg.near_off_x = map.off_x; dg.near_off_y = map.off_y;
+            dg.near_nx = map.nx; dg.near_ny = map.ny;
+            o_near_info = arena.add(map.info);
         }
     }
 
@@ -1233,6 +1187,22 @@ int clsimcu_describe_tables_from_config(const clsimcu_config *config, char *buf,
         SceneTables t;
         build_scene_tables(*config, t);
         return copy_text(describe_scene_tables(t), buf, cap, needed);
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_INVALID, ex.what());
+    }
+}
+
+int clsimcu_describe_collision_map_from_config(const clsimcu_config *config, int32_t pixel_budget, char *buf, size_t cap, size_t *needed)
+{
+    if (!config) return fail(CLSIMCU_ERR_INVALID, "config is NULL");
+    if (config->struct_size != static_cast<int32_t>(sizeof(clsimcu_config)))
+        return fail(CLSIMCU_ERR_INVALID, "clsimcu_config.struct_size does not match this library");
+    if (pixel_budget < 1) return fail(CLSIMCU_ERR_INVALID, "pixel_budget must be positive");
+    try {
+        SceneTables t;
+        build_scene_tables(*config, t);
+        if (!t.has_geometry) return fail(CLSIMCU_ERR_INVALID, "the configuration has no geometry");
+        return copy_text(describe_collision_map(t.geometry, build_collision_map(t.geometry, pixel_budget)), buf, cap, needed);
     } catch (const std::exception &ex) {
         return fail(CLSIMCU_ERR_INVALID, ex.what());
     }

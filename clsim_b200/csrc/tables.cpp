@@ -755,6 +755,79 @@ void safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *out, const std:
     std::copy(g_primes.begin() + first, g_primes.begin() + need, out);
 }
 
+// ------------------------------------------------------------------ collision map of the fast kernel
+CollisionMap build_collision_map(const GeometryTables &g, int pixel_budget)
+{
+    if (g.num_strings < 1) throw std::runtime_error("collision map: no strings");
+    CollisionMap m;
+    float xlo = g.string_x[0], xhi = g.string_x[0], ylo = g.string_y[0], yhi = g.string_y[0];
+    for (int i = 0; i < g.num_strings; ++i) {
+        xlo = std::min(xlo, g.string_x[i]); xhi = std::max(xhi, g.string_x[i]);
+        ylo = std::min(ylo, g.string_y[i]); yhi = std::max(yhi, g.string_y[i]);
+    }
+    // one pixel of margin is enough: a point outside the map is farther from every string
+    // than its projection onto the map, so the border pixels' bounds hold for it
+    float pixel = 4.f;
+    for (;;) {
+        const double w = (xhi - xlo) + 2.0 * pixel, h = (yhi - ylo) + 2.0 * pixel;
+        if (std::ceil(w / pixel) * std::ceil(h / pixel) <= static_cast<double>(pixel_budget)) break;
+        pixel *= 1.05f;
+    }
+    m.pixel = pixel;
+    m.x0 = xlo - pixel;
+    m.y0 = ylo - pixel;
+    m.inv_pixel = 1.f / pixel;
+    m.off_x = -m.x0 * m.inv_pixel;
+    m.off_y = -m.y0 * m.inv_pixel;
+    m.nx = static_cast<int>(std::ceil((xhi - xlo + 2 * pixel) / pixel));
+    m.ny = static_cast<int>(std::ceil((yhi - ylo + 2 * pixel) / pixel));
+    const double half_diag = 0.5 * std::sqrt(2.0) * pixel + 1e-2; // + slack for fp32 pixel assignment
+    const double min_range = 1.0; // below this the map cannot limit flights sensibly: cell walk
+    m.info.resize(static_cast<size_t>(m.nx) * m.ny);
+    for (int iy = 0; iy < m.ny; ++iy) {
+        for (int ix = 0; ix < m.nx; ++ix) {
+            const double cx = m.x0 + (ix + 0.5) * pixel, cy = m.y0 + (iy + 0.5) * pixel;
+            double best = 1e30, second = 1e30;
+            int who = 0;
+            for (int k = 0; k < g.num_strings; ++k) {
+                const double d = std::hypot(cx - g.string_x[k], cy - g.string_y[k]);
+                if (d < best) { second = best; best = d; who = k; }
+                else if (d < second) second = d;
+            }
+            // how far a photon anywhere in this pixel may fly before a string other than
+            // `who` can come within the collision radius
+            double range = std::min(second, 1e9) - half_diag - g.string_max_radius - 1e-2;
+            const float rf = static_cast<float>(range);
+            uint32_t bits;
+            std::memcpy(&bits, &rf, 4);
+            bits &= 0xffff0000u; // truncation of a positive float rounds down: the bound stays a lower bound
+            uint32_t low = static_cast<uint32_t>(who) << 4; // byte offset of the string's 16-byte record
+            if (range < min_range) {
+                // strings too dense for the pixel size: no range (+inf) and no string (the record behind the
+                // last one, which the kernel fills with NaN): every leg takes the reference's cell walk
+                bits = 0x7f800000u;
+                low = static_cast<uint32_t>(g.num_strings) << 4;
+            }
+            m.info[static_cast<size_t>(iy) * m.nx + ix] = low | bits;
+        }
+    }
+    return m;
+}
+
+std::string describe_collision_map(const GeometryTables &g, const CollisionMap &m)
+{
+    std::ostringstream o;
+    o.precision(9);
+    o << "{\"nx\":" << m.nx << ",\"ny\":" << m.ny << ",\"x0\":" << m.x0 << ",\"y0\":" << m.y0 << ",\"pixel\":" << m.pixel
+      << ",\"inv_pixel\":" << m.inv_pixel << ",\"off_x\":" << m.off_x << ",\"off_y\":" << m.off_y
+      << ",\"num_strings\":" << g.num_strings << ",\"string_max_radius\":" << g.string_max_radius;
+    o << ",\"string_pos_x\":"; put_floats(o, g.string_x);
+    o << ",\"string_pos_y\":"; put_floats(o, g.string_y);
+    o << ",\"info\":"; put_ints(o, m.info);
+    o << "}";
+    return o.str();
+}
+
 void seed_rng_states(uint64_t seed, const uint32_t *a, uint64_t *x, size_t n)
 {
     // splitmix64 stands in for I3RandomService::Integer(0xffffffff); the acceptance rule is the

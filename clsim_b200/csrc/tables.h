@@ -100,6 +100,17 @@ void build_scene_tables(const clsimcu_config &config, SceneTables &out);
 // JSON text, same schema as the oracle's, for table parity tests.
 std::string describe_scene_tables(const SceneTables &tables);
 
+// xy pixel map of the fast kernel's collision pre-test (device_scene.h, DevGeometry::near_info): per pixel the byte
+// offset of the nearest string's 16-byte record (low 16 bits) and the pixel's RANGE as the upper 16 bits of an fp32,
+// rounded down.  Host code, no GPU needed: the engine uploads it, the CPU tests check its guarantees.
+struct CollisionMap {
+    int nx = 0, ny = 0;
+    float x0 = 0.f, y0 = 0.f, pixel = 0.f, inv_pixel = 0.f, off_x = 0.f, off_y = 0.f;
+    std::vector<uint32_t> info;
+};
+CollisionMap build_collision_map(const GeometryTables &g, int pixel_budget);
+std::string describe_collision_map(const GeometryTables &g, const CollisionMap &m);
+
 // Safe-prime MWC multipliers, rows [first, first+n) of the descending sequence from
 // 4294967118 (private/make_safeprimes/main.cxx:32-104).  Multi-threaded; memoised on disk in
 // the reference's binary "safeprimes_base32" format when cache_path is non-empty

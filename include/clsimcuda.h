@@ -278,6 +278,12 @@ int clsimcu_describe_tables(clsimcu_engine *engine, char *buf, size_t cap, size_
 /* Table building without a GPU (host only): same JSON as above. */
 int clsimcu_describe_tables_from_config(const clsimcu_config *config, char *buf, size_t cap, size_t *needed);
 
+/* The fast kernel's xy collision map for a given pixel budget (host only, no GPU needed), as a JSON text: per pixel
+ * the nearest string (16 x its index, low 16 bits) and the range within which no other string can be touched (upper 16
+ * bits of an fp32).  No counterpart in the reference (its cell grids, sparse_collision_kernel.c.cl:194-460, are what
+ * the map prunes); exported so that the guarantees the kernel relies on can be tested without a device. */
+int clsimcu_describe_collision_map_from_config(const clsimcu_config *config, int32_t pixel_budget, char *buf, size_t cap, size_t *needed);
+
 /* Safe-prime MWC multipliers (private/make_safeprimes/main.cxx:32-104): writes the
  * rows [first, first+n) of the descending sequence that starts at 4294967118. */
 int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
