@@ -74,6 +74,45 @@ def test_ic86_like_detector(budget):
     assert np.all(d.argmin(axis=2)[named] == who[named])
 
 
+def test_legs_flown_on_clearance_stay_clear_of_every_string():
+    """kernel_fast.cu advance_photon: the leg that looks at the map leaves the lane a clearance,
+    min(distance to the named string's axis - R, range) - 1 cm; the legs after it fly without map or test as long as
+    their summed length stays below it.  Restated in numpy: random walks started anywhere, three legs per look."""
+    sc = make_scene("spice_mie")
+    m = capi.describe_collision_map(sc.medium, sc.geo, sc.generators, sc.bias, sc.options(), pixel_budget=11000)
+    who, rng, bits = decode(m)
+    sx, sy = np.asarray(m["string_pos_x"]), np.asarray(m["string_pos_y"])
+    R = m["string_max_radius"]
+    r = np.random.default_rng(11)
+    n = 100000
+    x = r.uniform(m["x0"], m["x0"] + m["nx"] * m["pixel"], n)
+    y = r.uniform(m["y0"], m["y0"] + m["ny"] * m["pixel"], n)
+    px, py = pixel_of(m, x, y)
+    w, rg = who[py, px], rng[py, px].astype(np.float64)
+    assert np.all(bits[py, px] != np.uint32(0x7f800000))
+    clearance = np.minimum(np.hypot(sx[w] - x, sy[w] - y) - R, rg) - 0.01
+    flown = np.zeros(n)
+    flew = 0
+    for leg in range(3):
+        length = r.exponential(4.0, n)                       # metres; clear ice has legs this long
+        phi = r.uniform(0, 2 * np.pi, n)
+        sin_theta = np.sqrt(1 - r.uniform(-1, 1, n) ** 2)    # the xy projection of an isotropic direction
+        ok = length < clearance - flown if leg > 0 else np.ones(n, dtype=bool)   # the first leg is tested by the kernel itself
+        if leg > 0:
+            # closest approach of the leg's xy projection to every string axis
+            dx, dy = np.cos(phi) * sin_theta, np.sin(phi) * sin_theta
+            t = np.clip(((sx[None, :] - x[:, None]) * dx[:, None] + (sy[None, :] - y[:, None]) * dy[:, None])
+                        / np.maximum(dx * dx + dy * dy, 1e-30)[:, None], 0.0, length[:, None])
+            dist = np.hypot(x[:, None] + t * dx[:, None] - sx[None, :], y[:, None] + t * dy[:, None] - sy[None, :])
+            assert np.all(dist[ok].min(axis=1) > R)
+            flew += int(ok.sum())
+        else:
+            dx, dy = np.cos(phi) * sin_theta, np.sin(phi) * sin_theta
+        step = np.where(ok, length, 0.0)                      # a lane without clearance waits
+        x, y, flown = x + step * dx, y + step * dy, flown + step
+    assert flew > 1.5 * n                                     # most legs do fly on clearance
+
+
 def test_dense_cluster_has_pixels_without_a_range():
     sc = make_scene("homogeneous", geo_kind="ring")
     ring = sc.geo
