@@ -17,9 +17,10 @@ photons = 2.1e8 photons per bunch and GPU.
              (155 per segment + 120 per photon, the reference formulation's count) per second
              against SMs x 128 lanes x clock.  HBM figures for the hit stream are attached to
              show that memory is not the bound.
-* cpu_baseline : the oracle (CPU restatement of the reference kernel, "port" -- POCL/OpenCL
-             does not exist in this image) on all host cores, on a bounded sample of the same
-             workload.  --impl reference times exactly that as its own arm.
+* cpu_baseline : the reference's own kernel text compiled for the host (oracle/_ref, kind
+             "reference"; POCL/OpenCL does not exist in this image) -- or, where that library was not
+             built, the oracle restatement (kind "port") -- on all host cores, on a bounded sample of
+             the same workload.  --impl reference times exactly that as its own arm.
 
 Multi-GPU (--gpus N under torchrun): weak scaling, every rank propagates its own bunch on
 its own GPU with its own slice of the MWC multiplier table; there is no collective on the
@@ -130,20 +131,44 @@ def make_bunch(n, seed):
     return steps.muon_track_steps(n, photons_per_step=PHOTONS_PER_STEP, seed=seed)
 
 
-def oracle_rate(scene, sample_steps, seed, threads):
-    """photons/s of the CPU oracle on `sample_steps` steps of the workload."""
-    from clsim_b200.description import ConverterOptions
-    from oracle import pyoracle
-    medium, geo, gens, bias = scene
-    opt = ConverterOptions(stop_detected_photons=True, pancake_factor=5.0)
-    osc = pyoracle.Scene(medium, geo, gens, bias, opt)
-    bunch = make_bunch(sample_steps, seed)
-    a, _, _ = pyoracle.safeprimes(0, sample_steps)
-    x = pyoracle.seed_states(seed, a)
-    t0 = time.perf_counter()
-    _, hits, st, _, _ = osc.propagate(bunch, x, a, cap=max(1000, 10 * sample_steps), num_threads=threads)
-    dt = time.perf_counter() - t0
-    return st["photons"] / dt, dt, st, hits
+class CpuArm(object):
+    """The reference's implementation of the path on the host cores.  kind "reference": the reference's own kernel
+    text (resources/kernels/*.cl) compiled for the host under oracle/ref_shim (oracle/_ref/libclsim_ref.so, built
+    where /root/reference exists and shipped prebuilt); kind "port": the oracle restatement, when that library is
+    absent.  The scene and the MWC multipliers are built ONCE; each run() times one launch over `sample_steps`
+    work-items (one per step, like an OpenCL CPU device) on all host threads."""
+
+    def __init__(self, scene, max_steps, threads):
+        from clsim_b200.description import ConverterOptions
+        from oracle import pyoracle
+        self.threads = threads
+        medium, geo, gens, bias = scene
+        opt = ConverterOptions(stop_detected_photons=True, pancake_factor=5.0)
+        if pyoracle.ref_available():
+            self.kind = "reference"
+            self.scene = pyoracle.RefScene(medium, geo, gens, bias, opt)
+            self.flags = "g++ -O3 -ffp-contract=off -fopenmp (no -march=native: the .so is built off-box), glibc libm; kernel text of the reference under a C++ shim for OpenCL C, variant %s" % self.scene.variant()
+        else:
+            self.kind = "port"
+            self.scene = pyoracle.Scene(medium, geo, gens, bias, opt)
+            self.flags = "g++ -O3 -ffp-contract=off -fopenmp (no -march=native), glibc libm; oracle restatement"
+        self.a, _, _ = pyoracle.safeprimes(0, max_steps)
+        self.max_steps = max_steps
+        self._seed_states = pyoracle.seed_states
+
+    def run(self, sample_steps, seed):
+        """-> (photons/s, seconds, photons, hits)"""
+        n = min(sample_steps, self.max_steps)
+        bunch = make_bunch(n, seed)
+        x = self._seed_states(seed, self.a[:n])
+        photons = int(bunch["num_photons"].sum())
+        t0 = time.perf_counter()
+        out = self.scene.propagate(bunch, x, self.a[:n], cap=max(1000, 10 * n), num_threads=self.threads)
+        dt = time.perf_counter() - t0
+        return photons / dt, dt, photons, int(out[1])
+
+    def describe(self, value, sample):
+        return {"value": value, "unit": "photons/s", "cores": self.threads, "kind": self.kind, "sample": sample, "flags": self.flags}
 
 
 def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, sum_over_ranks):
@@ -194,32 +219,33 @@ def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, 
 
 
 def run_reference_arm(args):
-    """The reference's own implementation of the path on the host cores: the oracle ("port";
-    the OpenCL reference cannot be built or run here)."""
+    """The reference's own implementation of the path on the host cores (CpuArm: oracle/_ref when it was built, else
+    the oracle port; OpenCL itself cannot run in this image)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    scene = build_scene()
-    sample = 1 << 14
-    rate, dt, _, _ = oracle_rate(scene, sample, 100, threads)  # calibration + warm caches
-    # size each step to about 4 s of CPU work, bounded
-    per_step = int(min(1 << 18, max(1 << 12, rate * 4.0 / PHOTONS_PER_STEP)))
+    t_start = time.perf_counter()
+    max_steps = 1 << 16
+    arm = CpuArm(build_scene(), max_steps, threads)
+    rate, _, _, _ = arm.run(1 << 12, 100)   # calibration (and first-touch of the thread pool)
+    # every timed step about 2.5 s of CPU work, bounded; warm-up steps an eighth of that
+    per_step = int(min(max_steps, max(1 << 11, rate * 2.5 / PHOTONS_PER_STEP)))
     for i in range(args.warmup):
-        oracle_rate(scene, max(1 << 10, per_step // 8), 200 + i, threads)
+        arm.run(max(1 << 10, per_step // 8), 200 + i)
     t_total, photons = 0.0, 0
     for i in range(args.steps):
-        r, dt, st, _ = oracle_rate(scene, per_step, 300 + i, threads)
+        _, dt, n_photons, _ = arm.run(per_step, 300 + i)
         t_total += dt
-        photons += st["photons"]
+        photons += n_photons
     value = photons / t_total
+    sample = "%d steps x %d photons per timed step (bounded sample of the bunch), %d timed steps" % (per_step, PHOTONS_PER_STEP, args.steps)
     line = {
         "impl": "reference", "metric": "photons propagated/sec", "value": value, "unit": "photons/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": "%d steps x %d photons per timed step (bounded sample of the bunch)" % (per_step, PHOTONS_PER_STEP)},
-        "cpu_baseline": {"value": value, "unit": "photons/s", "cores": threads, "kind": "port",
-                         "sample": "%d steps x %d photons per timed step, %d steps" % (per_step, PHOTONS_PER_STEP, args.steps)},
+        "config": {"workload": WORKLOAD, "sample": sample, "wall_s": time.perf_counter() - t_start},
+        "cpu_baseline": arm.describe(value, sample),
         "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -382,11 +408,11 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        rate0, _, _, _ = oracle_rate(scene, 1 << 13, 77, threads)
-        sample = int(min(1 << 19, max(1 << 13, rate0 * 12.0 / PHOTONS_PER_STEP)))
-        rate, dt, st, _ = oracle_rate(scene, sample, 78, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": "photons/s", "cores": threads, "kind": "port",
-                                "sample": "%d steps x %d photons of the same workload, %.1f s" % (sample, PHOTONS_PER_STEP, dt)}
+        arm = CpuArm(scene, 1 << 17, threads)
+        rate0, _, _, _ = arm.run(1 << 12, 77)
+        sample = int(min(1 << 17, max(1 << 12, rate0 * 12.0 / PHOTONS_PER_STEP)))   # about 12 s of CPU work
+        rate, dt, _, _ = arm.run(sample, 78)
+        line["cpu_baseline"] = arm.describe(rate, "%d steps x %d photons of the same workload, %.1f s" % (sample, PHOTONS_PER_STEP, dt))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

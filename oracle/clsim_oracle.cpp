@@ -1756,24 +1756,36 @@ void oracle_rng_uniform_co(uint64_t *x, uint32_t a, float *out, size_t n)
 
 int oracle_safeprimes(uint64_t first, uint64_t n, uint32_t *a_out, uint64_t *n2_out, uint64_t *n1_out)
 {
-    uint64_t a = 4294967118ull; // make_safeprimes/main.cxx:59
+    // make_safeprimes/main.cxx:59-104 descends one candidate at a time; the test of a candidate does not depend on the
+    // others, so blocks of candidates are tested in parallel and their survivors appended in descending order: the
+    // same rows, found on all host cores.
+    uint64_t a = 4294967118ull;
     uint64_t row = 0, written = 0;
+    const uint64_t block = 1u << 18;
+    std::vector<uint8_t> keep(block);
     while (written < n) {
         if (a == 0) { g_last_error = "ran out of multiplier candidates"; return -1; }
-        const uint64_t n2 = (a << 32) - 1;
-        if (is_prime_u64(n2)) {
-            const uint64_t n1 = (n2 - 1) >> 1;
-            if (is_prime_u64(n1)) {
-                if (row >= first) {
-                    a_out[written] = static_cast<uint32_t>(a);
-                    if (n2_out) n2_out[written] = n2;
-                    if (n1_out) n1_out[written] = n1;
-                    ++written;
-                }
-                ++row;
-            }
+        const uint64_t count = std::min<uint64_t>(block, a);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1024)
+#endif
+        for (long long k = 0; k < static_cast<long long>(count); ++k) {
+            const uint64_t cand = a - static_cast<uint64_t>(k);
+            const uint64_t n2 = (cand << 32) - 1;
+            keep[k] = (is_prime_u64(n2) && is_prime_u64((n2 - 1) >> 1)) ? 1 : 0;
         }
-        --a;
+        for (uint64_t k = 0; k < count && written < n; ++k) {
+            if (!keep[k]) continue;
+            if (row >= first) {
+                const uint64_t cand = a - k, n2 = (cand << 32) - 1;
+                a_out[written] = static_cast<uint32_t>(cand);
+                if (n2_out) n2_out[written] = n2;
+                if (n1_out) n1_out[written] = (n2 - 1) >> 1;
+                ++written;
+            }
+            ++row;
+        }
+        a -= count;
     }
     return 0;
 }

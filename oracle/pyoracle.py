@@ -197,3 +197,86 @@ class Scene(object):
         xs = C.c_uint64(int(x))
         lib().oracle_sample(self._h, which, C.byref(xs), int(a), out.ctypes.data, n)
         return out, xs.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own propKernel text compiled for the host (oracle/ref_shim/).  Exists only where
+# the library was built, i.e. in a container that holds /root/reference (the built .so travels to the GPU box).
+# ---------------------------------------------------------------------------------------------------------
+_REF_LIB = os.path.join(_HERE, "_ref", "libclsim_ref.so")
+_ref_lib = None
+
+
+def ref_available():
+    return os.path.isfile(_REF_LIB)
+
+
+def ref_lib():
+    global _ref_lib
+    if _ref_lib is None:
+        L = C.CDLL(_REF_LIB)
+        L.oracle_last_error.restype = C.c_char_p
+        L.oracle_scene_create.restype = C.c_void_p
+        L.oracle_scene_create.argtypes = [C.POINTER(ConfigStruct)]
+        L.oracle_scene_destroy.argtypes = [C.c_void_p]
+        L.oracle_propagate.restype = C.c_uint64
+        L.oracle_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_variant_name.restype = C.c_char_p
+        L.ref_variant_name.argtypes = [C.c_void_p, C.c_int]
+        L.ref_propagate.restype = C.c_uint64
+        L.ref_propagate.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.c_int, C.c_int]
+        _ref_lib = L
+    return _ref_lib
+
+
+class RefScene(object):
+    """A scene inside oracle/_ref/libclsim_ref.so: propagate() runs the REFERENCE's kernel text, oracle_propagate()
+    the hand-written restatement compiled into the same library (the same code as libclsim_oracle.so)."""
+
+    def __init__(self, medium, geometry, wlen_generators, wlen_bias, options):
+        self._cfg, self._keep = build_config(medium, geometry, wlen_generators, wlen_bias, options)
+        self.history_entries = int(options.photon_history_entries)
+        self.with_flasher = len(wlen_generators) > 1   # the reference passes -DNO_FLASHER for a single generator (…OpenCL.cxx:648-649)
+        self._h = ref_lib().oracle_scene_create(C.byref(self._cfg))
+        if not self._h:
+            raise RuntimeError(ref_lib().oracle_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            ref_lib().oracle_scene_destroy(self._h)
+            self._h = None
+
+    def variant(self):
+        v = ref_lib().ref_variant_name(self._h, int(self.with_flasher))
+        return v.decode() if v else None
+
+    def _run(self, which, steps, rng_x, rng_a, cap, num_threads):
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        n = len(steps)
+        x = np.array(rng_x[:n], dtype=np.uint64, copy=True)
+        a = np.ascontiguousarray(rng_a[:n], dtype=np.uint32)
+        if cap is None:
+            cap = max(1000, 10 * n)
+        out = np.zeros(cap, dtype=PHOTON_DTYPE)
+        hist = np.zeros((cap, self.history_entries, 4), dtype=np.float32) if self.history_entries else None
+        hp = hist.ctypes.data if hist is not None else None
+        if which == "ref":
+            cnt = ref_lib().ref_propagate(self._h, steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, out.ctypes.data, cap, hp,
+                                          int(self.with_flasher), int(num_threads))
+            if cnt == 2 ** 64 - 1:
+                raise RuntimeError(ref_lib().oracle_last_error().decode())
+        else:
+            stats = np.zeros(4, dtype=np.uint64)
+            cnt = ref_lib().oracle_propagate(self._h, steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, out.ctypes.data, cap, hp,
+                                             int(num_threads), stats.ctypes.data)
+        k = min(int(cnt), cap)
+        return out[:k], int(cnt), x, (hist[:k] if hist is not None else None)
+
+    def propagate(self, steps, rng_x, rng_a, cap=None, num_threads=1):
+        """The reference's kernel text -> (photons, hits counted, new rng_x, history or None)"""
+        return self._run("ref", steps, rng_x, rng_a, cap, num_threads)
+
+    def oracle_propagate(self, steps, rng_x, rng_a, cap=None, num_threads=1):
+        return self._run("oracle", steps, rng_x, rng_a, cap, num_threads)
