@@ -74,6 +74,15 @@ struct CudaError : std::runtime_error {
     explicit CudaError(const std::string &m) : std::runtime_error(m) {}
 };
 
+// launch_*_kernel: 0 ok, -1 bunch too large for the fast kernel's step index, -2 unsupported option, -3 CUDA error
+// (left in place by the launcher: cudaPeekAtLastError, so that its text can be read here)
+static std::string launch_error_text(int rc)
+{
+    if (rc == -1) return "kernel launch failed: more steps in one bunch than the fast kernel's birth tag can index";
+    if (rc == -2) return "kernel launch failed: option not supported by this kernel (photon history longer than 32 entries)";
+    return std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError());
+}
+
 #define CUDA_OK(call)                                                                                         \
     do {                                                                                                      \
         cudaError_t e__ = (call);                                                                             \
@@ -452,7 +461,7 @@ void launch(clsimcu_engine &e, const LaunchArgs &args, cudaStream_t stream)
     int rc;
     if (e.kernel_mode == CLSIMCU_KERNEL_REFERENCE) rc = launch_reference_kernel(e.scene, args, stream);
     else rc = launch_fast_kernel(e.scene, args, e.fast_blocks, stream);
-    if (rc != 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (rc != 0) throw CudaError(launch_error_text(rc));
 }
 
 void submit_loop(clsimcu_engine *e)
@@ -651,7 +660,7 @@ std::string engine_launch_tabulate(clsimcu_engine *e, const clsimcu_step *steps,
         a.rng_a = e->d_rng_a;
         a.scene_dev = e->d_scene;
         a.tabulate = d_tab;
-        if (launch_reference_kernel(e->scene, a, e->compute) != 0) throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (const int rc = launch_reference_kernel(e->scene, a, e->compute)) throw CudaError(launch_error_text(rc));
     } catch (const std::exception &ex) {
         return ex.what();
     }
@@ -1086,7 +1095,8 @@ int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint6
                          e->h_res_stats[5], e->h_res_stats[6], e->h_res_stats[7]);
         for (auto &x : ev) cudaEventDestroy(x);
         if (kernel_ms) *kernel_ms = ms;
-        if (photons_generated) *photons_generated = e->res_generated_per_run * static_cast<uint64_t>(repeat);
+        // photons CREATED, as counted by the kernel itself (stats[0]) -- not the host's sum over the step records
+        if (photons_generated) *photons_generated = e->h_res_stats[0];
         if (hits_counted) *hits_counted = hits;
         if (segments) *segments = segs;
     } catch (const std::exception &ex) {

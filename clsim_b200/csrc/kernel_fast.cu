@@ -1392,13 +1392,11 @@ int launch_mix(const DevScene &scene, const LaunchArgs &args, int blocks, cudaSt
 {
     const SmemLayout lay = plan_smem(scene);
     auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL, MIXED>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)) != cudaSuccess) return -3;
-        configured = true;
-    }
+    // the attribute belongs to the (function, device) pair and engines on several devices launch from several threads
+    // of one process: set it on every launch (a host-side table write, no device work)
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)) != cudaSuccess) return -3;
     kernel<<<blocks, kThreads, lay.total, stream>>>(scene, args, lay);
-    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;   // (peek: the caller reads the error text)
 }
 
 template <bool TILT, bool ANISO, bool SAVE_ALL>

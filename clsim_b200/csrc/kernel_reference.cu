@@ -677,7 +677,7 @@ int launch_reference_kernel(const DevScene &scene, const LaunchArgs &args, void 
     const int threads = 64;
     const unsigned blocks = (args.num_steps + threads - 1) / threads;
     propagate_reference_order<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(scene, args);
-    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -3;   // (peek: the caller reads the error text)
 }
 
 } // namespace clsimcu

@@ -190,6 +190,10 @@ struct clsimcu_mcpe_converter {
     int blocks = 0;
     cudaStream_t stream = nullptr;
     std::mutex mutex;
+    // every launch reads and writes the object's MWC rows: launches from different streams (the object's own, and the
+    // compute stream of the engine it is attached to) are chained through this event, under launch_mutex
+    std::mutex launch_mutex;
+    cudaEvent_t last_use = nullptr;
 };
 
 namespace clsimcu {
@@ -198,8 +202,11 @@ int mcpe_device(const clsimcu_mcpe_converter *c) { return c->device; }
 
 void mcpe_enqueue(clsimcu_mcpe_converter *c, const McpeLaunch &l, cudaStream_t stream)
 {
+    std::lock_guard<std::mutex> lk(c->launch_mutex);
+    if (c->last_use) CUDA_OK(cudaStreamWaitEvent(stream, c->last_use, 0));
     photons_to_mcpe<<<c->blocks, kThreadsPerBlock, 0, stream>>>(c->dev, l, c->d_rng_x, c->d_rng_a);
     CUDA_OK(cudaGetLastError());
+    if (c->last_use) CUDA_OK(cudaEventRecord(c->last_use, stream));
 }
 
 std::string mcpe_error_text(const clsimcu_mcpe_converter *c, const uint32_t *k)
@@ -224,6 +231,7 @@ void free_converter(clsimcu_mcpe_converter *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaFree(c->d_tables);
+    if (c->last_use) cudaEventDestroy(c->last_use);
     cudaFree(c->d_rng_x);
     cudaFree(c->d_rng_a);
     delete c;
@@ -338,6 +346,7 @@ int clsimcu_mcpe_create(const clsimcu_mcpe_config *cfg, clsimcu_mcpe_converter *
         CUDA_OK(cudaMalloc(&c->d_rng_x, c->streams * sizeof(uint64_t)));
         CUDA_OK(cudaMalloc(&c->d_rng_a, c->streams * sizeof(uint32_t)));
         CUDA_OK(cudaMemcpy(c->d_rng_x, x.data(), c->streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
         CUDA_OK(cudaMemcpy(c->d_rng_a, a.data(), c->streams * sizeof(uint32_t), cudaMemcpyHostToDevice));
     } catch (const std::invalid_argument &ex) {
         free_converter(c);

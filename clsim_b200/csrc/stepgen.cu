@@ -188,6 +188,10 @@ struct clsimcu_step_generator {
     int blocks = 0;
     cudaStream_t stream = nullptr;
     std::mutex mutex;
+    // every launch reads and writes the object's MWC rows: launches from different streams (the object's own, and the
+    // compute stream of the engine it is attached to) are chained through this event, under launch_mutex
+    std::mutex launch_mutex;
+    cudaEvent_t last_use = nullptr;
 };
 
 namespace clsimcu {
@@ -197,8 +201,11 @@ int stepgen_device(const clsimcu_step_generator *g) { return g->device; }
 void stepgen_enqueue(clsimcu_step_generator *g, const StepGenLaunch &l, cudaStream_t stream)
 {
     if (l.total == 0) return;
+    std::lock_guard<std::mutex> lk(g->launch_mutex);
+    if (g->last_use) CUDA_OK(cudaStreamWaitEvent(stream, g->last_use, 0));
     make_steps<<<g->blocks, kThreadsPerBlock, 0, stream>>>(g->dev, l, g->d_rng_x, g->d_rng_a);
     CUDA_OK(cudaGetLastError());
+    if (g->last_use) CUDA_OK(cudaEventRecord(g->last_use, stream));
 }
 
 // Validates n queue entries and lays their steps out: first_step[i] = index of entry i's first step,
@@ -236,6 +243,7 @@ void free_generator(clsimcu_step_generator *g)
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->last_use) cudaEventDestroy(g->last_use);
     cudaFree(g->d_rng_x);
     cudaFree(g->d_rng_a);
     delete g;
@@ -276,6 +284,7 @@ int clsimcu_stepgen_create(const clsimcu_step_generator_config *cfg, clsimcu_ste
         CUDA_OK(cudaMalloc(&g->d_rng_x, g->streams * sizeof(uint64_t)));
         CUDA_OK(cudaMalloc(&g->d_rng_a, g->streams * sizeof(uint32_t)));
         CUDA_OK(cudaMemcpy(g->d_rng_x, x.data(), g->streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaEventCreateWithFlags(&g->last_use, cudaEventDisableTiming));
         CUDA_OK(cudaMemcpy(g->d_rng_a, a.data(), g->streams * sizeof(uint32_t), cudaMemcpyHostToDevice));
     } catch (const std::exception &ex) {
         free_generator(g);

@@ -505,6 +505,7 @@ void build_scene_tables(const clsimcu_config &c, SceneTables &out)
     if (c.save_all_photons && c.stop_detected_photons)
         throw std::runtime_error("Internal error: both the saveAllPhotons and stopDetectedPhotons options are set at the same time.");
     if (c.photon_history_entries < 0) throw std::runtime_error("photon_history_entries must not be negative");
+    if (c.photon_history_entries > 32) throw std::runtime_error("photon_history_entries: at most 32 scatter points per photon are kept on the device");
     make_medium(c.medium, out.medium);
     out.generators.clear();
     for (int i = 0; i < c.num_wlen_generators; ++i) out.generators.push_back(make_generator(c.wlen_generators[i]));

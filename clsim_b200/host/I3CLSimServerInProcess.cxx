@@ -8,6 +8,7 @@ struct I3CLSimServerInProcess::Mailbox {
     std::mutex mutex;
     std::condition_variable ready;
     std::deque<I3CLSimStepToPhotonConverter::ConversionResult_t> results;
+    std::string failure;   // set when the server failed while this client was waiting
 };
 
 namespace {
@@ -57,6 +58,7 @@ void I3CLSimServerInProcess::Submit(const std::shared_ptr<Mailbox> &from, I3CLSi
     {
         std::lock_guard<std::mutex> lock(mutex_);
         if (shutdown_) throw std::runtime_error("I3CLSimServerInProcess is shutting down");
+        if (!failure_.empty()) throw std::runtime_error("I3CLSimServerInProcess: a converter failed: " + failure_);
         // assign an internal ID for later reply to the client (I3CLSimServer.cxx:169-180)
         uint32_t internalId = 0;
         if (!clients_.empty()) internalId = (--clients_.end())->first + 1;
@@ -83,9 +85,12 @@ void I3CLSimServerInProcess::WorkerThread(unsigned index)
             converters_[index]->EnqueueSteps(task.steps, task.internalId);
             // next result, not necessarily from the batch just enqueued (I3CLSimServer.cxx:318-321)
             result = converters_[index]->GetConversionResult();
-        } catch (const std::exception &) {
-            // a failing converter must not strand the client: answer the bunch with an empty result
-            result = I3CLSimStepToPhotonConverter::ConversionResult_t(task.internalId);
+        } catch (const std::exception &e) {
+            // A converter error is fatal in the reference (the worker's exception ends the server process,
+            // I3CLSimServer.cxx:310-343): no result is made up.  The server is marked failed, every waiting client is
+            // woken, and Submit / GetConversionResult throw from then on.
+            Fail(e.what());
+            return;
         }
         std::shared_ptr<Mailbox> destination;
         {
@@ -102,6 +107,31 @@ void I3CLSimServerInProcess::WorkerThread(unsigned index)
         }
         destination->ready.notify_one();
     }
+}
+
+void I3CLSimServerInProcess::Fail(const std::string &what)
+{
+    std::vector<std::shared_ptr<Mailbox> > waiting;
+    {
+        std::lock_guard<std::mutex> lock(mutex_);
+        if (failure_.empty()) failure_ = what.empty() ? "unknown error" : what;
+        for (auto &c : clients_) waiting.push_back(c.second.first);
+        clients_.clear();
+        frontend_.clear();
+    }
+    for (auto &box : waiting) {
+        {
+            std::lock_guard<std::mutex> lock(box->mutex);
+            box->failure = failure_;
+        }
+        box->ready.notify_all();
+    }
+}
+
+std::string I3CLSimServerInProcess::Failure() const
+{
+    std::lock_guard<std::mutex> lock(mutex_);
+    return failure_;
 }
 
 std::map<std::string, double> I3CLSimServerInProcess::GetStatistics() const
@@ -130,7 +160,8 @@ I3CLSimStepToPhotonConverter::ConversionResult_t I3CLSimClientInProcess::GetConv
     I3CLSimStepToPhotonConverter::ConversionResult_t result;
     if (pending_ != 0) { // I3CLSimServer.cxx:394-419
         std::unique_lock<std::mutex> lock(mailbox_->mutex);
-        mailbox_->ready.wait(lock, [&] { return !mailbox_->results.empty(); });
+        mailbox_->ready.wait(lock, [&] { return !mailbox_->results.empty() || !mailbox_->failure.empty(); });
+        if (mailbox_->results.empty()) throw std::runtime_error("I3CLSimServerInProcess: a converter failed: " + mailbox_->failure);
         result = mailbox_->results.front();
         mailbox_->results.pop_front();
         pending_--;

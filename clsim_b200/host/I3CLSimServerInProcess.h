@@ -47,6 +47,8 @@ public:
     std::map<std::string, double> GetStatistics() const;
     std::size_t GetWorkgroupSize() const { return workgroupSize_; }
     std::size_t GetMaxNumWorkitems() const { return maxBunchSize_; }
+    // empty while every converter works; otherwise the first converter error (the server no longer accepts or answers work)
+    std::string Failure() const;
 
     // the "servus" handshake: a new client bound to this server
     std::shared_ptr<I3CLSimClientInProcess> Connect();
@@ -60,6 +62,7 @@ private:
     };
     void Submit(const std::shared_ptr<Mailbox> &from, I3CLSimStepSeriesConstPtr steps, uint32_t externalId);
     void WorkerThread(unsigned index);
+    void Fail(const std::string &what);
 
     std::vector<I3CLSimStepToPhotonConverterPtr> converters_;
     std::size_t workgroupSize_, maxBunchSize_;
@@ -69,6 +72,7 @@ private:
     std::deque<Task> frontend_;                                                      // bunches waiting for an idle worker
     std::map<uint32_t, std::pair<std::shared_ptr<Mailbox>, uint32_t> > clients_;     // internal id -> (origin, external id)
     bool shutdown_;
+    std::string failure_;
     std::vector<std::thread> workerThreads_;
 };
 

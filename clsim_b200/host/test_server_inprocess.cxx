@@ -183,6 +183,47 @@ static void test_with_dummy_converters()
     }
 }
 
+// A converter that fails must fail its clients, not hand them empty photon series (light would be lost silently).
+class FailingConverter : public DummyConverter {
+public:
+    explicit FailingConverter(int good) : DummyConverter(1, 64), good_(good) {}
+    void EnqueueSteps(I3CLSimStepSeriesConstPtr steps, uint32_t id) override
+    {
+        if (good_.fetch_sub(1) <= 0) throw I3CLSimStepToPhotonConverter_exception("device lost");
+        DummyConverter::EnqueueSteps(steps, id);
+    }
+
+private:
+    std::atomic<int> good_;
+};
+
+static void test_failing_converter_fails_the_clients()
+{
+    std::vector<I3CLSimStepToPhotonConverterPtr> converters(1, I3CLSimStepToPhotonConverterPtr(new FailingConverter(2)));
+    I3CLSimServerInProcess server(converters);
+    std::shared_ptr<I3CLSimClientInProcess> client = server.Connect();
+    int results = 0;
+    bool threw = false;
+    try {
+        for (uint32_t i = 0; i < 6; ++i) client->EnqueueSteps(make_steps(8, 10, 1, i), i);
+        for (uint32_t i = 0; i < 6; ++i) {
+            I3CLSimStepToPhotonConverter::ConversionResult_t res = client->GetConversionResult();
+            CHECK(res.photons && res.photons->size() == 8);   // a result that does arrive is a real one
+            ++results;
+        }
+    } catch (const std::runtime_error &e) {
+        threw = std::strstr(e.what(), "device lost") != nullptr;
+    }
+    CHECK(threw);
+    CHECK(results <= 2);
+    CHECK(server.Failure().find("device lost") != std::string::npos);
+    threw = false;
+    try {
+        client->EnqueueSteps(make_steps(8, 10, 1, 0), 99);
+    } catch (const std::runtime_error &) { threw = true; }
+    CHECK(threw);
+}
+
 static void test_with_cuda_converters(int want)
 {
     int devices = 0;
@@ -249,6 +290,7 @@ int main(int argc, char **argv)
 {
     try {
         test_with_dummy_converters();
+        test_failing_converter_fails_the_clients();
         if (argc > 1 && std::string(argv[1]) == "--gpu") test_with_cuda_converters(argc > 2 ? std::atoi(argv[2]) : 2);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "unexpected exception: %s\n", e.what());
