@@ -26,6 +26,7 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <limits>
 #include <mutex>
 #include <stdexcept>
 #include <string>

@@ -80,6 +80,9 @@ namespace {
 #ifndef CLSIMCU_REFILL_BATCH
 #define CLSIMCU_REFILL_BATCH 3
 #endif
+#ifndef CLSIMCU_WLEN_BIN_RECORDS
+#define CLSIMCU_WLEN_BIN_RECORDS 1  // A/B knob: generator 0's trapezoid inversion from per-bin records
+#endif
 constexpr int kThreads = CLSIMCU_THREADS;
 // legs a lane flies between two looks at the warp's state (ballots, refill decisions) in the hot loop
 constexpr int kHotUnroll = CLSIMCU_HOT_UNROLL;
@@ -174,6 +177,7 @@ __device__ __forceinline__ uint64_t pack64(float lo, float hi)
 struct SmemLayout {
     uint32_t off_layers, off_strings, off_sets, off_string_set, off_layer_to_dom, off_cells, off_near, off_tilt_dist, off_tilt_corr;
     uint32_t off_gen0;    // generator 0's cumulative | density | guide tables (gen0_n entries each, 64 guide bytes), see draw_wavelength
+    uint32_t off_gen0_bins; // ... and its per-bin inversion records (float4 + float2 per bin)
     uint32_t gen0_n;      // 0: not staged
     uint32_t off_state;   // per-thread arrays: state | birth tag | segment counter | propagation-stream tag (save-all only)
     uint32_t off_queue;   // per-warp arrays: photon queues | step records | control blocks
@@ -228,6 +232,8 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         s.generators[0].n >= 2 && s.generators[0].n <= kGen0MaxEntries) {
         L.gen0_n = static_cast<uint32_t>(s.generators[0].n);
         at = align16(at + 2 * L.gen0_n * 4 + kGen0Guide);
+        L.off_gen0_bins = at;
+        at = align16(at + (CLSIMCU_WLEN_BIN_RECORDS ? L.gen0_n * 24 : 0));
     }
     L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kPopTagWords : 0)) * kThreads * 4);
     L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
@@ -314,7 +320,7 @@ __device__ __forceinline__ float inv_group_velocity(const DevMedium &m, float wl
 // cumulative[k+1] >= r.  `staged` != nullptr: the generator's cumulative and density tables sit in shared memory
 // behind a guide table (guide[c] = the bin of r = c/64, a lower bound for every r in that cell), and the bin is found
 // by a forward scan of a step or two from there; otherwise by bisection over the tables in global memory.
-__device__ float draw_wavelength(const DevWlenGenerator &g, Mwc &rng, const float *staged = nullptr)
+__device__ float draw_wavelength(const DevWlenGenerator &g, Mwc &rng, const float *staged = nullptr, const float *bins = nullptr)
 {
     if (g.kind == CLSIMCU_WLEN_CONSTANT) return g.value;
     const float r = rng.oc();
@@ -326,6 +332,19 @@ __device__ float draw_wavelength(const DevWlenGenerator &g, Mwc &rng, const floa
         const uint8_t *guide = reinterpret_cast<const uint8_t *>(staged + 2 * g.n);
         k = guide[min(__float2int_rz(r * static_cast<float>(kGen0Guide)), kGen0Guide - 1)];
         while (k < g.n - 2 && cum[k + 1] < r) ++k;
+#if CLSIMCU_WLEN_BIN_RECORDS
+        if (bins) {
+            // the four cases of the reference's inversion (I3CLSimRandomValueInterpolatedDistribution.cxx:308-334) as
+            // ONE expression on per-bin constants made when the tables were staged:
+            //   x0 + (sqrt(dy c1 + c0) - c0) c2 + dy c3
+            // c0 = 1, c1 = 2 slope / b^2, c2 = b / slope in the general case; b == 0: c0 = 0, c1 = 2 / slope, c2 = 1;
+            // slope == 0: c3 = 1 / b, the rest 0; both 0: all 0
+            const float4 rec = reinterpret_cast<const float4 *>(bins)[k];
+            const float2 lin = reinterpret_cast<const float2 *>(bins + 4 * g.n)[k];
+            const float dy = r - rec.x;
+            return fmaf(dy, lin.y, fmaf(mufu_sqrt(fmaf(dy, rec.z, lin.x)) - lin.x, rec.w, rec.y));
+        }
+#endif
         below = (k == 0) ? 0.f : cum[k];
         b = dens[k];
         b_next = dens[k + 1];
@@ -541,7 +560,8 @@ __device__ __forceinline__ Born create_core(const DevScene *scene, const StepVie
     b.dir = s.axis;
     if (scene->num_generators <= 1 || s.source == 0) {
         const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
-        b.wlen = draw_wavelength(scene->generators[0], rng, lay.gen0_n ? reinterpret_cast<const float *>(smem_base() + lay.off_gen0) : nullptr);
+        b.wlen = draw_wavelength(scene->generators[0], rng, lay.gen0_n ? reinterpret_cast<const float *>(smem_base() + lay.off_gen0) : nullptr,
+                                 (CLSIMCU_WLEN_BIN_RECORDS && lay.gen0_n) ? reinterpret_cast<const float *>(smem_base() + lay.off_gen0_bins) : nullptr);
         const float cos_c = fminf(1.f, mufu_rcp(s.beta * phase_index(m, b.wlen)));
         const float sin_c = mufu_sqrt(1.f - cos_c * cos_c);
         rotate_by(cos_c, sin_c, b.dir, rng.co());
@@ -1271,6 +1291,28 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             cum[i] = __ldg(g0.cumulative + i);
             dens[i] = __ldg(g0.density + i);
         }
+#if CLSIMCU_WLEN_BIN_RECORDS
+        for (int k = tid; k < g0.n - 1; k += kThreads) {
+            float4 *rec = reinterpret_cast<float4 *>(smem + lay.off_gen0_bins);
+            float2 *lin = reinterpret_cast<float2 *>(rec + g0.n);
+            const float b = __ldg(g0.density + k), b_next = __ldg(g0.density + k + 1);
+            float x0, slope;
+            if (g0.kind == CLSIMCU_WLEN_INTERP_UNEQUAL) {
+                x0 = __ldg(g0.xs + k);
+                slope = (b_next - b) / (__ldg(g0.xs + k + 1) - x0);
+            } else {
+                x0 = static_cast<float>(k) * g0.dx + g0.x0;
+                slope = (b_next - b) / g0.dx;
+            }
+            const float below = (k == 0) ? 0.f : __ldg(g0.cumulative + k);
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            if (b == 0.f && slope != 0.f) { c1 = 2.f / slope; c2 = 1.f; }
+            else if (b != 0.f && slope == 0.f) { c3 = 1.f / b; }
+            else if (b != 0.f) { c0 = 1.f; c1 = (2.f * slope) / (b * b); c2 = b / slope; }
+            rec[k] = make_float4(below, x0, c1, c2);
+            lin[k] = make_float2(c0, c3);
+        }
+#endif
         if (tid < kGen0Guide) {
             // the bin of r = tid/64, by the reference's linear scan
             const float r = static_cast<float>(tid) * (1.f / static_cast<float>(kGen0Guide));
