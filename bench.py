@@ -218,6 +218,241 @@ def run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, 
     return out
 
 
+def roofline_frac(photons, segments, kernel_ms, sms, sm_mhz, gpus=1):
+    return ((segments * OPS_PER_SEGMENT + photons * OPS_PER_PHOTON) / (kernel_ms * 1e-3)) / (sms * 128 * sm_mhz * 1e6 * gpus)
+
+
+def run_other_configs(args, local, sms, sm_mhz):
+    """The single-GPU BASELINE configurations besides the headline one (resident bunch, kernel-only timing, the same
+    launch path and L2 flush as `value`): C1 point source in homogeneous ice at its stated size (1e6 photons: a
+    fraction of one wave of the persistent kernel) and filled up to 2^20 steps, C3's ice (SpiceLea + tilt +
+    anisotropy) under a muon bundle, C5 flasher at oversize 1.  N = 1 only."""
+    from clsim_b200 import capi, geometry, ice, steps
+    from clsim_b200.description import KERNEL_FAST, ConverterOptions
+    k = max(3, args.steps // 4)
+    out = {}
+
+    def one(name, workload, medium, geo, gens, bias, bunch, pancake):
+        opt = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=pancake, kernel_mode=KERNEL_FAST,
+                               max_num_workitems=len(bunch), rng_seed=777, rng_first_multiplier=0)
+        with capi.Engine(medium, geo, gens, bias, opt) as eng:
+            eng.upload_resident(bunch)
+            eng.run_resident(args.warmup)
+            r = eng.run_resident(k)
+        out[name] = {"workload": workload, "value": r["photons"] / (r["kernel_ms"] * 1e-3), "unit": "photons/s", "steps": k,
+                     "ms_per_step": r["kernel_ms"] / k, "hit_fraction": r["hits"] / float(max(1, r["photons"])),
+                     "segments_per_photon": r["segments"] / float(max(1, r["photons"])),
+                     "roofline_frac": roofline_frac(r["photons"], r["segments"], r["kernel_ms"], sms, sm_mhz)}
+
+    geo5 = geometry.make_ic86_like_geometry(oversize=5.0)
+    bias5 = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0)
+    hom = ice.MakeHomogeneousIceMediumProperties("spice_mie")
+    gen = [ice.makeCherenkovWavelengthGenerator(bias5, False, hom)]
+    one("config1", "point source at the origin, 5000 steps x 200 photons = 1e6 photons (the stated size), homogeneous bulk ice, IC86-like, oversize 5",
+        hom, geo5, gen, bias5, steps.point_source_steps(5000, 200, seed=1), 5.0)
+    one("config1_filled", "the same source, 2^20 steps x 200 photons (fills the device)", hom, geo5, gen, bias5,
+        steps.point_source_steps(1 << 20, 200, seed=1), 5.0)
+    lea = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_lea", useTiltIfAvailable=True)
+    gen = [ice.makeCherenkovWavelengthGenerator(bias5, False, lea)]
+    one("config3", "muon bundle (100 muons, 20 m spread), SpiceLea + tilt + anisotropy, IC86-like, oversize 5, 2^20 steps x 200 photons",
+        lea, geo5, gen, bias5, steps.muon_bundle_steps(1 << 20, num_muons=100, seed=3), 5.0)
+    geo1 = geometry.make_ic86_like_geometry(oversize=1.0)
+    bias1 = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS)
+    wl, val = ice.GetFlasherLED405Spectrum()
+    gens = [ice.makeCherenkovWavelengthGenerator(bias1, False, lea), ice.makeWavelengthGenerator(wl, val, bias1, lea)]
+    d2 = (geo1.posX - 0.0) ** 2 + (geo1.posY - 0.0) ** 2 + (geo1.posZ + 200.0) ** 2
+    i = int(np.argmin(d2))
+    dom = np.array([geo1.posX[i], geo1.posY[i], geo1.posZ[i]])
+    one("config5", "flasher LED (405 nm spectrum, sourceType 1) inside a DOM, SpiceLea + tilt + anisotropy, oversize 1 (no pancake), 2^20 steps x 200 photons",
+        lea, geo1, gens, bias1, steps.flasher_steps(1 << 20, dom, seed=5), 1.0)
+    return out
+
+
+def e2e_through_engine(eng, bunches, first_id=100):
+    """EnqueueSteps / GetConversionResult over a list of host bunches; -> (seconds, hits, results as (id, photons))."""
+    t0 = time.perf_counter()
+    pending, got = 0, []
+    for i, b in enumerate(bunches):
+        eng.enqueue(b, first_id + i)
+        pending += 1
+        while eng.more_photons_available():
+            r = eng.get_result()
+            got.append((r.identifier, r.photons))
+            pending -= 1
+    while pending:
+        r = eng.get_result()
+        got.append((r.identifier, r.photons))
+        pending -= 1
+    return time.perf_counter() - t0, got
+
+
+def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks):
+    """What the weak-scaling headline cannot show (every rank its own feeder, nothing shared):
+    (a) STRONG scaling: ONE fixed step series of config 3 (muon bundle, SpiceLea + tilt + anisotropy) split over the
+        ranks (sharding.split_steps), propagated end to end from host buffers, hit lists gathered on rank 0 and merged
+        by identifier (sharding.merge_results); time from the barrier to the merged result;
+    (b) ONE PROCESS, N devices: rank 0 alone drives one converter per GPU behind the in-process server with a single
+        feeder -- the reference's own topology (I3CLSimModule.cxx:611-638, I3CLSimServer.cxx:126-135) -- while the other
+        ranks wait on a CPU barrier (an NCCL barrier would sit on the SMs the persistent kernel needs);
+    (c) config 4 at its stated size: cascade steps made on the device, photo-electrons out, 1.25e10 propagated photons
+        per GPU (= the config's ~1e11 on eight)."""
+    import torch
+    from clsim_b200 import capi, geometry, ice, mcpe, stepgen, steps
+    from clsim_b200.converter import configureCUDADevices, initializeCUDA
+    from clsim_b200.description import KERNEL_FAST, ConverterOptions
+    from clsim_b200.server import I3CLSimServerInProcess
+    from clsim_b200.sharding import RNG_ROWS_PER_DEVICE, mcpe_row_offset, merge_results, rng_row_offset, split_steps, stepgen_row_offset
+    out = {}
+    lea = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_lea", useTiltIfAvailable=True)
+    geo = geometry.make_ic86_like_geometry(oversize=5.0)
+    bias = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0)
+    gens = [ice.makeCherenkovWavelengthGenerator(bias, False, lea)]
+    bunch_steps = args.bunch
+
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=gloo)
+
+    # ---------------- (a) strong scaling -------------------------------------------------------------------------
+    total_steps = 8 * bunch_steps
+    series = steps.muon_bundle_steps(total_steps, num_muons=100, seed=3)   # the same series on every rank (seeded)
+    shard = split_steps(series, world)[rank]
+    pieces = [shard[i:i + bunch_steps] for i in range(0, len(shard), bunch_steps)]
+    opt = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=5.0, kernel_mode=KERNEL_FAST, enable_double_buffering=True,
+                           max_num_workitems=bunch_steps, rng_seed=5150 + rank, rng_first_multiplier=rng_row_offset(rank))
+    with capi.Engine(lea, geo, gens, bias, opt) as eng:
+        e2e_through_engine(eng, pieces[:1] * 2)   # warm the staging pool
+        barrier()
+        t0 = time.perf_counter()
+        # bunch identifiers name (rank, piece): the caller's key for putting results back together (I3CLSimClientModule.cxx:359-439)
+        _, got = e2e_through_engine(eng, pieces, first_id=1000 * rank)
+        t_prop = time.perf_counter() - t0
+        # hand the hit lists to rank 0: lengths first, then the records as bytes over NCCL (padded to the longest)
+        ids = np.array([i for i, _ in got], dtype=np.int64)
+        lens = np.array([len(p) for _, p in got], dtype=np.int64)
+        mine = np.concatenate([p for _, p in got]) if got else np.zeros(0, dtype=capi.PHOTON_DTYPE)
+        if world > 1:
+            meta = torch.zeros(2 * 16 + 1, dtype=torch.int64, device="cuda")
+            meta[0] = len(got)
+            meta[1:1 + len(got)] = torch.from_numpy(ids).cuda()
+            meta[17:17 + len(got)] = torch.from_numpy(lens).cuda()
+            metas = torch.empty(world * meta.numel(), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(metas, meta)
+            metas = metas.view(world, -1).cpu().numpy()
+            longest = int(max(metas[r, 17:17 + metas[r, 0]].sum() for r in range(world))) * mine.dtype.itemsize
+            payload = torch.zeros(max(16, longest), dtype=torch.uint8, device="cuda")
+            payload[:mine.nbytes] = torch.from_numpy(mine.view(np.uint8)).cuda()
+            everything = torch.empty(world * payload.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(everything, payload)
+            results = []
+            if rank == 0:
+                host = everything.view(world, -1).cpu().numpy()
+                for r in range(world):
+                    k = int(metas[r, 0])
+                    recs = host[r, :int(metas[r, 17:17 + k].sum()) * mine.dtype.itemsize].view(mine.dtype)
+                    at = 0
+                    for j in range(k):
+                        results.append((int(metas[r, 1 + j]), recs[at:at + int(metas[r, 17 + j])]))
+                        at += int(metas[r, 17 + j])
+        else:
+            results = got
+        merged_bunches, merged_hits = 0, 0
+        if rank == 0:
+            merged = merge_results(results)
+            merged_bunches, merged_hits = len(merged), int(sum(len(v) for v in merged.values()))
+        t_all = time.perf_counter() - t0
+    t_prop = max_over_ranks(t_prop)
+    t_all = max_over_ranks(t_all)
+    photons_total = float(series["num_photons"].sum())
+    out["strong_scaling_config3"] = {
+        "workload": "ONE muon-bundle step series (config 3: SpiceLea + tilt + anisotropy), %d steps x %d photons, split over the ranks; host buffers in, hit lists handed to rank 0 and merged by bunch identifier" % (total_steps, PHOTONS_PER_STEP),
+        "value": photons_total / t_all, "unit": "photons/s", "scaling": "strong", "seconds_to_merged_result": t_all,
+        "seconds_to_last_rank_result": t_prop, "bunches_merged": merged_bunches, "hits_merged": merged_hits, "photons": photons_total}
+
+    # ---------------- (b) one process, N converters behind the server seam ------------------------------------------
+    cpu_barrier()
+    if rank == 0:
+        c2 = build_scene()
+        devices = configureCUDADevices(UseGPUs=True, OverrideApproximateNumberOfWorkItems=bunch_steps, numDevices=world)
+        converters = [initializeCUDA(dev, 6000 + i, c2[1], c2[0], c2[3], c2[2], enableDoubleBuffering=True, stopDetectedPhotons=True, pancakeFactor=5.0,
+                                     kernelMode=KERNEL_FAST, rngFirstMultiplierRow=i * RNG_ROWS_PER_DEVICE) for i, dev in enumerate(devices)]
+        server = I3CLSimServerInProcess(converters)
+        client = server.Connect()
+        bunch = make_bunch(bunch_steps, seed=4000)
+        per_gpu = 6
+        for i in range(2 * world):   # warm every converter's staging pool
+            client.EnqueueSteps(bunch, i)
+        for i in range(2 * world):
+            client.GetConversionResult()
+        t0 = time.perf_counter()
+        hits, sent, received, window = 0, 0, 0, 4 * world   # one feeder: at most `window` bunches in flight
+        total = per_gpu * world
+        while received < total:
+            while sent < total and sent - received < window:
+                client.EnqueueSteps(bunch, sent)
+                sent += 1
+            hits += len(client.GetConversionResult().photons)
+            received += 1
+        dt = time.perf_counter() - t0
+        st = server.GetStatistics()
+        calls = [st.get("NumKernelCalls" + ("" if world == 1 else "_%d" % i), 0.0) for i in range(world)]
+        server.Close()
+        for c in converters:
+            c.Close()
+        out["one_process_n_converters"] = {
+            "workload": "config 2 bunches (2^20 steps x 200 photons) from ONE feeder thread through I3CLSimServerInProcess to %d converters, one per GPU, host buffers in and hit lists out" % world,
+            "value": total * float(bunch["num_photons"].sum()) / dt, "unit": "photons/s", "bunches": total, "seconds": dt, "hits": hits,
+            "kernel_calls_per_converter": calls}
+    cpu_barrier()
+
+    # ---------------- (c) config 4 at its stated size -----------------------------------------------------------------
+    ang = mcpe.GetIceCubeDOMAngularSensitivity()
+    acc = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0, efficiency=0.9 * mcpe.GetHoleIcePeak())
+    gen4 = ice.makeCherenkovWavelengthGenerator(acc, False, lea)
+    opt4 = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=5.0, kernel_mode=KERNEL_FAST, enable_double_buffering=True,
+                            max_num_workitems=bunch_steps, rng_seed=7000 + rank, output_photons_per_workitem=2, rng_first_multiplier=rng_row_offset(rank))
+    conv = stepgen.I3CLSimLightSourceToStepConverterPPC(photonsPerStep=PHOTONS_PER_STEP, device=local)
+    conv.SetMediumProperties(lea)
+    conv.SetWlenBias(acc)
+    conv.SetRandomService(40 + rank)
+    conv.Initialize(rngFirstMultiplierRow=stepgen_row_offset(rank))
+    pe = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(50 + rank, {(int(s), int(o)): acc for s, o in zip(geo.stringIDs, geo.domIDs)}, ang,
+                                                 device=local, rngFirstMultiplierRow=mcpe_row_offset(rank))
+    want_photons = 1.25e10
+    with capi.Engine(lea, geo, [gen4], acc, opt4) as eng:
+        pe.attach_to(eng)
+        vertex, axis = (20.0, -30.0, -250.0), (0.3, 0.2, -0.93)
+        conv.EnqueueLightSource(stepgen.Particle("EMinus", 1e3, vertex, axis), 0)   # warm-up, and the yield per GeV
+        small = 0
+        while conv.EnqueueInto(eng, 0):
+            small += eng.get_result().num_photons_generated
+        energy = 1e3 * want_photons / max(1.0, small)
+        conv.EnqueueLightSource(stepgen.Particle("EMinus", energy, vertex, axis), 1)
+        conv.EnqueueBarrier()
+        barrier()
+        t0 = time.perf_counter()
+        sent = pending = photons = hits = pes = 0
+        while True:
+            if conv.EnqueueInto(eng, 100 + sent) == 0:
+                break
+            sent += 1
+            pending += 1
+            while eng.more_photons_available():
+                r = eng.get_result(); pending -= 1
+                photons += r.num_photons_generated; hits += r.num_hits_counted; pes += len(r.mcpes)
+        while pending:
+            r = eng.get_result(); pending -= 1
+            photons += r.num_photons_generated; hits += r.num_hits_counted; pes += len(r.mcpes)
+        dt = time.perf_counter() - t0
+    pe.close()
+    dt = max_over_ranks(dt)
+    out["config4_cascade"] = {
+        "workload": "config 4: e- cascade in SpiceLea + tilt + anisotropy, steps made on the device from the step-generation queue entry, photo-electrons out; %.3g propagated photons per GPU (a %.3g GeV e- with the DOM-acceptance bias; the config's ~1e11 photons on eight GPUs)" % (want_photons, energy),
+        "value": sum_over_ranks(float(photons)) / dt, "unit": "photons/s", "scaling": "weak", "seconds": dt, "photons": sum_over_ranks(float(photons)),
+        "hits": sum_over_ranks(float(hits)), "mcpes": sum_over_ranks(float(pes)), "bunches_per_gpu": sent}
+    return out
+
+
 def run_reference_arm(args):
     """The reference's own implementation of the path on the host cores (CpuArm: oracle/_ref when it was built, else
     the oracle port; OpenCL itself cannot run in this image)."""
@@ -261,6 +496,7 @@ def main():
     ap.add_argument("--bunch", type=int, default=STEPS_PER_BUNCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-variants", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--multi-gpu-legs", action="store_true", help=argparse.SUPPRESS)   # run the N > 1 legs at N = 1 too (the series' first point)
     # side measurements (not the headline): BASELINE config 3's ice, "spice_lea" = SpiceLea with tilt and anisotropy
     ap.add_argument("--ice", default="spice_mie", help=argparse.SUPPRESS)
     ap.add_argument("--tilt", action="store_true", help=argparse.SUPPRESS)
@@ -283,8 +519,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")   # CPU-side barriers and the host-side merge of hit lists
 
     def barrier():
         if world > 1:
@@ -365,14 +603,21 @@ def main():
     if not args.no_variants:
         variants = run_variants(args, scene, bunch, opt, local, rank, barrier, max_over_ranks, sum_over_ranks)
 
+    peaks = measured_peaks()
+    props = torch.cuda.get_device_properties(local)
+    sms = props.multi_processor_count
+    other = None
+    if world == 1 and not args.no_variants and args.ice == "spice_mie" and not args.tilt:
+        other = run_other_configs(args, local, sms, peaks["sm_max_mhz"])
+    multi = None
+    if not args.no_variants and args.ice == "spice_mie" and not args.tilt and (world > 1 or args.multi_gpu_legs):
+        multi = run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = measured_peaks()
-    props = torch.cuda.get_device_properties(local)
-    sms = props.multi_processor_count
     peak_ops = sms * 128 * peaks["sm_max_mhz"] * 1e6 * world
     achieved_ops = (segments_all * OPS_PER_SEGMENT + photons_all * OPS_PER_PHOTON) / (kernel_ms * 1e-3)
     hit_bytes = hits_all * 80.0
@@ -403,6 +648,8 @@ def main():
                 "kernel_ms_per_step": e2e_kernel_ms / max(1, args.steps), "wall_ms": e2e_s * 1e3, "timeline_ms": timeline},
         "gpu_launches": args.steps,
         "e2e_variants": variants,
+        "other_configs": other,
+        "multi_gpu": multi,
         "roofline": roofline,
         "clocks": clocks,
     }

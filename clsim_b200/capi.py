@@ -22,7 +22,7 @@ SYMBOLS = [
     "clsimcu_create", "clsimcu_destroy", "clsimcu_enqueue", "clsimcu_get_result", "clsimcu_release_result",
     "clsimcu_queue_size", "clsimcu_more_photons_available", "clsimcu_workgroup_size", "clsimcu_max_num_workitems",
     "clsimcu_get_statistics", "clsimcu_upload_resident", "clsimcu_run_resident", "clsimcu_download_resident",
-    "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
+    "clsimcu_download_resident_history", "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
     "clsimcu_describe_collision_map_from_config",
     "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
     "clsimcu_sizeof_config", "clsimcu_device_count",
@@ -70,6 +70,7 @@ def lib():
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.clsimcu_download_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_download_resident_rng_tags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.clsimcu_download_resident_history.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_rng_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.clsimcu_rng_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.clsimcu_describe_tables.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -226,6 +227,13 @@ class Engine(object):
         out = np.zeros(k, dtype=PHOTON_DTYPE)
         if k:
             _check(lib().clsimcu_download_resident(self._h, out.ctypes.data, k, C.byref(n)))
+        return out
+
+    def download_resident_history(self, k, entries):
+        """[k][entries][4]: the scatter points of the hits of the last resident run, forward order, unused rows NaN"""
+        out = np.zeros((k, entries, 4), dtype=np.float32)
+        n = C.c_size_t(0)
+        _check(lib().clsimcu_download_resident_history(self._h, out.ctypes.data, k, C.byref(n)))
         return out
 
     def download_resident_rng_tags(self, k):

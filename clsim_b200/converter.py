@@ -195,9 +195,6 @@ class I3CLSimStepToPhotonConverterCUDA(object):
         if self._engine is not None:
             raise _already()
         self.Compile()
-        # photon history and non-stopping detection exist only in the reference-order kernel (slow path, still on the GPU)
-        if self._opt.photon_history_entries > 0 or not (self._opt.stop_detected_photons or self._opt.save_all_photons):
-            self._opt.kernel_mode = KERNEL_REFERENCE
         try:
             self._engine = capi.Engine(self._medium, None if self._opt.save_all_photons else self._geometry,
                                        self._wlenGenerators, self._wlenBias, self._opt)

@@ -127,6 +127,7 @@ struct LaunchArgs {
     uint32_t max_hits;         // capacity of photons[]
     void *photons;             // clsimcu_photon[max_hits]
     float *history;            // [max_hits][history_entries][4] or nullptr
+    float *history_ring;       // fast kernel with photon history: [history_entries][resident threads][4], the lanes' scatter-point rings
     uint32_t *hit_counter;     // device counter (keeps counting past max_hits, quirk 10)
     unsigned long long *stats; // [0] photons created, [1] segments
     uint32_t *work_counter;    // fast kernel: next step to hand out

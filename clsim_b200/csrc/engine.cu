@@ -251,6 +251,8 @@ struct clsimcu_engine {
     clsimcu_photon *d_res_photons = nullptr;
     uint32_t *d_res_counters = nullptr, *h_res_counters = nullptr;
     unsigned long long *d_res_stats = nullptr, *h_res_stats = nullptr;
+    float *d_res_history = nullptr;                // resident path: raw history rings of the hits, [res_cap][entries][4]
+    float *d_history_ring = nullptr;               // fast kernel with photon history: the lanes' scatter-point rings
     uint64_t *d_tag_x = nullptr;
     uint32_t *d_tag_a = nullptr;
     uint8_t *d_l2_flush = nullptr;   // written between timed launches (larger than the 126 MB L2)
@@ -505,6 +507,7 @@ void submit_loop(clsimcu_engine *e)
                 a.max_hits = static_cast<uint32_t>(e->max_hits);
                 a.photons = s.d_photons;
                 a.history = s.d_history;
+                a.history_ring = e->d_history_ring;
                 a.hit_counter = s.d_counters;
                 a.work_counter = s.d_counters + 1;
                 a.stats = s.d_stats;
@@ -628,6 +631,7 @@ void free_engine(clsimcu_engine *e)
         if (s.xfer) cudaStreamDestroy(s.xfer);
     }
     for (size_t i = 0; i < e->staging_count; ++i) cudaFreeHost(e->staging[i]);
+    cudaFree(e->d_history_ring); cudaFree(e->d_res_history);
     cudaFree(e->d_arena); cudaFree(e->d_scene); cudaFree(e->d_rng_x); cudaFree(e->d_rng_a);
     cudaFree(e->d_res_steps); cudaFree(e->d_res_photons); cudaFree(e->d_res_counters); cudaFree(e->d_res_stats);
     cudaFree(e->d_tag_x); cudaFree(e->d_tag_a); cudaFree(e->d_l2_flush); cudaFree(e->d_tab_steps);
@@ -661,7 +665,20 @@ std::string engine_launch_tabulate(clsimcu_engine *e, const clsimcu_step *steps,
         a.rng_a = e->d_rng_a;
         a.scene_dev = e->d_scene;
         a.tabulate = d_tab;
-        if (const int rc = launch_reference_kernel(e->scene, a, e->compute)) throw CudaError(launch_error_text(rc));
+        if (e->kernel_mode == CLSIMCU_KERNEL_FAST) {
+            // the persistent kernel's bookkeeping: work counter (zeroed per launch), creation streams behind the
+            // propagation streams; table mode records no photons, the hit counter stays untouched
+            Slot &s = e->slots[0];
+            CUDA_OK(cudaMemsetAsync(s.d_counters, 0, 2 * sizeof(uint32_t), e->compute));
+            a.hit_counter = s.d_counters;
+            a.work_counter = s.d_counters + 1;
+            a.stats = s.d_stats;
+            a.count_stats = 0;
+            a.rng_creation_offset = static_cast<uint32_t>(e->fast_blocks) * e->fast_threads;
+            if (const int rc = launch_fast_kernel(e->scene, a, e->fast_blocks, e->compute)) throw CudaError(launch_error_text(rc));
+        } else if (const int rc = launch_reference_kernel(e->scene, a, e->compute)) {
+            throw CudaError(launch_error_text(rc));
+        }
     } catch (const std::exception &ex) {
         return ex.what();
     }
@@ -754,6 +771,11 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
                 budget = budget * 7 / 8;
             }
             fast_kernel_geometry(e->device, &e->fast_blocks, &e->fast_threads);
+            if (e->history_entries > 0) {
+                const size_t ring_bytes = static_cast<size_t>(e->history_entries) * e->fast_blocks * e->fast_threads * 4 * sizeof(float);
+                CUDA_OK(cudaMalloc(&e->d_history_ring, ring_bytes));
+                CUDA_OK(cudaMemset(e->d_history_ring, 0, ring_bytes));
+            }
             if (e->max_items > (size_t(1) << kFastKernelStepIndexBits))
                 throw std::runtime_error("the fast kernel takes bunches of at most 2^27 steps (max_num_workitems is " + std::to_string(e->max_items) + ")");
         } else {
@@ -1029,6 +1051,7 @@ int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t
             CUDA_OK(cudaHostAlloc(&e->h_res_counters, 2 * sizeof(uint32_t), cudaHostAllocDefault));
             CUDA_OK(cudaHostAlloc(&e->h_res_stats, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
             CUDA_OK(cudaMalloc(&e->d_l2_flush, kL2FlushBytes));
+            if (e->history_entries > 0) CUDA_OK(cudaMalloc(&e->d_res_history, e->res_cap * e->history_entries * 4 * sizeof(float)));
             if (e->save_all) {
                 CUDA_OK(cudaMalloc(&e->d_tag_x, 2 * e->res_cap * sizeof(uint64_t)));
                 CUDA_OK(cudaMalloc(&e->d_tag_a, 2 * e->res_cap * sizeof(uint32_t)));
@@ -1067,7 +1090,8 @@ int clsimcu_run_resident(clsimcu_engine *e, int repeat, double *kernel_ms, uint6
             a.num_steps = static_cast<uint32_t>(e->res_steps);
             a.max_hits = static_cast<uint32_t>(e->res_cap);
             a.photons = e->d_res_photons;
-            a.history = nullptr;
+            a.history = e->d_res_history;
+            a.history_ring = e->d_history_ring;
             a.hit_counter = e->d_res_counters;
             a.work_counter = e->d_res_counters + 1;
             a.stats = e->d_res_stats;
@@ -1134,6 +1158,31 @@ int clsimcu_download_resident_rng_tags(clsimcu_engine *e, uint64_t *x, uint32_t 
             CUDA_OK(cudaMemcpy(x, e->d_tag_x, 2 * k * sizeof(uint64_t), cudaMemcpyDeviceToHost));
             CUDA_OK(cudaMemcpy(a, e->d_tag_a, 2 * k * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         }
+    } catch (const std::exception &ex) {
+        return fail(CLSIMCU_ERR_CUDA, ex.what());
+    }
+    return CLSIMCU_OK;
+}
+
+int clsimcu_download_resident_history(clsimcu_engine *e, float *out, size_t cap, size_t *n)
+{
+    if (!e) return fail(CLSIMCU_ERR_STATE, "engine is NULL");
+    if (e->history_entries <= 0 || !e->d_res_history) return fail(CLSIMCU_ERR_STATE, "no photon history was requested (photon_history_entries is 0)");
+    try {
+        std::lock_guard<std::mutex> lk(e->compute_mutex);
+        CUDA_OK(cudaSetDevice(e->device));
+        const size_t have = std::min<size_t>(e->res_last_hits, e->res_cap);
+        const size_t k = std::min(have, cap);
+        if (k > 0 && out) {
+            std::vector<clsimcu_photon> photons(k);
+            std::vector<float> raw(k * e->history_entries * 4);
+            CUDA_OK(cudaMemcpy(photons.data(), e->d_res_photons, k * sizeof(clsimcu_photon), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(raw.data(), e->d_res_history, raw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            std::vector<float> ordered;
+            unroll_history(raw.data(), photons.data(), k, e->history_entries, ordered);
+            std::memcpy(out, ordered.data(), ordered.size() * sizeof(float));
+        }
+        if (n) *n = have;
     } catch (const std::exception &ex) {
         return fail(CLSIMCU_ERR_CUDA, ex.what());
     }

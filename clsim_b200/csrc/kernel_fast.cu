@@ -58,6 +58,7 @@
 
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
+#include "tabulate_device.h"
 
 namespace clsimcu {
 namespace {
@@ -138,6 +139,10 @@ constexpr int kOffWarpStep = kWarpsPerBlock * kQueueWords * 32;
 constexpr int kOffWarpCtl = kOffWarpStep + kWarpsPerBlock * kWarpStepWords;
 
 enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3 };
+// rare variants of the kernel (template parameter V, a bit set): photon history ring, table-maker sink, StopDetectedPhotons = false
+// (kept out of the default instantiation: ptxas allocates registers over the whole call graph, and the slow path's extra
+// live values cost the hot loop spills)
+constexpr int kVarHist = 1, kVarTab = 2, kVarNonStop = 4;
 
 // ---- approximate MUFU wrappers ---------------------------------------------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -190,6 +195,7 @@ struct SmemLayout {
 struct SmemHeader {
     SmemLayout lay;
     LaunchArgs args;
+    TabulateArgs tab;   // table-maker variant: the table's description (args.tabulate points at the original in HBM)
 };
 
 struct SmemPlan {
@@ -205,13 +211,25 @@ struct SmemPlan {
     float *tilt_corr;        // [tilt_nd][tilt_nz] z corrections
 };
 
-__host__ __device__ inline uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
+
+// The regions of fixed size come first, at compile-time offsets: the hot loop then addresses the layer table, the
+// pixel map, the lane's state column and the warp's queue as  register + immediate  and keeps no base pointers alive
+// (the kernel runs at the 64-register limit; a base pointer in a register is a spill somewhere else).
+constexpr int kMaxStagedLayers = 256;   // entries of the layer table, the sentinel included
+constexpr uint32_t kSmLayers = align16(static_cast<uint32_t>(sizeof(SmemHeader)));
+constexpr uint32_t kSmQueue = kSmLayers + kMaxStagedLayers * 16u;
+constexpr uint32_t kSmState = kSmQueue + align16(kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4u);
+constexpr uint32_t kSmNear = kSmState + kPerThreadWords * kThreads * 4u;   // (save-all: the propagation-stream tags sit here, there is no pixel map)
 
 __host__ SmemLayout plan_smem(const DevScene &s)
 {
     SmemLayout L{};
-    uint32_t at = align16(sizeof(SmemHeader));
-    L.off_layers = at; at = align16(at + (s.medium.num_layers + 1) * 16);
+    L.off_layers = kSmLayers;
+    L.off_queue = kSmQueue;
+    L.off_state = kSmState;
+    uint32_t at = align16(kSmNear + (s.save_all ? kPopTagWords * kThreads * 4u : 0u));
+    L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
     L.off_strings = at; at = align16(at + (s.geo.num_strings + 1) * 16);
     L.off_sets = at; at = align16(at + s.geo.num_sets * 16);
     L.off_string_set = at; at = align16(at + s.geo.num_strings);
@@ -223,7 +241,6 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         cells += s.geo.grids[i].num_x * s.geo.grids[i].num_y;
     }
     at = align16(at + cells * 2);
-    L.off_near = at; at = align16(at + s.geo.near_nx * s.geo.near_ny * 4);
     L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 32);   // + 8 search keys
     L.off_tilt_corr = at; at = align16(at + s.medium.tilt_nd * s.medium.tilt_nz * 4);
     L.off_gen0 = at;
@@ -235,8 +252,6 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         L.off_gen0_bins = at;
         at = align16(at + (CLSIMCU_WLEN_BIN_RECORDS ? L.gen0_n * 24 : 0));
     }
-    L.off_state = at; at = align16(at + (kPerThreadWords + (s.save_all ? kPopTagWords : 0)) * kThreads * 4);
-    L.off_queue = at; at = align16(at + kWarpsPerBlock * (kQueueWords * 32 + kWarpStepWords + kWarpCtlWords) * 4);
     L.total = at;
     return L;
 }
@@ -456,9 +471,19 @@ struct Collision {
     int string, dom;
     bool hit;
 };
+// StopDetectedPhotons = false (sparse_collision_kernel.c.cl:166-187): every DOM whose entry point lies on the leg is
+// recorded and the photon flies on.  The slow phase walks the leg's hits in order of their entry points: the search
+// below returns the nearest hit BEYOND a lower bound (entry distance, then string and DOM as tie-breakers), and is
+// called again with the hit it returned as the new bound until nothing is left.  Each DOM has one entry point, so
+// none is recorded twice -- the reference's bit masks (:85-104, 250-269) without their aliasing.
+struct After {
+    float entry;
+    int key;   // string << 16 | DOM of the hit that was returned last; -1: none yet
+};
 
+template <bool NONSTOP>
 __device__ __forceinline__ void test_string(const SmemPlan &sp, const DevGeometry &geo, int s, const V3 &pos, const V3 &dir,
-                                            float inv_xy2, float inv_pancake, Collision &c)
+                                            float inv_xy2, float inv_pancake, Collision &c, After after)
 {
     const float4 sv = sp.strings[s];
     const float cross = (pos.x - sv.x) * dir.y - (pos.y - sv.y) * dir.x;
@@ -484,7 +509,8 @@ __device__ __forceinline__ void test_string(const SmemPlan &sp, const DevGeometr
         disc = mufu_sqrt(disc) * inv_pancake;
         const float entry = along - disc;
         if (entry < 0.f) continue; // started inside (or behind): let it leave (quirk 9)
-        if (entry < c.travel) {
+        if (NONSTOP && (entry < after.entry || (entry == after.entry && ((s << 16) | dom) <= after.key))) continue;   // already recorded
+        if (entry < c.travel || (NONSTOP && c.hit && entry == c.travel && ((s << 16) | dom) < ((c.string << 16) | c.dom))) {
             c.travel = entry;
             c.hit = true;
             c.string = s;
@@ -496,7 +522,8 @@ __device__ __forceinline__ void test_string(const SmemPlan &sp, const DevGeometr
 // The collision test proper, for the few segments the pixel map cannot rule out.  `who` >= 0:
 // only that string can be reached (string level of the reference); `who` < 0: the reference's
 // walk over the xy cells covered by the segment (sparse_collision_kernel.c.cl:194-303, 305-460).
-__device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos, V3 dir, float travel)
+template <bool NONSTOP>
+__device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos, V3 dir, float travel, After after = After{-1.f, -1})
 {
     const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
     const SmemPlan sp = table_plan(lay);
@@ -507,7 +534,7 @@ __device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos
     const float inv_xy2 = mufu_rcp(dir_xy2);
     const float inv_pancake = scene->inv_pancake_factor;
     if (who >= 0) {
-        test_string(sp, geo, who, pos, dir, inv_xy2, inv_pancake, c);
+        test_string<NONSTOP>(sp, geo, who, pos, dir, inv_xy2, inv_pancake, c, after);
         return c;
     }
     for (int gI = 0; gI < geo.num_grids; ++gI) {
@@ -521,7 +548,9 @@ __device__ __noinline__ Collision collide(const DevScene *scene, int who, V3 pos
         for (int cy = ya; cy <= yb; ++cy) {
             for (int cx = xa; cx <= xb; ++cx) {
                 const int s = cells[cy * cg.num_x + cx];
-                if (s != 0xFFFF) test_string(sp, geo, s, pos, dir, inv_xy2, inv_pancake, c);
+                if (s == 0xFFFF) continue;
+                // (a string that sits in several cells is simply tested again: the search is for a minimum)
+                test_string<NONSTOP>(sp, geo, s, pos, dir, inv_xy2, inv_pancake, c, after);
             }
         }
     }
@@ -542,6 +571,7 @@ struct Born {
     float t;
     V3 dir;
     float wlen, life;
+    float first_sample;   // table-maker variant
 };
 
 __device__ __forceinline__ V3 step_axis(float theta, float phi)
@@ -552,7 +582,7 @@ __device__ __forceinline__ V3 step_axis(float theta, float phi)
     return V3{sth * cph, sth * sph, cth};
 }
 
-__device__ __forceinline__ Born create_core(const DevScene *scene, const StepView &s, Mwc &rng)
+__device__ __forceinline__ Born create_core(const DevScene *scene, const StepView &s, Mwc &rng, float tab_step = 0.f)
 {
     const DevMedium &m = scene->medium;
     Born b;
@@ -568,6 +598,8 @@ __device__ __forceinline__ Born create_core(const DevScene *scene, const StepVie
     } else {
         b.wlen = (s.source < static_cast<uint32_t>(scene->num_generators)) ? draw_wavelength(scene->generators[s.source], rng) : 0.f;
     }
+    // (table-maker variant: the offset of the first sampling point is drawn here, propagation_kernel.c.cl:566-569)
+    b.first_sample = tab_step > 0.f ? tab_step * rng.oc() : 0.f;
     b.life = scene->fixed_abs ? scene->fixed_abs_lens : -fast_ln(rng.oc());
     b.pos = V3{s.x + s.axis.x * shift, s.y + s.axis.y * shift, s.z + s.axis.z * shift};
     b.t = s.t + shift * mufu_rcp(kSpeedOfLight * s.beta);
@@ -587,7 +619,9 @@ __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint
     s.length = __uint_as_float(wstep[6]); s.beta = __uint_as_float(wstep[7]);
     s.source = wstep[11] & 0xffu;
     s.axis = V3{__uint_as_float(wstep[12]), __uint_as_float(wstep[13]), __uint_as_float(wstep[14])};
-    const Born b = create_core(scene, s, rng);
+    const LaunchArgs &largs = reinterpret_cast<const SmemHeader *>(smem_base())->args;
+    const float tab_step = largs.tabulate ? largs.tabulate->step_length : 0.f;
+    const Born b = create_core(scene, s, rng, tab_step);
     // derived here, where all 32 lanes work, rather than when a lane takes the photon
     const int layer = min(max(__float2int_rz((b.pos.z - m.z0) * m.inv_h), 0), m.num_layers - 1);
     const float nm = b.wlen * 1e9f;
@@ -597,7 +631,10 @@ __device__ __noinline__ uint64_t create_photon(const DevScene *scene, const uint
     slot[0] = make_float4(b.pos.x, b.pos.y, b.dir.x, b.dir.y);
     slot[1] = make_float4(b.pos.z, b.dir.z, b.life, __int_as_float(layer));
     slot[2] = make_float4(f_scat, f_pure, f_dust, 0.f);
-    slot[3] = make_float4(__uint_as_float(static_cast<uint32_t>(rng_x)), __uint_as_float(static_cast<uint32_t>(rng_x >> 32)), __uint_as_float(tag_step), 0.f);
+    if (largs.tabulate)
+        slot[3] = make_float4(b.t, inv_group_velocity(m, b.wlen), __uint_as_float(wstep[9]), b.first_sample);   // (time, 1/v_g, step weight, first sample)
+    else
+        slot[3] = make_float4(__uint_as_float(static_cast<uint32_t>(rng_x)), __uint_as_float(static_cast<uint32_t>(rng_x >> 32)), __uint_as_float(tag_step), 0.f);
     return rng.x;
 }
 
@@ -664,6 +701,18 @@ __device__ __noinline__ void emit_record(const DevScene *scene_dev, float *st, V
                          __uint_as_float(__ldg(&step->identifier)), __uint_as_float(ids));
     dst[3] = make_float4(born.pos.x, born.pos.y, born.pos.z, born.t);
     dst[4] = make_float4(sth, sph, 1.f / ivg, born.life - abs_left_at_end);
+    if (args.history && args.history_ring) {
+        // the lane's ring as it is (the reference writes the raw ring too, propagation_kernel.c.cl:387-392; the host
+        // puts it in order, ...OpenCL.cxx:940-989); fourth component: absorption lengths used so far
+        const int n = scene.history_entries;
+        const float4 *ring = reinterpret_cast<const float4 *>(args.history_ring) + (blockIdx.x * kThreads + threadIdx.x);
+        float4 *out = reinterpret_cast<float4 *>(args.history) + static_cast<size_t>(slot) * n;
+        for (int i = 0; i < n; ++i) {
+            float4 e = ring[static_cast<size_t>(i) * (static_cast<size_t>(gridDim.x) * kThreads)];
+            e.w = born.life - e.w;
+            out[i] = e;
+        }
+    }
     if (save_all && args.rng_tag_x) {
         const uint32_t *ptag = reinterpret_cast<const uint32_t *>(st + kOffPopTag);
         args.rng_tag_x[2 * static_cast<size_t>(slot)] = birth_x;
@@ -718,14 +767,22 @@ struct Lane {
     int layer;
     uint32_t status;
     uint64_t rng_x;
+    // table-maker variant only (TAB): time at the start of the flight's current leg, 1 / group velocity, the step's
+    // weight, distance from the leg's start to the next sampling point of the path
+    float t, inv_vg, weight, rem;
 };
 
 // 1/dz without a guard: dz == 0 gives +-inf, and a leg then never reaches the boundary ahead (the reference treats
 // |dz| < 1e-5 as "stays in its layer", propagation_kernel.c.cl:669; a photon that flat flies > 1e5 layer heights per layer)
 __device__ __forceinline__ float raw_inv_dz(float dz) { return mufu_rcp(dz); }
 
-template <bool TILT, bool ANISO> __device__ __forceinline__ void load_lane(Lane &L, const float *st)
+template <bool TILT, bool ANISO, bool TAB = false> __device__ __forceinline__ void load_lane(Lane &L, const float *st)
 {
+    if (TAB) {
+        // (table mode records no photons: the birth-tag words and the parking words hold the four extra values)
+        L.t = st[(kOffBirthTag + 0 * kThreads)]; L.inv_vg = st[(kOffBirthTag + 1 * kThreads)]; L.weight = st[(kOffBirthTag + 2 * kThreads)];
+        L.rem = st[kPendTravel * kThreads];
+    }
     L.pxy = make_float2(st[kPx * kThreads], st[kPy * kThreads]); L.pz = st[kPz * kThreads];
     L.dxy = make_float2(st[kDx * kThreads], st[kDy * kThreads]); L.dz = st[kDz * kThreads];
     L.inv_dz = raw_inv_dz(L.dz);
@@ -739,8 +796,12 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void load_lane(Lane 
     L.inv_aniso = ANISO ? st[kInvAniso * kThreads] : 1.f;
 }
 
-template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(const Lane &L, float *st)
+template <bool TILT, bool ANISO, bool TAB = false> __device__ __forceinline__ void store_lane(const Lane &L, float *st)
 {
+    if (TAB) {
+        st[(kOffBirthTag + 0 * kThreads)] = L.t; st[(kOffBirthTag + 1 * kThreads)] = L.inv_vg; st[(kOffBirthTag + 2 * kThreads)] = L.weight;
+        st[kPendTravel * kThreads] = L.rem;
+    }
     st[kPx * kThreads] = L.pxy.x; st[kPy * kThreads] = L.pxy.y; st[kPz * kThreads] = L.pz;
     st[kDx * kThreads] = L.dxy.x; st[kDy * kThreads] = L.dxy.y; st[kDz * kThreads] = L.dz;
     st[kAbsLeft * kThreads] = L.bud.x; st[kScaLeft * kThreads] = L.bud.y; st[kPath * kThreads] = L.path;
@@ -756,9 +817,9 @@ template <bool TILT, bool ANISO> __device__ __forceinline__ void store_lane(cons
 
 // Second look at a leg the 2-D cylinder test could not rule out, still in the hot loop (one leg in ~600 gets here,
 // four in five of them leave again): the part of the leg inside the cylinder around string `who` covers a short
-// range in z; only if a DOM of that string sits within om_radius of that range can the leg touch it.  Every DOM
-// lies wholly inside its z-layer of the string's set (the table builder guarantees it), so the layers the range
-// covers name the candidates.  Conservative: the margins cover the rounding of the approximate root.
+// range in z; only if a DOM of that string sits within om_radius of that range can the leg touch it.  The z-layer
+// table of the string's set names a DOM in every layer its sphere touches (the table builder guarantees it), so the
+// layers the range covers name the candidates.  Conservative: the margins cover the rounding of the approximate root.
 __device__ __noinline__ bool dom_within_reach(const DevScene *scene, int who, float z, float dz, float travel, float t, float dxy2, float out2)
 {
     const SmemPlan sp = table_plan(reinterpret_cast<const SmemHeader *>(smem_base())->lay);
@@ -805,20 +866,36 @@ struct Leg {
 
 // +1 for a photon going up (or flat), -1 for one going down, from the sign of 1/dz
 __device__ __forceinline__ int layer_step(float inv_dz) { return (__float_as_int(inv_dz) >> 31) | 1; }
+// ... as a step of the layer record's address
+__device__ __forceinline__ int layer_address_step(float inv_dz) { return ((__float_as_int(inv_dz) >> 31) & -32) + 16; }
 // pixel-map word -> string index / "the strings are too dense here for the map: the reference's cell walk instead"
 __device__ __forceinline__ int cell_string(uint32_t cell) { return static_cast<int>((cell & 0xffffu) >> 4); }
 __device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff0000u) == 0x7f800000u; }
 
+// Loads from 32-bit shared-memory addresses.  The hot loop holds the layer table and the pixel map as such addresses: the
+// compiler re-derives a generic pointer's shared address (S2UR / ULEA, or a base register it then spills) at every use.
+__device__ __forceinline__ float4 lds128(uint32_t a) { float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ float lds32f(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// the shared-memory address of dynamic shared memory's first byte, opaque to the optimiser (so that it is computed once)
+__device__ __forceinline__ uint32_t smem_address()
+{
+    uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_base()));
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return a;
+}
+
 // LOOK_ALWAYS legs consult the collision map; the others are planned without it (no range limit) and may only be
 // flown if they are shorter than the photon's clearance (see advance_photon).
+// `L.layer` is the shared-memory ADDRESS of the photon's layer record (one LDS.128 and one LDS with no address arithmetic;
+// a layer change is +-16); `near` the address of the pixel map.
 template <bool TILT, bool SAVE_ALL, bool LOOK_ALWAYS>
-__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *layers, const float4 *strings,
-                                        const uint32_t *near)
+__device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, const float4 *strings, uint32_t near)
 {
     const DevGeometry &geo = scene.geo;
     Leg g;
-    const float4 c = layers[L.layer];
-    const float z_up = layers[L.layer + 1].w;
+    const float4 c = lds128(static_cast<uint32_t>(L.layer));
+    const float z_up = lds32f(static_cast<uint32_t>(L.layer) + 28u);
     g.q = __fmul2_rn(make_float2(c.x, c.y), L.f_sp);         // (b400 * f_scat, (1 + 0.01 dTau) * f_pure)
     g.q.y = fmaf(c.z, L.f_dust, g.q.y);
     g.zb = (L.inv_dz < 0.f) ? c.w : z_up;                    // +-1e30 when there is no layer beyond
@@ -842,7 +919,7 @@ __device__ __forceinline__ Leg plan_leg(const Lane &L, const DevScene &scene, co
         // (float -> unsigned conversion saturates below at 0)
         const uint32_t px = min(__float2uint_rz(fmaf(L.pxy.x, geo.near_inv_pixel, geo.near_off_x)), static_cast<uint32_t>(geo.near_nx - 1));
         const uint32_t py = min(__float2uint_rz(fmaf(L.pxy.y, geo.near_inv_pixel, geo.near_off_y)), static_cast<uint32_t>(geo.near_ny - 1));
-        g.cell = near[py * geo.near_nx + px];
+        g.cell = lds32(near + 4u * (py * geo.near_nx + px));
         g.cap = __uint_as_float(g.cell & 0xffff0000u);       // +inf: no limit (and every leg takes the reference's cell walk, see cell_walk)
         const float2 sxy = *reinterpret_cast<const float2 *>(reinterpret_cast<const uint8_t *>(strings) + (g.cell & 0xffffu));
         g.o = __fadd2_rn(sxy, make_float2(-L.pxy.x, -L.pxy.y));
@@ -898,13 +975,13 @@ __device__ __forceinline__ void rotate_packed(float cosa, float sina2, float2 &d
 // parks the lane (status kFrozen, the leg's length and string in the state words kPend*) with
 // nothing but the scattering-length draw applied; the slow phase runs the full collision test
 // and either ends the photon there or flies this leg itself (finish_leg) and sends the lane back.
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
-__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a);
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V = 0>
+__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring);
 
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS>
-__device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, const float4 *layers,
-                                               const float4 *strings, const uint32_t *near, const float2 *tilt_dist,
-                                               const float *tilt_corr, uint32_t rng_a, float *st)
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS, int V = 0>
+__device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, uint32_t layers,
+                                               const float4 *strings, uint32_t near, const float2 *tilt_dist,
+                                               const float *tilt_corr, uint32_t rng_a, float *st, float4 *ring)
 {
     const DevMedium &m = scene.medium;
 
@@ -914,7 +991,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
         // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
             L.z_eff = L.pz - tilt_shift(m, tilt_dist, tilt_corr, L.pxy.x, L.pxy.y, L.pz);
-            L.layer = min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
+            L.layer = static_cast<int>(layers) + 16 * min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
         }
         if (ANISO) {
             // R4b: 1/f = (B2-nB)*An/2 (I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx:92-134)
@@ -928,7 +1005,7 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
         L.bud.y = -fast_ln(rng.oc());
         L.rng_x = rng.x;
     }
-    const Leg g = plan_leg<TILT, SAVE_ALL, LOOK_ALWAYS>(L, scene, layers, strings, near);
+    const Leg g = plan_leg<TILT, SAVE_ALL, LOOK_ALWAYS>(L, scene, strings, near);
     // `clearance`: how far the photon may still fly before any string can come within the collision radius, as
     // known from the lane's last look at the collision map minus what it has flown since.  The first leg after each
     // look at the warp state consults the map and sets it; the legs after that one do not look: a leg shorter than
@@ -975,15 +1052,61 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
         clearance = (o2 > 0.f) ? fminf(mufu_sqrt(o2) - R, g.cap) - 0.01f : 0.f;
     }
     clearance -= g.travel;
-    finish_leg<TILT, ANISO, SAVE_ALL, MIXED>(L, g, scene, rng_a);
+    finish_leg<TILT, ANISO, SAVE_ALL, MIXED, V>(L, g, scene, rng_a, ring);
 }
 
 // The rest of the iteration, once the leg is known to be free of DOMs: fly it, then scatter (or go on / end).
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
-__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a)
+// HIST: the last scene.history_entries scatter points of the photon are kept in the lane's ring in HBM (`ring` points at
+// the lane's column of [entry][thread] float4; the rings of all lanes together are a few tens of MB and live in L2):
+// (x, y, z, absorption lengths LEFT); the hit record turns the fourth into "absorption lengths used"
+// (propagation_kernel.c.cl:833-837).
+// The table-maker variant's sink (savePath, propagation_kernel.c.cl:226-304): every step_length metres along the leg
+// the photon adds  weight x angular acceptance x exp(-absorption lengths used so far)  to the bin of the table its
+// position and delay time fall into -- straight into the table in HBM (RED.ADD.F32), no entry buffers.  The
+// absorption used at a sampling point is taken from the leg's own layer (the reference interpolates linearly over a
+// whole multi-layer segment, :296-297; the same within a layer).  A point beyond the table's radius or delay-time
+// range ends the photon.  Returns false when the photon is to be stopped.
+template <bool ANISO>
+__device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, const DevScene &scene)
 {
+    const TabulateArgs &tb = reinterpret_cast<const SmemHeader *>(smem_base())->tab;
+    float d = L.rem;
+    if (d < g.travel) {
+        const float impact_weight = L.weight * table_angular_acceptance(tb, L.dz);
+        // absorption lengths: used up to the start of the leg, and per metre in this layer (the budget of an anisotropic
+        // medium is held scaled during a flight, see advance_photon)
+        const float scale = ANISO ? L.inv_aniso : 1.f;
+        const float depth0 = scene.fixed_abs_lens - L.bud.x * scale;
+        const float per_metre = g.q.y * scale;
+        do {
+            const float x = fmaf(L.dxy.x, d, L.pxy.x), y = fmaf(L.dxy.y, d, L.pxy.y), z = fmaf(L.dz, d, L.pz);
+            float c[5];
+            table_coordinates_4(tb, table_frame(tb, x, y, z, fmaf(L.inv_vg, d, L.t)), c);
+            if (table_out_of_bounds(tb, c)) return false;
+            const uint32_t index = table_bin_index(tb, c);
+            const float w = impact_weight * __expf(-fmaf(per_metre, d, depth0));
+            atomicAdd(tb.table + index, w);
+            if (tb.squared) atomicAdd(tb.squared + index, w * w);
+            d += tb.step_length;
+        } while (d < g.travel);
+    }
+    L.rem = d - g.travel;
+    L.t = fmaf(L.inv_vg, g.travel, L.t);
+    return true;
+}
+
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
+__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring)
+{
+    constexpr bool HIST = (V & kVarHist) != 0, TAB = (V & kVarTab) != 0;
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
+    if (TAB) {
+        if (!sample_leg<ANISO>(L, g, scene)) {
+            L.status = kDead;   // out of the table's range: stop the photon (:770-776); table mode records no photons
+            return;
+        }
+    }
     // ------------------------------------------------------------------ advance
     L.pxy = __ffma2_rn(L.dxy, make_float2(g.travel, g.travel), L.pxy);
     L.pz = fmaf(L.dz, g.travel, L.pz);
@@ -993,7 +1116,7 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
         // the flight goes on (in the neighbouring layer, or past the range limit of the collision
         // map) with what is left of both budgets
         const bool cross = g.d_b <= g.cap;
-        if (cross) L.layer += layer_step(L.inv_dz);
+        if (cross) L.layer += layer_address_step(L.inv_dz);
         L.bud = g.rem;
         if (TILT) L.z_eff = cross ? g.zb : fmaf(L.dz, g.travel, L.z_eff);
         return;
@@ -1001,10 +1124,11 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
     L.bud.x = g.absorbed ? 0.f : g.rem.x;
     if (ANISO) L.bud.x *= L.inv_aniso;
     if (L.bud.x < kEpsilon) {
-        L.status = SAVE_ALL ? kDying : kDead;
+        L.status = (SAVE_ALL && !TAB) ? kDying : kDead;   // (#if defined(SAVE_ALL_PHOTONS) && !defined(TABULATE), :800)
         return;
     }
     // ------------------------------------------------------------------ R9 + R8: scatter
+    if (HIST) ring[static_cast<size_t>(L.scatters % static_cast<uint32_t>(scene.history_entries)) * (static_cast<size_t>(gridDim.x) * kThreads)] = make_float4(L.pxy.x, L.pxy.y, L.pz, L.bud.x);
     if (ANISO) {
         V3 d{L.dxy.x, L.dxy.y, L.dz};
         apply_matrix(m.pre, d);
@@ -1052,35 +1176,54 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
 // Slow phase, for a parked lane: the reference's collision test over the pending leg.  No hit:
 // the leg is flown here (the same code as in the hot loop) and the lane goes back.  Hit: the photon
 // ends at the DOM and is written out.
-template <bool TILT, bool ANISO, bool MIXED>
-__device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, uint32_t rng_a)
+template <bool TILT, bool ANISO, bool MIXED, int V>
+__device__ __noinline__ uint32_t resolve_parked(const DevScene *scene, float *st, uint32_t rng_a, float4 *ring)
 {
+    constexpr bool NONSTOP = (V & kVarNonStop) != 0;
     const SmemLayout &lay = reinterpret_cast<const SmemHeader *>(smem_base())->lay;
     const V3 pos{st[kPx * kThreads], st[kPy * kThreads], st[kPz * kThreads]};
     const V3 dir{st[kDx * kThreads], st[kDy * kThreads], st[kDz * kThreads]};
-    const Collision col = collide(scene, __float_as_int(st[kPendWho * kThreads]), pos, dir, st[kPendTravel * kThreads]);
+    const int who = __float_as_int(st[kPendWho * kThreads]);
+    const float leg = st[kPendTravel * kThreads];
+    // (the test first, the leg's plan after it: nothing but the hit has to survive the call)
+    Collision col{leg, 0, 0, false};
+    if constexpr (!NONSTOP) col = collide<false>(scene, who, pos, dir, leg);
     // the leg again (the plan is a function of the parked state alone)
     const SmemPlan sp = table_plan(lay);
     Lane L;
     load_lane<TILT, ANISO>(L, st);
-    const Leg g = plan_leg<TILT, false, true>(L, *scene, sp.layers, sp.strings, sp.near);
-    if (!col.hit) {
-        L.status = kActive;
-        finish_leg<TILT, ANISO, false, MIXED>(L, g, *scene, rng_a);
-        store_lane<TILT, ANISO>(L, st);
-        return L.status;
+    const uint32_t sbase = smem_address();
+    const Leg g = plan_leg<TILT, false, true>(L, *scene, sp.strings, sbase + lay.off_near);
+    const int layer_index = (L.layer - static_cast<int>(sbase + kSmLayers)) >> 4;
+    if (NONSTOP || col.hit) {
+        // the budgets: distInAbsLens is taken for the unshortened flight (propagation_kernel.c.cl:718)
+        float at_end = g.absorbed ? 0.f : g.rem.x;
+        const bool cross = g.limited && (g.d_b <= g.cap);
+        if (g.limited)
+            at_end = abs_left_at_end_of_flight(sp.layers, scene->medium.z0, scene->medium.h, scene->medium.num_layers,
+                                               cross ? layer_index + layer_step(L.inv_dz) : layer_index, cross ? g.zb : fmaf(L.dz, g.travel, g.zc),
+                                               L.dz, L.inv_dz, g.rem.y, g.rem.x, L.f_sp.x, L.f_dust, L.f_sp.y);
+        if (ANISO) at_end *= L.inv_aniso;
+        if constexpr (NONSTOP) {
+            // record every DOM on the leg, nearest first, then fly the leg
+            After after{-1.f, -1};
+            for (;;) {
+                const Collision c = collide<true>(scene, who, pos, dir, leg, after);
+                if (!c.hit) break;
+                const V3 at{fmaf(dir.x, c.travel, pos.x), fmaf(dir.y, c.travel, pos.y), fmaf(dir.z, c.travel, pos.z)};
+                emit_record(scene, st, at, dir, L.path + c.travel, L.scatters, c.string, c.dom, at_end, false, rng_a);
+                after = After{c.travel, (c.string << 16) | c.dom};
+            }
+        } else {
+            const V3 end{fmaf(dir.x, col.travel, pos.x), fmaf(dir.y, col.travel, pos.y), fmaf(dir.z, col.travel, pos.z)};
+            emit_record(scene, st, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, at_end, false, rng_a);
+            return kDead;
+        }
     }
-    // the budgets: distInAbsLens is taken for the unshortened flight (propagation_kernel.c.cl:718)
-    float at_end = g.absorbed ? 0.f : g.rem.x;
-    const bool cross = g.limited && (g.d_b <= g.cap);
-    if (g.limited)
-        at_end = abs_left_at_end_of_flight(sp.layers, scene->medium.z0, scene->medium.h, scene->medium.num_layers,
-                                           cross ? L.layer + layer_step(L.inv_dz) : L.layer, cross ? g.zb : fmaf(L.dz, g.travel, g.zc),
-                                           L.dz, L.inv_dz, g.rem.y, g.rem.x, L.f_sp.x, L.f_dust, L.f_sp.y);
-    if (ANISO) at_end *= L.inv_aniso;
-    const V3 end{fmaf(dir.x, col.travel, pos.x), fmaf(dir.y, col.travel, pos.y), fmaf(dir.z, col.travel, pos.z)};
-    emit_record(scene, st, end, dir, L.path + col.travel, L.scatters, col.string, col.dom, at_end, false, rng_a);
-    return kDead;
+    L.status = kActive;
+    finish_leg<TILT, ANISO, false, MIXED, V>(L, g, *scene, rng_a, ring);
+    store_lane<TILT, ANISO>(L, st);
+    return L.status;
 }
 
 // Queue fill, by all 32 lanes of the warp at once: the next photons of the warp's step (and of the
@@ -1149,8 +1292,8 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
 
 // A lane takes the photon in queue slot `slot` (four 16-byte chunks): running state into `L`, birth tag (and,
 // save-all, the propagation-stream state) into the lane's tag words.
-template <bool SAVE_ALL>
-__device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *st)
+template <bool SAVE_ALL, bool TAB = false>
+__device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *st, uint32_t layers)
 {
     const float4 c0 = slot[0], c1 = slot[1], c2 = slot[2], c3 = slot[3];
     L.pxy = make_float2(c0.x, c0.y); L.pz = c1.x;
@@ -1160,8 +1303,13 @@ __device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *
     L.path = 0.f;
     L.f_sp = make_float2(c2.x, c2.y); L.f_dust = c2.z;
     L.scatters = 0u;
-    L.layer = __float_as_int(c1.w);
+    L.layer = static_cast<int>(layers) + 16 * __float_as_int(c1.w);
     L.status = kActive;
+    if (TAB) {
+        // (the fourth chunk carries the table-mode values in place of the birth tag, see create_photon)
+        L.t = c3.x; L.inv_vg = c3.y; L.weight = c3.z; L.rem = c3.w;
+        return;
+    }
     tag_word(st, 0) = __float_as_uint(c3.x); tag_word(st, 1) = __float_as_uint(c3.y); tag_word(st, 2) = __float_as_uint(c3.z);
     if (SAVE_ALL) {
         float *ptag = st + kOffPopTag;
@@ -1175,9 +1323,10 @@ __device__ __forceinline__ void take_photon(Lane &L, const float4 *slot, float *
 // collision test (hits are written out), save-all photons that ended are recorded, the queue is
 // refilled, lanes without a photon take one.  Returns the number of idle lanes that ends the next fast
 // phase, or -1 when the warp is done.
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
 __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *warp_region)
 {
+    constexpr bool HIST = (V & kVarHist) != 0, TAB = (V & kVarTab) != 0;
     const LaunchArgs &args = reinterpret_cast<const SmemHeader *>(smem_base())->args;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1188,10 +1337,11 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = __ldg(args.rng_a + gthread);
+    float4 *ring = HIST ? reinterpret_cast<float4 *>(args.history_ring) + gthread : nullptr;
     uint32_t status = __float_as_uint(st[kStatus * kThreads]);
 
     // ---- photons whose next leg may touch a DOM: the full collision test
-    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO, MIXED>(scene, st, rng_a);
+    if (!SAVE_ALL && status == kFrozen) status = resolve_parked<TILT, ANISO, MIXED, V>(scene, st, rng_a, ring);
     // ---- save-all: every photon that ended is recorded with probability `prescale`
     //      (propagation_kernel.c.cl:800-826)
     if (SAVE_ALL && status == kDying) {
@@ -1226,7 +1376,11 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
             *nseg += __float_as_uint(st[kScatters * kThreads]) + 1u;
             Lane L;
             L.rng_x = pack64(st[kRngLo * kThreads], st[kRngHi * kThreads]);
-            take_photon<SAVE_ALL>(L, queue + kQueueChunks * (queued - 1u - rank), st);
+            take_photon<SAVE_ALL, TAB>(L, queue + kQueueChunks * (queued - 1u - rank), st, smem_address() + kSmLayers);
+            if (TAB) {
+                st[(kOffBirthTag + 0 * kThreads)] = L.t; st[(kOffBirthTag + 1 * kThreads)] = L.inv_vg; st[(kOffBirthTag + 2 * kThreads)] = L.weight;
+                st[kPendTravel * kThreads] = L.rem;
+            }
             st[kPx * kThreads] = L.pxy.x; st[kPy * kThreads] = L.pxy.y; st[kPz * kThreads] = L.pz;
             st[kDx * kThreads] = L.dxy.x; st[kDy * kThreads] = L.dxy.y; st[kDz * kThreads] = L.dz;
             st[kAbsLeft * kThreads] = L.bud.x; st[kScaLeft * kThreads] = 0.f; st[kPath * kThreads] = 0.f;
@@ -1246,13 +1400,15 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     __syncwarp();
     if (n_idle == 32) return -1;                    // nothing in flight, nothing queued, nothing to fetch
     // idle lanes remain only when the work has run out: drain
-    return (n_idle > 0) ? n_idle + 1 : (SAVE_ALL ? kIdleLimitSaveAll : kIdleLimit);
+    // (flasher scenes: photons start inside a string's cylinder and park on their first leg -- batch them like save-all does)
+    return (n_idle > 0) ? n_idle + 1 : ((SAVE_ALL || scene->num_generators > 1) ? kIdleLimitSaveAll : kIdleLimit);
 }
 
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 propagate_persistent(const __grid_constant__ DevScene scene, const __grid_constant__ LaunchArgs args, const __grid_constant__ SmemLayout lay)
 {
+    constexpr bool HIST = (V & kVarHist) != 0, TAB = (V & kVarTab) != 0;
     uint8_t *smem = smem_base();
     const DevMedium &m = scene.medium;
     const DevGeometry &geo = scene.geo;
@@ -1263,6 +1419,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
         SmemHeader *hdr = reinterpret_cast<SmemHeader *>(smem);
         hdr->lay = lay;
         hdr->args = args;
+    }
+    if (TAB) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(args.tabulate);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&reinterpret_cast<SmemHeader *>(smem)->tab);
+        for (int i = tid; i < static_cast<int>(sizeof(TabulateArgs) / 4); i += kThreads) dst[i] = __ldg(src + i);
     }
     const SmemPlan sp = table_plan(lay);
 
@@ -1341,12 +1502,15 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     }
 
     // ---- lane and warp state
-    float *st = reinterpret_cast<float *>(smem + lay.off_state) + tid;
-    float *warp_region = reinterpret_cast<float *>(smem + lay.off_queue);
+    float *st = reinterpret_cast<float *>(smem + kSmState) + tid;
+    float *warp_region = reinterpret_cast<float *>(smem + kSmQueue);
+    const uint32_t sbase = smem_address();
+    const uint32_t layers = sbase + kSmLayers, near = sbase + kSmNear;   // (the pixel map is not read in save-all mode)
     const float4 *queue = reinterpret_cast<const float4 *>(warp_region) + warp * (kQueueChunks * 32);
     uint32_t *wctl = reinterpret_cast<uint32_t *>(warp_region + kOffWarpCtl) + warp * kWarpCtlWords;
     const uint32_t gthread = blockIdx.x * kThreads + tid;
     const uint32_t rng_a = args.rng_a[gthread];
+    float4 *ring = HIST ? reinterpret_cast<float4 *>(args.history_ring) + gthread : nullptr;
     {
         const uint64_t x = args.rng_x[gthread];
         st[kRngLo * kThreads] = __uint_as_float(static_cast<uint32_t>(x));
@@ -1361,13 +1525,13 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     __syncthreads();
 
     for (;;) {
-        const int limit = slow_phase<TILT, ANISO, SAVE_ALL, MIXED>(args.scene_dev, st, warp_region);
+        const int limit = slow_phase<TILT, ANISO, SAVE_ALL, MIXED, V>(args.scene_dev, st, warp_region);
         if (limit < 0) break;
         // ---- fast phase: photon state in registers, no calls.  A lane whose photon ended takes the next
         //      one from the warp's queue right here; the phase ends when the queue runs dry, or when
         //      `limit` lanes wait for the slow phase.
         Lane L;
-        load_lane<TILT, ANISO>(L, st);
+        load_lane<TILT, ANISO, TAB>(L, st);
         if (!ANISO) {
             // the unit length of the direction, restored once per fast phase (see rotate_by)
             const float inv = fmaf(L.dxy.x * L.dxy.x + L.dxy.y * L.dxy.y + L.dz * L.dz, -0.5f, 1.5f);
@@ -1389,7 +1553,7 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                         const uint32_t rank = __popc(dead & lanemask_lt());
                         if (L.status == kDead && rank < queued) {
                             tag_word(st, 3) += L.scatters + 1u;   // statistics, kept in shared memory: a register here is a spill
-                            take_photon<SAVE_ALL>(L, queue + kQueueChunks * (queued - 1u - rank), st);
+                            take_photon<SAVE_ALL, TAB>(L, queue + kQueueChunks * (queued - 1u - rank), st, layers);
                         }
                         const uint32_t taken = min(n_dead, queued);
                         queued -= taken;
@@ -1402,15 +1566,15 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             }
             float clearance = 0.f;   // set by the first leg, used by the others (see plan_leg)
             if (L.status == kActive)
-                advance_photon<TILT, ANISO, SAVE_ALL, MIXED, true>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near, sp.tilt_dist,
-                                                                   sp.tilt_corr, rng_a, st);
+                advance_photon<TILT, ANISO, SAVE_ALL, MIXED, true, V>(L, clearance, scene, args.scene_dev, layers, sp.strings, near, sp.tilt_dist,
+                                                                         sp.tilt_corr, rng_a, st, ring);
 #pragma unroll
             for (int leg = 1; leg < ((TILT || ANISO) ? kHotUnrollTilted : kHotUnroll); ++leg)
                 if (L.status == kActive)
-                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED, kLookEveryLeg>(L, clearance, scene, args.scene_dev, sp.layers, sp.strings, sp.near,
-                                                                                sp.tilt_dist, sp.tilt_corr, rng_a, st);
+                    advance_photon<TILT, ANISO, SAVE_ALL, MIXED, kLookEveryLeg, V>(L, clearance, scene, args.scene_dev, layers, sp.strings, near,
+                                                                                      sp.tilt_dist, sp.tilt_corr, rng_a, st, ring);
         }
-        store_lane<TILT, ANISO>(L, st);
+        store_lane<TILT, ANISO, TAB>(L, st);
         __syncwarp();   // every lane has read the control block before lane 0 rewrites it
         if (lane == 0) wctl[kWQueued] = queued;
         __syncwarp();
@@ -1429,11 +1593,11 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
     }
 }
 
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED>
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V = 0>
 int launch_mix(const DevScene &scene, const LaunchArgs &args, int blocks, cudaStream_t stream)
 {
     const SmemLayout lay = plan_smem(scene);
-    auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL, MIXED>;
+    auto kernel = propagate_persistent<TILT, ANISO, SAVE_ALL, MIXED, V>;
     // the attribute belongs to the (function, device) pair and engines on several devices launch from several threads
     // of one process: set it on every launch (a host-side table write, no device work)
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)) != cudaSuccess) return -3;
@@ -1444,26 +1608,38 @@ int launch_mix(const DevScene &scene, const LaunchArgs &args, int blocks, cudaSt
 template <bool TILT, bool ANISO, bool SAVE_ALL>
 int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cudaStream_t stream)
 {
-    // the save-all variants are checkers' tools: no need to specialise them further
-    if constexpr (!SAVE_ALL) {
-        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, SAVE_ALL, true>(scene, args, blocks, stream);
+    if constexpr (SAVE_ALL) {
+        // table-maker variant: save-all scene (no DOMs), fixed number of absorption lengths, four table axes
+        if (args.tabulate) return launch_mix<TILT, ANISO, true, false, kVarTab>(scene, args, blocks, stream);
+        // the save-all variants are checkers' tools: no need to specialise them further
+        if (scene.history_entries > 0) return launch_mix<TILT, ANISO, true, false, kVarHist>(scene, args, blocks, stream);
+        return launch_mix<TILT, ANISO, true, false, 0>(scene, args, blocks, stream);
+    } else {
+        // photon history and StopDetectedPhotons = false: checkers' and event-display options, one generic instantiation
+        if (scene.history_entries > 0 || !scene.stop_detected) {
+            if (scene.history_entries > 0 && !scene.stop_detected) return launch_mix<TILT, ANISO, false, false, kVarHist | kVarNonStop>(scene, args, blocks, stream);
+            if (scene.history_entries > 0) return launch_mix<TILT, ANISO, false, false, kVarHist>(scene, args, blocks, stream);
+#ifdef CLSIMCU_NONSTOP_MIXED
+            if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, false, true, kVarNonStop>(scene, args, blocks, stream);
+#endif
+            return launch_mix<TILT, ANISO, false, false, kVarNonStop>(scene, args, blocks, stream);
+        }
+        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, false, true, 0>(scene, args, blocks, stream);
+        return launch_mix<TILT, ANISO, false, false, 0>(scene, args, blocks, stream);
     }
-    return launch_mix<TILT, ANISO, SAVE_ALL, false>(scene, args, blocks, stream);
 }
 
 } // namespace
 
 bool fast_kernel_supports(const DevScene &scene, const char **why)
 {
-    static const char *k_history = "photon history is only recorded by the reference-order kernel";
-    static const char *k_nonstop = "StopDetectedPhotons=false is only implemented by the reference-order kernel";
     static const char *k_renorm = "non-renormalising direction transforms are only implemented by the reference-order kernel";
     static const char *k_smem = "geometry/medium tables do not fit into shared memory";
     static const char *k_strings = "more than 4094 strings";
-    if (scene.history_entries > 0) { *why = k_history; return false; }
-    if (!scene.save_all && !scene.stop_detected) { *why = k_nonstop; return false; }
+    static const char *k_layers = "more than 255 ice layers";
     if (scene.medium.anisotropy && (!scene.medium.pre_renorm || !scene.medium.post_renorm)) { *why = k_renorm; return false; }
     if (scene.geo.num_strings > 4094) { *why = k_strings; return false; }
+    if (scene.medium.num_layers + 1 > kMaxStagedLayers) { *why = k_layers; return false; }
     if (plan_smem(scene).total + 1024u > kSmemBudget / kBlocksPerSM) { *why = k_smem; return false; }
     return true;
 }

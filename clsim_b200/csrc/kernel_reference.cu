@@ -17,6 +17,7 @@
 
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
+#include "tabulate_device.h"
 
 namespace clsimcu {
 namespace {
@@ -25,7 +26,6 @@ constexpr float kSpeedOfLight = 0.299792458f; // propagation_kernel.h.cl:144-151
 constexpr float kPi = 3.14159265359f;
 constexpr float kEpsilon = 0.00001f;          // propagation_kernel.c.cl:505
 constexpr int kMaxHistory = 32;
-constexpr int kDedupWords = 32;               // non-stopping mode: 1024 strings / DOMs per string
 
 struct Stream {
     uint64_t x;
@@ -311,19 +311,17 @@ __device__ void test_string(const Output &o, const Flight &f, int string, float 
     lo = clampi(lo, 0, layers - 1);
     hi = clampi(hi, 0, layers - 1);
 
-    uint32_t seen[kDedupWords];
-    const bool dedup = !o.scene.stop_detected;
-    if (dedup) for (int i = 0; i < kDedupWords; ++i) seen[i] = 0u;
-
+    // Non-stop mode: the reference keeps a bit mask of the DOMs it has tested (sparse_collision_kernel.c.cl:85-104) because
+    // the z-layer table names a DOM in EVERY layer its sphere touches (two for a DOM that straddles a boundary).  Those
+    // layers are adjacent and a layer holds one DOM at most, so "the same DOM as in the layer before" is the whole
+    // mask -- without the mask's limit on the number of DOMs per string.
     const uint16_t *row = g.layer_to_dom + static_cast<uint32_t>(set) * g.max_layers;
+    int previous = 0xFFFF;
     for (int layer = lo; layer <= hi; ++layer) {
         const int dom = __ldg(row + layer);
         if (dom == 0xFFFF) continue;
-        if (dedup) {
-            const uint32_t bit = 1u << (dom & 31);
-            if (seen[(dom >> 5) & (kDedupWords - 1)] & bit) continue;
-            seen[(dom >> 5) & (kDedupWords - 1)] |= bit;
-        }
+        if (!o.scene.stop_detected && dom == previous) continue;
+        previous = dom;
         float cx, cy, cz;
         dom_centre(g, string, dom, cx, cy, cz);
         const float rx = cx - f.pos.x, ry = cy - f.pos.y, rz = cz - f.pos.z;
@@ -367,17 +365,19 @@ __device__ bool find_collision(const Output &o, const Flight &f, float &length, 
         y0 = clampi(y0, 0, c.num_y - 1);
         x1 = clampi(x1, 0, c.num_x - 1);
         y1 = clampi(y1, 0, c.num_y - 1);
-        uint32_t seen[kDedupWords];
         const bool dedup = !o.scene.stop_detected;
-        if (dedup) for (int i = 0; i < kDedupWords; ++i) seen[i] = 0u;
         for (int cy = y0; cy <= y1; ++cy) {
             for (int cx = x0; cx <= x1; ++cx) {
                 const int string = __ldg(c.cell_to_string + cy * c.num_x + cx);
                 if (string == 0xFFFF) continue;
                 if (dedup) {
-                    const uint32_t bit = 1u << (string & 31);
-                    if (seen[(string >> 5) & (kDedupWords - 1)] & bit) continue;
-                    seen[(string >> 5) & (kDedupWords - 1)] |= bit;
+                    // a string may sit in several cells and must be tested once per segment (the reference's string bit
+                    // mask, :250-269, as intended -- SURVEY quirk 8): skip it if an earlier cell of this walk named it.
+                    // No mask, so no limit on the number of strings.
+                    bool seen = false;
+                    for (int py = y0; py <= cy && !seen; ++py)
+                        for (int px = x0; px <= ((py < cy) ? x1 : cx - 1) && !seen; ++px) seen = __ldg(c.cell_to_string + py * c.num_x + px) == string;
+                    if (seen) continue;
                 }
                 test_string(o, f, string, dir_xy2, length, dist_abs, hit);
             }
@@ -391,79 +391,30 @@ __device__ bool find_collision(const Output &o, const Flight &f, float &length, 
 }
 
 // ---- table-maker variant (-DTABULATE) -------------------------------------------------------------------
-// Coordinates of a point of the photon's path relative to the reference particle
-// (resources/kernels/spherical_coordinates.c.cl, cylindrical_coordinates.c.cl).  OpenCL's dot() of two float4
-// includes the fourth components: zero for the reference vectors, but wavelength x delay time in the impact-angle
-// product (a quirk of the reference, kept).
+// The coordinate and binning code is shared with the fast kernel: tabulate_device.h.  Here: the fifth (impact angle)
+// coordinate, which draws from the work item's stream (spherical_coordinates.c.cl / cylindrical_coordinates.c.cl).
+// OpenCL's dot() of two float4 includes the fourth components: zero for the reference vectors, but wavelength x delay
+// time in the impact-angle product (a quirk of the reference, kept).
 __device__ void table_coordinates(const TabulateArgs &tb, const V3 &p, float t, V3 dir, float wlen, Stream &rng, float c[5])
 {
-    const float px = p.x - tb.ref_pos[0], py = p.y - tb.ref_pos[1], pz = p.z - tb.ref_pos[2], pw = t - tb.ref_pos[3];
-    const float l = ((px * tb.ref_dir[0] + py * tb.ref_dir[1]) + pz * tb.ref_dir[2]) + pw * tb.ref_dir[3];
-    const float rx = px - l * tb.ref_dir[0], ry = py - l * tb.ref_dir[1], rz = pz - l * tb.ref_dir[2], rw = pw - l * tb.ref_dir[3];
-    const float n_rho = sqrtf(rx * rx + ry * ry + rz * rz);
-    const float rho_perp = ((rx * tb.ref_perp[0] + ry * tb.ref_perp[1]) + rz * tb.ref_perp[2]) + rw * tb.ref_perp[3];
+    const TableFrame fr = table_frame(tb, p.x, p.y, p.z, t);
+    table_coordinates_4(tb, fr, c);
+    if (tb.ndim <= 4) return;
+    const float px = fr.px, py = fr.py, pz = fr.pz, pw = fr.pw, l = fr.l, rx = fr.rx, ry = fr.ry, rz = fr.rz, rw = fr.rw;
     if (tb.geometry == 0) {
-        c[0] = sqrtf(px * px + py * py + pz * pz);
-        const float azimuth = (n_rho > 0) ? acosf(rho_perp / n_rho) / (kPi / 180) : 0;
-        if (tb.full_azimuth) {
-            // cross(rho, perpDir) . dir
-            const float cx = ry * tb.ref_perp[2] - rz * tb.ref_perp[1], cy = rz * tb.ref_perp[0] - rx * tb.ref_perp[2],
-                        cz = rx * tb.ref_perp[1] - ry * tb.ref_perp[0];
-            const float sign = (cx * tb.ref_dir[0] + cy * tb.ref_dir[1]) + cz * tb.ref_dir[2];
-            c[1] = (sign > 0) ? 360.f - azimuth : azimuth;
-        } else {
-            c[1] = azimuth;
-        }
-        c[2] = (c[0] > 0) ? (l / c[0]) : 0;
-        c[3] = pw - c[0] * tb.min_inv_group_vel;
-        if (tb.ndim > 4) {
-            const float sina = sqrtf(rng.co());
-            rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
-            c[4] = (c[0] > 0) ? ((((dir.x * px + dir.y * py) + dir.z * pz) + wlen * pw) / c[0]) : 1;
-        }
+        const float sina = sqrtf(rng.co());
+        rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
+        c[4] = (c[0] > 0) ? ((((dir.x * px + dir.y * py) + dir.z * pz) + wlen * pw) / c[0]) : 1;
     } else {
-        c[0] = n_rho;
-        c[1] = (c[0] > 0) ? acosf(rho_perp / c[0]) : 0;
-        c[2] = tb.ref_pos[2] + l * tb.ref_dir[2];
-        c[3] = pw - (l + c[0] * tb.tan_theta_c) * 3.33564095f;   // recip_speedOfLight, propagation_kernel.h.cl:149
-        if (tb.ndim > 4) {
-            const float sina = sqrtf(rng.co());
-            rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
-            // vector from the nominal Cherenkov emission point; (l - rho/tan_thetaC) is a float4 in the reference, component-wise
-            const float k = 1.f / tb.tan_theta_c;
-            const float qx = p.x - (tb.ref_pos[0] + (l - rx * k) * tb.ref_dir[0]), qy = p.y - (tb.ref_pos[1] + (l - ry * k) * tb.ref_dir[1]),
-                        qz = p.z - (tb.ref_pos[2] + (l - rz * k) * tb.ref_dir[2]), qw = t - (tb.ref_pos[3] + (l - rw * k) * tb.ref_dir[3]);
-            const float cdist = sqrtf(qx * qx + qy * qy + qz * qz);
-            c[4] = (cdist > 0) ? ((((dir.x * qx + dir.y * qy) + dir.z * qz) + wlen * qw) / cdist) : 1;
-        }
+        const float sina = sqrtf(rng.co());
+        rotate_by(sqrtf(1 - sina * sina), sina, dir, rng.co());
+        // vector from the nominal Cherenkov emission point; (l - rho/tan_thetaC) is a float4 in the reference, component-wise
+        const float k = 1.f / tb.tan_theta_c;
+        const float qx = p.x - (tb.ref_pos[0] + (l - rx * k) * tb.ref_dir[0]), qy = p.y - (tb.ref_pos[1] + (l - ry * k) * tb.ref_dir[1]),
+                    qz = p.z - (tb.ref_pos[2] + (l - rz * k) * tb.ref_dir[2]), qw = t - (tb.ref_pos[3] + (l - rw * k) * tb.ref_dir[3]);
+        const float cdist = sqrtf(qx * qx + qy * qy + qz * qz);
+        c[4] = (cdist > 0) ? ((((dir.x * qx + dir.y * qy) + dir.z * qz) + wlen * qw) / cdist) : 1;
     }
-}
-
-// getBinIndex (Axes.cxx:71-93) with Axis::GetIndexCode (Axis.cxx:44-60): convert_int_sat_rtn = floor with saturation
-__device__ uint32_t table_bin_index(const TabulateArgs &tb, const float c[5])
-{
-    uint32_t index = 0;
-    for (int i = 0; i < tb.ndim; ++i) {
-        const DevAxis &ax = tb.axes[i];
-        float v = c[i];
-        if (ax.inverse == 1) v = 1.f;
-        else if (ax.inverse == 2) v = sqrtf(v);
-        else if (ax.inverse == 3) v = cbrtf(v);
-        else if (ax.inverse == 4) v = powf(v, ax.inv_power);
-        const float f = floorf(ax.scale * v - ax.offset);
-        int k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f)));
-        k = min(max(k, -1), ax.n_bins) + 1;
-        index += ax.stride * static_cast<uint32_t>(k);
-    }
-    return index;
-}
-
-__device__ float table_angular_acceptance(const TabulateArgs &tb, float x)
-{
-    if (tb.num_angular == 0) return 0.f;
-    float v = tb.angular[tb.num_angular - 1];
-    for (int i = tb.num_angular - 2; i >= 0; --i) v = tb.angular[i] + x * v;
-    return v;
 }
 
 // savePath (propagation_kernel.c.cl:226-304).  The entries go straight into the table in HBM; there is no entry

@@ -179,7 +179,10 @@ int clsimcu_tabulator_create(const clsimcu_config *scene, const clsimcu_tabulato
 
         // the engine behind it: the reference's preamble (…cxx:177-183) as options
         clsimcu_config sc = *scene;
-        sc.kernel_mode = CLSIMCU_KERNEL_REFERENCE;
+        // four-axis tables run on the persistent kernel unless the caller asks for the reference-order twin; the fifth axis
+        // (impact angle) draws two numbers per entry from the work item's stream and stays with the twin
+        sc.kernel_mode = (nd == 4 && scene->kernel_mode == CLSIMCU_KERNEL_FAST) ? CLSIMCU_KERNEL_FAST : CLSIMCU_KERNEL_REFERENCE;
+        if (sc.kernel_mode == CLSIMCU_KERNEL_FAST && sc.rng_a == nullptr) sc.rng_n = 0;   // the engine sizes and seeds its own streams
         sc.enable_double_buffering = 0;
         sc.stop_detected_photons = 0;
         sc.save_all_photons = 1;
@@ -188,7 +191,7 @@ int clsimcu_tabulator_create(const clsimcu_config *scene, const clsimcu_tabulato
         sc.fixed_number_of_absorption_lengths = 42.;
         sc.output_photons_per_workitem = 1;
         std::memset(&sc.geometry, 0, sizeof sc.geometry);
-        if (sc.rng_n == 0) sc.rng_n = sc.max_num_workitems;
+        if (sc.rng_n == 0 && sc.kernel_mode == CLSIMCU_KERNEL_REFERENCE) sc.rng_n = sc.max_num_workitems;
         if (clsimcu_create(&sc, &t->engine) != CLSIMCU_OK) {
             const std::string msg = clsimcu_last_error();
             free_tabulator(t);

@@ -1,0 +1,91 @@
+// tabulate_device.h -- device code of the table-maker variant shared by the two kernels: where a point of a photon's
+// path falls in the table around the reference particle, and what it weighs.
+//
+// Restated from resources/kernels/spherical_coordinates.c.cl, cylindrical_coordinates.c.cl (getCoordinates), the code
+// the reference generates from its Axes (private/clsim/tabulator/Axes.cxx:71-93 getBinIndex, Axis.cxx:44-60
+// GetIndexCode) and I3CLSimFunctionPolynomial.cxx:139-153 (getAngularAcceptance); precise math in both kernels, so
+// that a point lands in the same bin whichever kernel propagated the photon.
+#pragma once
+
+#include <cstdint>
+
+#include "device_scene.h"
+
+namespace clsimcu {
+
+// the point relative to the reference particle: p - ref (with time), its component along the particle's axis, the rest
+struct TableFrame {
+    float px, py, pz, pw, l, rx, ry, rz, rw, n_rho, rho_perp;
+};
+
+__device__ inline TableFrame table_frame(const TabulateArgs &tb, float x, float y, float z, float t)
+{
+    TableFrame f;
+    f.px = x - tb.ref_pos[0]; f.py = y - tb.ref_pos[1]; f.pz = z - tb.ref_pos[2]; f.pw = t - tb.ref_pos[3];
+    f.l = ((f.px * tb.ref_dir[0] + f.py * tb.ref_dir[1]) + f.pz * tb.ref_dir[2]) + f.pw * tb.ref_dir[3];
+    f.rx = f.px - f.l * tb.ref_dir[0]; f.ry = f.py - f.l * tb.ref_dir[1]; f.rz = f.pz - f.l * tb.ref_dir[2]; f.rw = f.pw - f.l * tb.ref_dir[3];
+    f.n_rho = sqrtf(f.rx * f.rx + f.ry * f.ry + f.rz * f.rz);
+    f.rho_perp = ((f.rx * tb.ref_perp[0] + f.ry * tb.ref_perp[1]) + f.rz * tb.ref_perp[2]) + f.rw * tb.ref_perp[3];
+    return f;
+}
+
+// the four coordinates every table has: (r, azimuth, cos polar angle, delay time) or (rho, azimuth, z, delay time)
+__device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFrame &f, float c[5])
+{
+    const float kPiOver180 = 3.14159265359f / 180;
+    if (tb.geometry == 0) {
+        c[0] = sqrtf(f.px * f.px + f.py * f.py + f.pz * f.pz);
+        const float azimuth = (f.n_rho > 0) ? acosf(f.rho_perp / f.n_rho) / kPiOver180 : 0;
+        if (tb.full_azimuth) {
+            // cross(rho, perpDir) . dir
+            const float cx = f.ry * tb.ref_perp[2] - f.rz * tb.ref_perp[1], cy = f.rz * tb.ref_perp[0] - f.rx * tb.ref_perp[2],
+                        cz = f.rx * tb.ref_perp[1] - f.ry * tb.ref_perp[0];
+            const float sign = (cx * tb.ref_dir[0] + cy * tb.ref_dir[1]) + cz * tb.ref_dir[2];
+            c[1] = (sign > 0) ? 360.f - azimuth : azimuth;
+        } else {
+            c[1] = azimuth;
+        }
+        c[2] = (c[0] > 0) ? (f.l / c[0]) : 0;
+        c[3] = f.pw - c[0] * tb.min_inv_group_vel;
+    } else {
+        c[0] = f.n_rho;
+        c[1] = (c[0] > 0) ? acosf(f.rho_perp / c[0]) : 0;
+        c[2] = tb.ref_pos[2] + f.l * tb.ref_dir[2];
+        c[3] = f.pw - (f.l + c[0] * tb.tan_theta_c) * 3.33564095f;   // recip_speedOfLight, propagation_kernel.h.cl:149
+    }
+}
+
+// isOutOfBounds (Axes.cxx:113-123, 151-159)
+__device__ inline bool table_out_of_bounds(const TabulateArgs &tb, const float c[5])
+{
+    return (tb.geometry == 0) ? ((c[3] > tb.max3) || (c[0] > tb.max0)) : (c[3] > tb.max3);
+}
+
+// getBinIndex (Axes.cxx:71-93) with Axis::GetIndexCode (Axis.cxx:44-60): convert_int_sat_rtn = floor with saturation
+__device__ inline uint32_t table_bin_index(const TabulateArgs &tb, const float c[5])
+{
+    uint32_t index = 0;
+    for (int i = 0; i < tb.ndim; ++i) {
+        const DevAxis &ax = tb.axes[i];
+        float v = c[i];
+        if (ax.inverse == 1) v = 1.f;
+        else if (ax.inverse == 2) v = sqrtf(v);
+        else if (ax.inverse == 3) v = cbrtf(v);
+        else if (ax.inverse == 4) v = powf(v, ax.inv_power);
+        const float f = floorf(ax.scale * v - ax.offset);
+        int k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f)));
+        k = min(max(k, -1), ax.n_bins) + 1;
+        index += ax.stride * static_cast<uint32_t>(k);
+    }
+    return index;
+}
+
+__device__ inline float table_angular_acceptance(const TabulateArgs &tb, float x)
+{
+    if (tb.num_angular == 0) return 0.f;
+    float v = tb.angular[tb.num_angular - 1];
+    for (int i = tb.num_angular - 2; i >= 0; --i) v = tb.angular[i] + x * v;
+    return v;
+}
+
+} // namespace clsimcu

@@ -177,9 +177,9 @@ void I3CLSimStepToPhotonConverterCUDA::Flatten()
     std::memset(&c, 0, sizeof(c));
     c.struct_size = static_cast<int32_t>(sizeof(clsimcu_config));
     c.device = device_;
-    // photon history and non-stopping detection are implemented by the reference-order kernel only (slow path, still on the GPU)
-    const bool fastCapable = (photonHistoryEntries_ == 0) && (stopDetectedPhotons_ || saveAllPhotons_);
-    c.kernel_mode = (useNativeMath_ && fastCapable) ? CLSIMCU_KERNEL_FAST : CLSIMCU_KERNEL_REFERENCE;
+    // every option of the path runs on the fast kernel (photon history, non-stopping detection included); the
+    // reference-order kernel is the precise-math twin (useNativeMath = false)
+    c.kernel_mode = useNativeMath_ ? CLSIMCU_KERNEL_FAST : CLSIMCU_KERNEL_REFERENCE;
     c.enable_double_buffering = enableDoubleBuffering_ ? 1 : 0;
     c.stop_detected_photons = stopDetectedPhotons_ ? 1 : 0;
     c.save_all_photons = saveAllPhotons_ ? 1 : 0;

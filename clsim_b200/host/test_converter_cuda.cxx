@@ -213,9 +213,9 @@ static void test_on_device()
     }
     CHECK(on_sphere);
 
-    // photon history through the precise (reference-order) kernel
+    // photon history (on the fast kernel: native math requested)
     {
-        I3CLSimCUDADevice precise = {0, 1024, true}; // native math requested: history still routes to the reference-order kernel
+        I3CLSimCUDADevice precise = {0, 1024, true};
         auto hc = I3CLSimModuleHelper::initializeCUDA(precise, 5, make_ring_geometry(5.0), medium, bias, gens, false, false, true, false, 0.01, NAN,
                                                       5.0, /*history*/ 4, 0);
         hc->EnqueueSteps(make_steps(1024, 200, 7, 77), 7);

