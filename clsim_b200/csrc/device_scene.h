@@ -8,6 +8,8 @@
 
 namespace clsimcu {
 
+constexpr int kTiltLutMaxCells = 64;   // fast kernel: cells of the interval grid of the ice-tilt table
+
 constexpr int kMaxWlenGenerators = 8;
 constexpr int kMaxSubdetectors = 9; // sparse_collision_kernel.c.cl:455-457
 constexpr uint32_t kFastKernelStepIndexBits = 27; // the fast kernel tags photons with (step index | creating lane << 27)
@@ -42,6 +44,10 @@ struct DevMedium {
     int mix_folded; // the five constants above are set (f_sl in (0,1), g != 0)
     int tilt_nd, tilt_nz;
     float tilt_z0, tilt_dz, tilt_inv_dz, tilt_lnx, tilt_lny;
+    // fast kernel: the interval of the tilt table along the tilt direction from a uniform grid (cell = scale * nr + offset),
+    // at most one interior node per cell; tilt_lut_n == 0: no grid (nodes too close together), compare against the nodes
+    float tilt_lut_scale, tilt_lut_offset;
+    int tilt_lut_n;
     int anisotropy, pre_renorm, post_renorm;
     float l[3], rl[3], azx, azy, neg_azy, B2;
     float pre[9], post[9];

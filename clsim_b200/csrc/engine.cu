@@ -311,6 +311,22 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
     dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
     dm.tilt_inv_dz = (m.tilt_nd > 0 && m.tilt_dz != 0.f) ? 1.f / m.tilt_dz : 0.f;
+    dm.tilt_lut_n = 0; dm.tilt_lut_scale = dm.tilt_lut_offset = 0.f;
+    if (m.tilt_nd >= 4) {
+        // interior nodes dist[1 .. nd-2]; cell 0 is everything below dist[1], cell c >= 1 starts at dist[1] + (c - 1) * width
+        double gap = std::numeric_limits<double>::infinity();
+        for (int i = 2; i <= m.tilt_nd - 2; ++i) gap = std::min(gap, static_cast<double>(m.tilt_dist[i]) - m.tilt_dist[i - 1]);
+        const double span = static_cast<double>(m.tilt_dist[m.tilt_nd - 2]) - m.tilt_dist[1];
+        if (gap > 0. && std::isfinite(gap)) {
+            const double width = gap * 0.99;   // below the smallest gap, with room for the margin the kernel widens a cell by: never two nodes in a cell
+            const int cells = static_cast<int>(std::ceil(span / width)) + 2;
+            if (cells <= kTiltLutMaxCells) {
+                dm.tilt_lut_n = cells;
+                dm.tilt_lut_scale = static_cast<float>(1. / width);
+                dm.tilt_lut_offset = static_cast<float>(1. - m.tilt_dist[1] / width);
+            }
+        }
+    }
     dm.anisotropy = m.anisotropy; dm.pre_renorm = m.pre_renorm; dm.post_renorm = m.post_renorm;
     for (int i = 0; i < 3; ++i) { dm.l[i] = m.l[i]; dm.rl[i] = m.rl[i]; }
     dm.azx = m.azx; dm.azy = m.azy; dm.neg_azy = m.neg_azy; dm.B2 = m.B2;

@@ -143,6 +143,9 @@ enum Status : uint32_t { kActive = 0, kFrozen = 1, kDying = 2, kDead = 3 };
 // (kept out of the default instantiation: ptxas allocates registers over the whole call graph, and the slow path's extra
 // live values cost the hot loop spills)
 constexpr int kVarHist = 1, kVarTab = 2, kVarNonStop = 4;
+// ... and one frequent specialisation: direction transforms of the form [[a, c, 0], [d, b, 0], [0, 0, e]] (the ppc anisotropy:
+// a stretch in the horizontal plane and along z), five multiplications instead of nine and five constants instead of nine
+constexpr int kVarBlockTransforms = 8;
 
 // ---- approximate MUFU wrappers ---------------------------------------------------------------
 __device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -241,7 +244,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
         cells += s.geo.grids[i].num_x * s.geo.grids[i].num_y;
     }
     at = align16(at + cells * 2);
-    L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 32);   // + 8 search keys
+    L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 8 * kTiltLutMaxCells);   // + the interval grid
     L.off_tilt_corr = at; at = align16(at + s.medium.tilt_nd * s.medium.tilt_nz * 4);
     L.off_gen0 = at;
     L.gen0_n = 0;
@@ -431,14 +434,14 @@ __device__ __forceinline__ float tilt_shift(const DevMedium &m, const float2 *di
     const float above = zr - static_cast<float>(k);
     const float below = 1.f - above;
     const float nr = m.tilt_lnx * x + m.tilt_lny * y;
-    // j = first interval end in [1, nd-1] with nr < dist[j], or nd-1 (the reference's scan, :178-186).  The
-    // distances ascend, so j = 1 + the number of interior nodes not above nr; up to 8 nodes (the ice models have 6)
-    // sit in two float4 behind the table, padded with +inf
+    // j = first interval end in [1, nd-1] with nr < dist[j], or nd-1 (the reference's scan, :178-186).  The distances
+    // ascend, so j = 1 + the number of interior nodes not above nr: read from a uniform grid over nr whose cells hold at
+    // most one node each -- (nodes below the cell, the node inside it) -- behind the table; see the staging code
     int j = 1;
-    if (m.tilt_nd <= 8) {
-        const float4 *keys = reinterpret_cast<const float4 *>(dist + m.tilt_nd + (m.tilt_nd & 1));
-        const float4 k0 = keys[0], k1 = keys[1];
-        j += ((nr < k0.y) ? 0 : 1) + ((nr < k0.z) ? 0 : 1) + ((nr < k0.w) ? 0 : 1) + ((nr < k1.x) ? 0 : 1) + ((nr < k1.y) ? 0 : 1) + ((nr < k1.z) ? 0 : 1);
+    if (m.tilt_lut_n > 0) {
+        const float2 *lut = dist + m.tilt_nd + (m.tilt_nd & 1);
+        const float2 e = lut[min(max(__float2int_rz(fmaf(nr, m.tilt_lut_scale, m.tilt_lut_offset)), 0), m.tilt_lut_n - 1)];
+        j = __float_as_int(e.x) + ((nr < e.y) ? 0 : 1);
     } else {
 #pragma unroll 1
         for (int i = 1; i < m.tilt_nd - 1; ++i) j += (nr < dist[i].x) ? 0 : 1;
@@ -460,6 +463,16 @@ __device__ __forceinline__ void apply_matrix(const float *M, V3 &d)
     const float nz = M[6] * d.x + M[7] * d.y + M[8] * d.z;
     const float inv = mufu_rsqrt(nx * nx + ny * ny + nz * nz);
     d.x = nx * inv; d.y = ny * inv; d.z = nz * inv;
+}
+
+// ... for a matrix whose z row and column are (0, 0, e): I3CLSimVectorTransformMatrix.cxx:101-133 with the zeros left out
+__device__ __forceinline__ void apply_block_matrix(const float *M, float2 &dxy, float &dz)
+{
+    // (scalar on purpose: the constants sit in uniform registers, packing them into register pairs costs more than it saves)
+    const float nx = fmaf(M[1], dxy.y, M[0] * dxy.x), ny = fmaf(M[4], dxy.y, M[3] * dxy.x), nz = M[8] * dz;
+    const float inv = mufu_rsqrt(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+    dxy = __fmul2_rn(make_float2(nx, ny), make_float2(inv, inv));
+    dz = nz * inv;
 }
 
 // ---- R6: DOM collision, restated for SIMT -----------------------------------------------------
@@ -971,24 +984,13 @@ __device__ __forceinline__ void rotate_packed(float cosa, float sina2, float2 &d
     }
 }
 
-// One iteration of the hot loop: move the photon to its next event.  A leg that might touch a DOM
-// parks the lane (status kFrozen, the leg's length and string in the state words kPend*) with
-// nothing but the scattering-length draw applied; the slow phase runs the full collision test
-// and either ends the photon there or flies this leg itself (finish_leg) and sends the lane back.
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V = 0>
-__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring);
-
-template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS, int V = 0>
-__device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, uint32_t layers,
-                                               const float4 *strings, uint32_t near, const float2 *tilt_dist,
-                                               const float *tilt_corr, uint32_t rng_a, float *st, float4 *ring)
+// R5, first part: a new flight (after creation or a scatter) draws its length in scattering lengths and, where the ice
+// is tilted or anisotropic, takes the layer and the absorption scaling of its direction (propagation_kernel.c.cl:599-631).
+template <bool TILT, bool ANISO>
+__device__ __forceinline__ void start_flight(Lane &L, const DevMedium &m, uint32_t layers, const float2 *tilt_dist, const float *tilt_corr, uint32_t rng_a)
 {
-    const DevMedium &m = scene.medium;
-
-    // ------------------------------------------------------------------ R5: next event of the flight
     if (L.bud.y <= 0.f) {
         Mwc rng{L.rng_x, rng_a};
-        // a new flight (after creation or a scatter): propagation_kernel.c.cl:599-631
         if (TILT) {
             L.z_eff = L.pz - tilt_shift(m, tilt_dist, tilt_corr, L.pxy.x, L.pxy.y, L.pz);
             L.layer = static_cast<int>(layers) + 16 * min(max(__float2int_rz((L.z_eff - m.z0) * m.inv_h), 0), m.num_layers - 1);
@@ -1005,6 +1007,23 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
         L.bud.y = -fast_ln(rng.oc());
         L.rng_x = rng.x;
     }
+}
+
+// One iteration of the hot loop: move the photon to its next event.  A leg that might touch a DOM
+// parks the lane (status kFrozen, the leg's length and string in the state words kPend*) with
+// nothing but the scattering-length draw applied; the slow phase runs the full collision test
+// and either ends the photon there or flies this leg itself (finish_leg) and sends the lane back.
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V = 0>
+__device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring);
+
+template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS, int V = 0>
+__device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, uint32_t layers,
+                                               const float4 *strings, uint32_t near, const float2 *tilt_dist,
+                                               const float *tilt_corr, uint32_t rng_a, float *st, float4 *ring)
+{
+    const DevMedium &m = scene.medium;
+
+    start_flight<TILT, ANISO>(L, m, layers, tilt_dist, tilt_corr, rng_a);
     const Leg g = plan_leg<TILT, SAVE_ALL, LOOK_ALWAYS>(L, scene, strings, near);
     // `clearance`: how far the photon may still fly before any string can come within the collision radius, as
     // known from the lane's last look at the collision map minus what it has flown since.  The first leg after each
@@ -1067,46 +1086,82 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
 // whole multi-layer segment, :296-297; the same within a layer).  A point beyond the table's radius or delay-time
 // range ends the photon.  Returns false when the photon is to be stopped.
 template <bool ANISO>
-__device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, const DevScene &scene)
+__device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, bool flying, const DevScene &scene)
 {
+    // WARP-COOPERATIVE: called by all 32 lanes, converged.  Lane i has n_i sampling points on its leg (0 for a lane
+    // without a flying photon); the warp's points are numbered through and handed out 32 at a time, so that a lane with
+    // a long leg does not hold the others (a lane-private loop ran at 4 of 32 lanes: ncu r02_v34_tab).  A point needs
+    // the twelve numbers of its leg: fetched from the owning lane by shuffle.
     const TabulateArgs &tb = reinterpret_cast<const SmemHeader *>(smem_base())->tab;
-    float d = L.rem;
-    if (d < g.travel) {
-        const float impact_weight = L.weight * table_angular_acceptance(tb, L.dz);
-        // absorption lengths: used up to the start of the leg, and per metre in this layer (the budget of an anisotropic
-        // medium is held scaled during a flight, see advance_photon)
-        const float scale = ANISO ? L.inv_aniso : 1.f;
-        const float depth0 = scene.fixed_abs_lens - L.bud.x * scale;
-        const float per_metre = g.q.y * scale;
-        do {
-            const float x = fmaf(L.dxy.x, d, L.pxy.x), y = fmaf(L.dxy.y, d, L.pxy.y), z = fmaf(L.dz, d, L.pz);
-            float c[5];
-            table_coordinates_4(tb, table_frame(tb, x, y, z, fmaf(L.inv_vg, d, L.t)), c);
-            if (table_out_of_bounds(tb, c)) return false;
-            const uint32_t index = table_bin_index(tb, c);
-            const float w = impact_weight * __expf(-fmaf(per_metre, d, depth0));
+    const int lane = threadIdx.x & 31;
+    const float step = tb.step_length;
+    int n = 0;
+    if (flying && L.rem < g.travel) {
+        n = __float2int_rz((g.travel - L.rem) * mufu_rcp(step));
+        n += (fmaf(static_cast<float>(n), step, L.rem) < g.travel) ? 1 : 0;          // d_k = rem + k step < travel for k < n
+        n -= (n > 0 && !(fmaf(static_cast<float>(n - 1), step, L.rem) < g.travel)) ? 1 : 0;
+    }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - n;
+    // per leg: weight x angular acceptance; absorption lengths used up to the start of the leg and per metre in this layer
+    // (the budget of an anisotropic medium is held scaled during a flight, see start_flight)
+    const float scale = ANISO ? L.inv_aniso : 1.f;
+    const float impact_weight = flying ? L.weight * table_angular_acceptance(tb, L.dz) : 0.f;
+    const float depth0 = scene.fixed_abs_lens - L.bud.x * scale;
+    const float per_metre = flying ? g.q.y * scale : 0.f;
+    unsigned stopped = 0u;
+    for (int base = 0; base < total; base += 32) {
+        const int mine = base + lane;
+        // owner of point `mine`: the first lane whose inclusive count exceeds it
+        int src = 0;
+#pragma unroll
+        for (int h = 16; h > 0; h >>= 1) {
+            const int below = __shfl_sync(0xffffffffu, incl, src + h - 1);
+            if (below <= mine) src += h;
+        }
+        src = min(src, 31);
+        const bool valid = mine < total;
+        const int k = mine - __shfl_sync(0xffffffffu, excl, src);
+        const float d = fmaf(static_cast<float>(k), step, __shfl_sync(0xffffffffu, L.rem, src));
+        const float x = fmaf(__shfl_sync(0xffffffffu, L.dxy.x, src), d, __shfl_sync(0xffffffffu, L.pxy.x, src));
+        const float y = fmaf(__shfl_sync(0xffffffffu, L.dxy.y, src), d, __shfl_sync(0xffffffffu, L.pxy.y, src));
+        const float z = fmaf(__shfl_sync(0xffffffffu, L.dz, src), d, __shfl_sync(0xffffffffu, L.pz, src));
+        const float t = fmaf(__shfl_sync(0xffffffffu, L.inv_vg, src), d, __shfl_sync(0xffffffffu, L.t, src));
+        const float w0 = __shfl_sync(0xffffffffu, impact_weight, src);
+        const float depth = fmaf(__shfl_sync(0xffffffffu, per_metre, src), d, __shfl_sync(0xffffffffu, depth0, src));
+        float c[4];
+        table_coordinates_4(tb, table_frame(tb, x, y, z, t), c);
+        // a point beyond the table's radius or delay-time range ends the photon (:770-776).  Both coordinates only grow
+        // along a leg once they are out (the distance to the reference point is convex along a line, the photon is at
+        // least as slow as the table's fastest light), so the points after it on the leg are out as well: none is added.
+        const bool out = valid && table_out_of_bounds(tb, c);
+        if (valid && !out) {
+            const uint32_t index = table_bin_index_4(tb, c);
+            const float w = w0 * __expf(-depth);
             atomicAdd(tb.table + index, w);
             if (tb.squared) atomicAdd(tb.squared + index, w * w);
-            d += tb.step_length;
-        } while (d < g.travel);
+        }
+        stopped |= __reduce_or_sync(0xffffffffu, out ? (1u << src) : 0u);
     }
-    L.rem = d - g.travel;
-    L.t = fmaf(L.inv_vg, g.travel, L.t);
-    return true;
+    if (flying) {
+        L.rem = fmaf(static_cast<float>(n), step, L.rem) - g.travel;
+        L.t = fmaf(L.inv_vg, g.travel, L.t);
+    }
+    return ((stopped >> lane) & 1u) == 0u;
 }
 
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
 __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring)
 {
-    constexpr bool HIST = (V & kVarHist) != 0, TAB = (V & kVarTab) != 0;
+    constexpr bool HIST = (V & kVarHist) != 0, TAB = (V & kVarTab) != 0, BLOCK = (V & kVarBlockTransforms) != 0;
     const DevMedium &m = scene.medium;
     Mwc rng{L.rng_x, rng_a};
-    if (TAB) {
-        if (!sample_leg<ANISO>(L, g, scene)) {
-            L.status = kDead;   // out of the table's range: stop the photon (:770-776); table mode records no photons
-            return;
-        }
-    }
     // ------------------------------------------------------------------ advance
     L.pxy = __ffma2_rn(L.dxy, make_float2(g.travel, g.travel), L.pxy);
     L.pz = fmaf(L.dz, g.travel, L.pz);
@@ -1130,9 +1185,13 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
     // ------------------------------------------------------------------ R9 + R8: scatter
     if (HIST) ring[static_cast<size_t>(L.scatters % static_cast<uint32_t>(scene.history_entries)) * (static_cast<size_t>(gridDim.x) * kThreads)] = make_float4(L.pxy.x, L.pxy.y, L.pz, L.bud.x);
     if (ANISO) {
-        V3 d{L.dxy.x, L.dxy.y, L.dz};
-        apply_matrix(m.pre, d);
-        L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+        if constexpr (BLOCK) {
+            apply_block_matrix(m.pre, L.dxy, L.dz);
+        } else {
+            V3 d{L.dxy.x, L.dxy.y, L.dz};
+            apply_matrix(m.pre, d);
+            L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+        }
     }
     const float ru = __uint2float_rz(rng.next());   // the draw, not yet scaled by 2^-32 (the MIXED constants carry the scale)
     float cs;
@@ -1163,9 +1222,13 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
     // (the samplers stay within [-1, 1] up to the rounding of the approximate exp2 / reciprocal: sin^2 saturates at 0)
     rotate_packed(cs, __saturatef(fmaf(-cs, cs, 1.f)), L.dxy, L.dz, rng.next());
     if (ANISO) {
-        V3 d{L.dxy.x, L.dxy.y, L.dz};
-        apply_matrix(m.post, d);
-        L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+        if constexpr (BLOCK) {
+            apply_block_matrix(m.post, L.dxy, L.dz);
+        } else {
+            V3 d{L.dxy.x, L.dxy.y, L.dz};
+            apply_matrix(m.post, d);
+            L.dxy = make_float2(d.x, d.y); L.dz = d.z;
+        }
     }
     L.inv_dz = raw_inv_dz(L.dz);
     L.bud.y = 0.f;
@@ -1438,9 +1501,21 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             const float here = __ldg(m.tilt_dist + i);
             sp.tilt_dist[i] = make_float2(here, (i > 0) ? 1.f / (here - __ldg(m.tilt_dist + i - 1)) : 0.f);
         }
-        if (tid < 8) {
-            float *keys = reinterpret_cast<float *>(sp.tilt_dist + m.tilt_nd + (m.tilt_nd & 1));
-            keys[tid] = (tid >= 1 && tid <= m.tilt_nd - 2) ? __ldg(m.tilt_dist + tid) : __int_as_float(0x7f800000);
+        // the interval grid (see tilt_shift): cell 0 is everything below dist[1], cell c >= 1 starts at dist[1] + (c - 1) w, the
+        // last one has no upper end; w is below the smallest gap between nodes (host), so a cell -- widened by a margin that
+        // covers the rounding of the cell index -- holds one node at most
+        for (int c = tid; c < m.tilt_lut_n; c += kThreads) {
+            float2 *lut = sp.tilt_dist + m.tilt_nd + (m.tilt_nd & 1);
+            const double w = 1.0 / static_cast<double>(m.tilt_lut_scale), d1 = static_cast<double>(__ldg(m.tilt_dist + 1)), margin = 1e-3 * w;
+            const double lo = d1 + (c - 1) * w - margin, hi = d1 + c * w + margin;
+            int below = 1;
+            float inside = __int_as_float(0x7f800000);
+            for (int i = 1; i <= m.tilt_nd - 2; ++i) {
+                const float d = __ldg(m.tilt_dist + i);
+                if (c > 0 && static_cast<double>(d) < lo) ++below;
+                else if (c == m.tilt_lut_n - 1 || static_cast<double>(d) <= hi) inside = fminf(inside, d);
+            }
+            lut[c] = make_float2(__int_as_float(below), inside);
         }
         for (int i = tid; i < m.tilt_nd * m.tilt_nz; i += kThreads) sp.tilt_corr[i] = __ldg(m.tilt_corr + i);
     }
@@ -1564,6 +1639,27 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                     if (n_waiting + static_cast<int>(n_dead) >= limit) break;
                 }
             }
+            if constexpr (TAB) {
+                // table mode: no DOMs, no collision map; plan, sample the leg (all lanes together, see sample_leg), fly it
+#pragma unroll 1
+                for (int leg = 0; leg < kHotUnroll; ++leg) {
+                    const bool flying = L.status == kActive;
+                    Leg g;
+                    g.travel = 0.f; g.q = make_float2(0.f, 0.f);
+                    if (flying) {
+                        start_flight<TILT, ANISO>(L, m, layers, sp.tilt_dist, sp.tilt_corr, rng_a);
+                        g = plan_leg<TILT, true, false>(L, scene, sp.strings, near);
+                    }
+                    __syncwarp();
+                    const bool goes_on = sample_leg<ANISO>(L, g, flying, scene);
+                    if (flying) {
+                        if (goes_on) finish_leg<TILT, ANISO, SAVE_ALL, MIXED, V>(L, g, scene, rng_a, ring);
+                        else L.status = kDead;   // out of the table's range: the photon is stopped; table mode records no photons
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             float clearance = 0.f;   // set by the first leg, used by the others (see plan_leg)
             if (L.status == kActive)
                 advance_photon<TILT, ANISO, SAVE_ALL, MIXED, true, V>(L, clearance, scene, args.scene_dev, layers, sp.strings, near, sp.tilt_dist,
@@ -1624,7 +1720,14 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
 #endif
             return launch_mix<TILT, ANISO, false, false, kVarNonStop>(scene, args, blocks, stream);
         }
-        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, false, true, 0>(scene, args, blocks, stream);
+        if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) {
+            if constexpr (ANISO) {
+                const float *a = scene.medium.pre, *b = scene.medium.post;
+                if (a[2] == 0.f && a[5] == 0.f && a[6] == 0.f && a[7] == 0.f && b[2] == 0.f && b[5] == 0.f && b[6] == 0.f && b[7] == 0.f)
+                    return launch_mix<TILT, ANISO, false, true, kVarBlockTransforms>(scene, args, blocks, stream);
+            }
+            return launch_mix<TILT, ANISO, false, true, 0>(scene, args, blocks, stream);
+        }
         return launch_mix<TILT, ANISO, false, false, 0>(scene, args, blocks, stream);
     }
 }

@@ -55,6 +55,26 @@ __device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFr
     }
 }
 
+// ... of a four-axis table, unrolled (the coordinates stay in registers)
+__device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float c[4])
+{
+    uint32_t index = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const DevAxis &ax = tb.axes[i];
+        float v = c[i];
+        if (ax.inverse == 1) v = 1.f;
+        else if (ax.inverse == 2) v = sqrtf(v);
+        else if (ax.inverse == 3) v = cbrtf(v);
+        else if (ax.inverse == 4) v = powf(v, ax.inv_power);
+        const float f = floorf(ax.scale * v - ax.offset);
+        int k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f)));
+        k = min(max(k, -1), ax.n_bins) + 1;
+        index += ax.stride * static_cast<uint32_t>(k);
+    }
+    return index;
+}
+
 // isOutOfBounds (Axes.cxx:113-123, 151-159)
 __device__ inline bool table_out_of_bounds(const TabulateArgs &tb, const float c[5])
 {
