@@ -144,6 +144,7 @@ struct LaunchArgs {
     uint64_t *rng_tag_x;       // optional (save-all replay): per record, creation and propagation RNG states
     uint32_t *rng_tag_a;
     int count_stats;
+    uint32_t step_chunks;      // fast kernel: parts a step is cut into when work is handed out (set by launch_fast_kernel)
     const TabulateArgs *tabulate;  // reference-order kernel only: table-maker variant (device pointer) or nullptr
 };
 

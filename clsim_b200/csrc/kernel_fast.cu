@@ -1317,12 +1317,20 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
             uint32_t idx = 0;
             if (lane == 0) idx = atomicAdd(args.work_counter, 1u);
             idx = __shfl_sync(0xffffffffu, idx, 0);
+            // a unit of work is one of `step_chunks` equal parts of a step (1 for bunches that fill the device many times
+            // over; small bunches are cut finer so that no warp ends up with twice the photons of its neighbours)
+            const uint32_t chunks = args.step_chunks, part = idx % chunks;
+            idx /= chunks;
             if (idx >= args.num_steps) { w_more = false; break; }
             __syncwarp();
             if (lane < 12) wstep[lane] = __ldg(reinterpret_cast<const uint32_t *>(args.steps) + static_cast<size_t>(idx) * 12 + lane);
             __syncwarp();
             w_step_index = idx;
             w_left = wstep[8];
+            if (chunks > 1u) {
+                const unsigned long long n = w_left;
+                w_left = static_cast<uint32_t>(n * (part + 1u) / chunks) - static_cast<uint32_t>(n * part / chunks);
+            }
             if (lane == 0) {
                 const V3 axis = step_axis(__uint_as_float(wstep[4]), __uint_as_float(wstep[5]));
                 wstep[12] = __float_as_uint(axis.x);
@@ -1768,17 +1776,25 @@ int launch_fast_kernel(const DevScene &scene, const LaunchArgs &args, int grid_b
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (args.num_steps == 0) return 0;
     if (args.num_steps > (1u << kStepIndexBits)) return -1;
+    LaunchArgs chunked = args;
+    {
+        // fewer than 8 steps per resident warp: cut the steps into parts (see fill_queue)
+        const uint32_t warps = static_cast<uint32_t>(grid_blocks) * kWarpsPerBlock;
+        uint32_t chunks = 1;
+        while (chunks < 8u && static_cast<unsigned long long>(args.num_steps) * chunks < 8ull * warps) chunks *= 2u;
+        chunked.step_chunks = chunks;
+    }
     const bool tilt = scene.medium.tilt_nd > 0, aniso = scene.medium.anisotropy != 0;
     if (scene.save_all) {
-        if (tilt && aniso) return launch_variant<true, true, true>(scene, args, grid_blocks, stream);
-        if (tilt) return launch_variant<true, false, true>(scene, args, grid_blocks, stream);
-        if (aniso) return launch_variant<false, true, true>(scene, args, grid_blocks, stream);
-        return launch_variant<false, false, true>(scene, args, grid_blocks, stream);
+        if (tilt && aniso) return launch_variant<true, true, true>(scene, chunked, grid_blocks, stream);
+        if (tilt) return launch_variant<true, false, true>(scene, chunked, grid_blocks, stream);
+        if (aniso) return launch_variant<false, true, true>(scene, chunked, grid_blocks, stream);
+        return launch_variant<false, false, true>(scene, chunked, grid_blocks, stream);
     }
-    if (tilt && aniso) return launch_variant<true, true, false>(scene, args, grid_blocks, stream);
-    if (tilt) return launch_variant<true, false, false>(scene, args, grid_blocks, stream);
-    if (aniso) return launch_variant<false, true, false>(scene, args, grid_blocks, stream);
-    return launch_variant<false, false, false>(scene, args, grid_blocks, stream);
+    if (tilt && aniso) return launch_variant<true, true, false>(scene, chunked, grid_blocks, stream);
+    if (tilt) return launch_variant<true, false, false>(scene, chunked, grid_blocks, stream);
+    if (aniso) return launch_variant<false, true, false>(scene, chunked, grid_blocks, stream);
+    return launch_variant<false, false, false>(scene, chunked, grid_blocks, stream);
 }
 
 } // namespace clsimcu
