@@ -1136,13 +1136,13 @@ __device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, bool flying, c
         const float w0 = __shfl_sync(0xffffffffu, impact_weight, src);
         const float depth = fmaf(__shfl_sync(0xffffffffu, per_metre, src), d, __shfl_sync(0xffffffffu, depth0, src));
         float c[4];
-        table_coordinates_4(tb, table_frame(tb, x, y, z, t), c);
+        table_coordinates_4<true>(tb, table_frame<true>(tb, x, y, z, t), c);
         // a point beyond the table's radius or delay-time range ends the photon (:770-776).  Both coordinates only grow
         // along a leg once they are out (the distance to the reference point is convex along a line, the photon is at
         // least as slow as the table's fastest light), so the points after it on the leg are out as well: none is added.
         const bool out = valid && table_out_of_bounds(tb, c);
         if (valid && !out) {
-            const uint32_t index = table_bin_index_4(tb, c);
+            const uint32_t index = table_bin_index_4<true>(tb, c);
             const float w = w0 * __expf(-depth);
             atomicAdd(tb.table + index, w);
             if (tb.squared) atomicAdd(tb.squared + index, w * w);
@@ -1636,7 +1636,8 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
                         const uint32_t rank = __popc(dead & lanemask_lt());
                         if (L.status == kDead && rank < queued) {
                             tag_word(st, 3) += L.scatters + 1u;   // statistics, kept in shared memory: a register here is a spill
-                            take_photon<SAVE_ALL, TAB>(L, queue + kQueueChunks * (queued - 1u - rank), st, layers);
+                            // (the layer table's address is derived again here rather than kept alive across the loop: a spill otherwise)
+                            take_photon<SAVE_ALL, TAB>(L, queue + kQueueChunks * (queued - 1u - rank), st, smem_address() + kSmLayers);
                         }
                         const uint32_t taken = min(n_dead, queued);
                         queued -= taken;

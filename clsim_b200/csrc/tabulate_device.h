@@ -13,29 +13,57 @@
 
 namespace clsimcu {
 
+// FAST = true (the persistent kernel): special-function-unit root and reciprocal (2^-22 relative) and a polynomial arc
+// cosine (Abramowitz & Stegun 4.4.46, |error| < 2e-8 rad) in place of the correctly rounded library functions, which are
+// 60 % of the table-maker kernel's instructions (ncu r02_v35_tab).  A point within ~1e-6 of a bin edge can land in the
+// neighbouring bin; the reference-order kernel (FAST = false) keeps the precise forms and stays comparable with the oracle
+// bin by bin.
+template <bool FAST> __device__ __forceinline__ float tab_sqrt(float x)
+{
+    if (FAST) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    return sqrtf(x);
+}
+template <bool FAST> __device__ __forceinline__ float tab_div(float a, float b)
+{
+    if (FAST) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return a * r; }
+    return a / b;
+}
+template <bool FAST> __device__ __forceinline__ float tab_acos(float x)
+{
+    if (!FAST) return acosf(x);
+    const float a = fminf(fabsf(x), 1.f);
+    float p = -0.0012624911f;
+    p = fmaf(p, a, 0.0066700901f); p = fmaf(p, a, -0.0170881256f); p = fmaf(p, a, 0.0308918810f); p = fmaf(p, a, -0.0501743046f);
+    p = fmaf(p, a, 0.0889789874f); p = fmaf(p, a, -0.2145988016f); p = fmaf(p, a, 1.5707963050f);
+    const float r = tab_sqrt<true>(1.f - a) * p;
+    return (x < 0.f) ? 3.14159265359f - r : r;
+}
+
 // the point relative to the reference particle: p - ref (with time), its component along the particle's axis, the rest
 struct TableFrame {
     float px, py, pz, pw, l, rx, ry, rz, rw, n_rho, rho_perp;
 };
 
+template <bool FAST = false>
 __device__ inline TableFrame table_frame(const TabulateArgs &tb, float x, float y, float z, float t)
 {
     TableFrame f;
     f.px = x - tb.ref_pos[0]; f.py = y - tb.ref_pos[1]; f.pz = z - tb.ref_pos[2]; f.pw = t - tb.ref_pos[3];
     f.l = ((f.px * tb.ref_dir[0] + f.py * tb.ref_dir[1]) + f.pz * tb.ref_dir[2]) + f.pw * tb.ref_dir[3];
     f.rx = f.px - f.l * tb.ref_dir[0]; f.ry = f.py - f.l * tb.ref_dir[1]; f.rz = f.pz - f.l * tb.ref_dir[2]; f.rw = f.pw - f.l * tb.ref_dir[3];
-    f.n_rho = sqrtf(f.rx * f.rx + f.ry * f.ry + f.rz * f.rz);
+    f.n_rho = tab_sqrt<FAST>(f.rx * f.rx + f.ry * f.ry + f.rz * f.rz);
     f.rho_perp = ((f.rx * tb.ref_perp[0] + f.ry * tb.ref_perp[1]) + f.rz * tb.ref_perp[2]) + f.rw * tb.ref_perp[3];
     return f;
 }
 
 // the four coordinates every table has: (r, azimuth, cos polar angle, delay time) or (rho, azimuth, z, delay time)
+template <bool FAST = false>
 __device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFrame &f, float c[5])
 {
     const float kPiOver180 = 3.14159265359f / 180;
     if (tb.geometry == 0) {
-        c[0] = sqrtf(f.px * f.px + f.py * f.py + f.pz * f.pz);
-        const float azimuth = (f.n_rho > 0) ? acosf(f.rho_perp / f.n_rho) / kPiOver180 : 0;
+        c[0] = tab_sqrt<FAST>(f.px * f.px + f.py * f.py + f.pz * f.pz);
+        const float azimuth = (f.n_rho > 0) ? (FAST ? tab_acos<FAST>(tab_div<FAST>(f.rho_perp, f.n_rho)) * (1.f / kPiOver180) : acosf(f.rho_perp / f.n_rho) / kPiOver180) : 0;
         if (tb.full_azimuth) {
             // cross(rho, perpDir) . dir
             const float cx = f.ry * tb.ref_perp[2] - f.rz * tb.ref_perp[1], cy = f.rz * tb.ref_perp[0] - f.rx * tb.ref_perp[2],
@@ -45,17 +73,18 @@ __device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFr
         } else {
             c[1] = azimuth;
         }
-        c[2] = (c[0] > 0) ? (f.l / c[0]) : 0;
+        c[2] = (c[0] > 0) ? tab_div<FAST>(f.l, c[0]) : 0;
         c[3] = f.pw - c[0] * tb.min_inv_group_vel;
     } else {
         c[0] = f.n_rho;
-        c[1] = (c[0] > 0) ? acosf(f.rho_perp / c[0]) : 0;
+        c[1] = (c[0] > 0) ? tab_acos<FAST>(tab_div<FAST>(f.rho_perp, c[0])) : 0;
         c[2] = tb.ref_pos[2] + f.l * tb.ref_dir[2];
         c[3] = f.pw - (f.l + c[0] * tb.tan_theta_c) * 3.33564095f;   // recip_speedOfLight, propagation_kernel.h.cl:149
     }
 }
 
 // ... of a four-axis table, unrolled (the coordinates stay in registers)
+template <bool FAST = false>
 __device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float c[4])
 {
     uint32_t index = 0;
@@ -64,7 +93,7 @@ __device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float
         const DevAxis &ax = tb.axes[i];
         float v = c[i];
         if (ax.inverse == 1) v = 1.f;
-        else if (ax.inverse == 2) v = sqrtf(v);
+        else if (ax.inverse == 2) v = tab_sqrt<FAST>(v);
         else if (ax.inverse == 3) v = cbrtf(v);
         else if (ax.inverse == 4) v = powf(v, ax.inv_power);
         const float f = floorf(ax.scale * v - ax.offset);
