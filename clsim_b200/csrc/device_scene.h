@@ -44,6 +44,7 @@ struct DevMedium {
     int mix_folded; // the five constants above are set (f_sl in (0,1), g != 0)
     int tilt_nd, tilt_nz;
     float tilt_z0, tilt_dz, tilt_inv_dz, tilt_lnx, tilt_lny;
+    float tilt_zr_offset;                  // fast kernel: -tilt_z0 / tilt_dz, so that the z node index is one FMA
     // fast kernel: the interval of the tilt table along the tilt direction from a uniform grid (cell = scale * nr + offset),
     // at most one interior node per cell; tilt_lut_n == 0: no grid (nodes too close together), compare against the nodes
     float tilt_lut_scale, tilt_lut_offset;

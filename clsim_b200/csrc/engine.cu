@@ -311,6 +311,7 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     dm.tilt_nd = m.tilt_nd; dm.tilt_nz = m.tilt_nz;
     dm.tilt_z0 = m.tilt_z0; dm.tilt_dz = m.tilt_dz; dm.tilt_lnx = m.tilt_lnx; dm.tilt_lny = m.tilt_lny;
     dm.tilt_inv_dz = (m.tilt_nd > 0 && m.tilt_dz != 0.f) ? 1.f / m.tilt_dz : 0.f;
+    dm.tilt_zr_offset = (m.tilt_nd > 0 && m.tilt_dz != 0.f) ? static_cast<float>(-static_cast<double>(m.tilt_z0) / static_cast<double>(m.tilt_dz)) : 0.f;
     dm.tilt_lut_n = 0; dm.tilt_lut_scale = dm.tilt_lut_offset = 0.f;
     if (m.tilt_nd >= 4) {
         // interior nodes dist[1 .. nd-2]; cell 0 is everything below dist[1], cell c >= 1 starts at dist[1] + (c - 1) * width

@@ -211,7 +211,7 @@ struct SmemPlan {
     uint16_t *cells;         // concatenated grids
     uint32_t *near;          // xy pixel map, see device_scene.h
     float2 *tilt_dist;       // [tilt_nd] (distance along the tilt direction, 1 / (this - previous)); ice tilt only
-    float *tilt_corr;        // [tilt_nd][tilt_nz] z corrections
+    float4 *tilt_corr;       // [tilt_nd - 1][tilt_nz - 1] cells of the correction table: (lower column, upper column, their steps to the next z node)
 };
 
 __host__ __device__ constexpr uint32_t align16(uint32_t v) { return (v + 15u) & ~15u; }
@@ -245,7 +245,7 @@ __host__ SmemLayout plan_smem(const DevScene &s)
     }
     at = align16(at + cells * 2);
     L.off_tilt_dist = at; at = align16(at + (s.medium.tilt_nd + (s.medium.tilt_nd & 1)) * 8 + 8 * kTiltLutMaxCells);   // + the interval grid
-    L.off_tilt_corr = at; at = align16(at + s.medium.tilt_nd * s.medium.tilt_nz * 4);
+    L.off_tilt_corr = at; at = align16(at + (s.medium.tilt_nd > 1 ? (s.medium.tilt_nd - 1) * (s.medium.tilt_nz - 1) * 16 : 0));
     L.off_gen0 = at;
     L.gen0_n = 0;
     if (s.num_generators >= 1 && (s.generators[0].kind == CLSIMCU_WLEN_INTERP_EQUAL || s.generators[0].kind == CLSIMCU_WLEN_INTERP_UNEQUAL) &&
@@ -281,7 +281,7 @@ __device__ __forceinline__ SmemPlan table_plan(const SmemLayout &lay)
     sp.cells = reinterpret_cast<uint16_t *>(smem + lay.off_cells);
     sp.near = reinterpret_cast<uint32_t *>(smem + lay.off_near);
     sp.tilt_dist = reinterpret_cast<float2 *>(smem + lay.off_tilt_dist);
-    sp.tilt_corr = reinterpret_cast<float *>(smem + lay.off_tilt_corr);
+    sp.tilt_corr = reinterpret_cast<float4 *>(smem + lay.off_tilt_corr);
     return sp;
 }
 
@@ -425,18 +425,21 @@ __device__ __forceinline__ void dom_centre(const DevGeometry &g, int string, int
     z = __ldg(g.tmpl_z + at);
 }
 
-// R4a (I3CLSimScalarFieldIceTiltZShift.cxx:145-216); both tables in shared memory, the reciprocal of every
-// distance interval precomputed, the interval found without a data-dependent loop
-__device__ __forceinline__ float tilt_shift(const DevMedium &m, const float2 *dist, const float *corr, float x, float y, float z)
+// R4a (I3CLSimScalarFieldIceTiltZShift.cxx:145-216): the z correction, interpolated linearly between the z nodes of two
+// neighbouring columns of the tilt table and then between the columns.  Restated for few instructions: the table sits in
+// shared memory as one float4 per (column interval, z interval) -- the two columns' values at the lower z node and their
+// steps to the upper one -- so the z interpolation of both columns is one LDS.128 and one packed FMA; the column interval
+// comes from a uniform grid over the distance along the tilt direction (see the staging code), its reciprocal width from
+// the distance table.  Same piecewise-bilinear function as the reference's, different rounding in the last bits.
+__device__ __forceinline__ float tilt_shift(const DevMedium &m, const float2 *dist, const float4 *corr, float x, float y, float z)
 {
-    const float zr = (z - m.tilt_z0) * m.tilt_inv_dz;
+    const float zr = fmaf(z, m.tilt_inv_dz, m.tilt_zr_offset);
     const int k = min(max(__float2int_rd(zr), 0), m.tilt_nz - 2);
     const float above = zr - static_cast<float>(k);
-    const float below = 1.f - above;
     const float nr = m.tilt_lnx * x + m.tilt_lny * y;
     // j = first interval end in [1, nd-1] with nr < dist[j], or nd-1 (the reference's scan, :178-186).  The distances
     // ascend, so j = 1 + the number of interior nodes not above nr: read from a uniform grid over nr whose cells hold at
-    // most one node each -- (nodes below the cell, the node inside it) -- behind the table; see the staging code
+    // most one node each -- (nodes below the cell, the node inside it) -- behind the table
     int j = 1;
     if (m.tilt_lut_n > 0) {
         const float2 *lut = dist + m.tilt_nd + (m.tilt_nd & 1);
@@ -448,12 +451,9 @@ __device__ __forceinline__ float tilt_shift(const DevMedium &m, const float2 *di
     }
     const float2 here = dist[j];
     const float w_lo = (here.x - nr) * here.y;
-    const float w_hi = 1.f - w_lo;
-    const float *lo_row = corr + (j - 1) * m.tilt_nz + k;
-    const float *hi_row = lo_row + m.tilt_nz;
-    const float v_lo = lo_row[1] * above + lo_row[0] * below;
-    const float v_hi = hi_row[1] * above + hi_row[0] * below;
-    return v_hi * w_hi + v_lo * w_lo;
+    const float4 c = corr[(j - 1) * (m.tilt_nz - 1) + k];
+    const float2 v = __ffma2_rn(make_float2(c.z, c.w), make_float2(above, above), make_float2(c.x, c.y));   // (lower, upper column) at z
+    return fmaf(w_lo, v.x - v.y, v.y);
 }
 
 __device__ __forceinline__ void apply_matrix(const float *M, V3 &d)
@@ -828,11 +828,14 @@ template <bool TILT, bool ANISO, bool TAB = false> __device__ __forceinline__ vo
     if (ANISO) st[kInvAniso * kThreads] = L.inv_aniso;
 }
 
-// Second look at a leg the 2-D cylinder test could not rule out, still in the hot loop (one leg in ~600 gets here,
-// four in five of them leave again): the part of the leg inside the cylinder around string `who` covers a short
-// range in z; only if a DOM of that string sits within om_radius of that range can the leg touch it.  The z-layer
-// table of the string's set names a DOM in every layer its sphere touches (the table builder guarantees it), so the
-// layers the range covers name the candidates.  Conservative: the margins cover the rounding of the approximate root.
+// Second look at a leg the 2-D cylinder test could not rule out, still in the hot loop (one leg in ~600 gets here): the
+// reference's string test (sparse_collision_kernel.c.cl:107-192) with approximate arithmetic and margins, deciding only
+// whether the leg MAY enter a DOM of string `who`.  The z-layer table of the string's set names a DOM in every layer its
+// sphere touches, so the layers the leg covers name the candidates; a candidate counts when the leg reaches its sphere
+// (oversized, flattened by the pancake factor) from outside, with margins that cover the rounding of the approximate root.
+// Nine in ten of the legs that a mere "a DOM is near in z" test parked were false alarms (hits are one leg in 30 000);
+// photons that start inside a DOM (flashers) leave it without a visit to the slow phase.
+#ifdef CLSIMCU_Z_RANGE_PRETEST
 __device__ __noinline__ bool dom_within_reach(const DevScene *scene, int who, float z, float dz, float travel, float t, float dxy2, float out2)
 {
     const SmemPlan sp = table_plan(reinterpret_cast<const SmemHeader *>(smem_base())->lay);
@@ -858,6 +861,37 @@ __device__ __noinline__ bool dom_within_reach(const DevScene *scene, int who, fl
         if (dom == 0xFFFF) continue;
         const float zd = __ldg(geo.tmpl_z + first + static_cast<uint32_t>(dom));
         if ((zd >= zlo - geo.om_radius) && (zd <= zhi + geo.om_radius)) return true;
+    }
+    return false;
+}
+#endif
+__device__ __noinline__ bool dom_may_be_hit(const DevScene *scene, int who, float px, float py, float pz, float dx, float dy, float dz, float travel)
+{
+    const SmemPlan sp = table_plan(reinterpret_cast<const SmemHeader *>(smem_base())->lay);
+    const DevGeometry &geo = scene->geo;
+    const float4 set = sp.sets[sp.string_set[who]];
+    const int nl = static_cast<int>(set.z);
+    const float margin = 2e-3f;   // metres; far above the rounding of a root of a number of the size of (leg length)^2
+    const float z_end = fmaf(dz, travel + margin, pz);
+    const int l0 = __float2int_rz((fminf(pz, z_end) - margin - set.x) * set.y), l1 = __float2int_rz((fmaxf(pz, z_end) + margin - set.x) * set.y);
+    const int la = min(max(l0, 0), nl - 1), lb = min(max(l1, 0), nl - 1);
+    const uint16_t *row = sp.layer_to_dom + static_cast<int>(set.w);
+    const float r_om2 = geo.om_radius * geo.om_radius;
+    for (int l = la; l <= lb; ++l) {
+        const int dom = row[l];
+        if (dom == 0xFFFF) continue;
+        float qx, qy, qz;
+        dom_centre(geo, who, dom, qx, qy, qz);
+        const float rx = qx - px, ry = qy - py, rz = qz - pz;
+        const float along = fmaf(rx, dx, fmaf(ry, dy, rz * dz));
+        const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+        const float disc = fmaf(along, along, r_om2 - r2);
+        const float tol = fmaf(1e-5f, r2, 1e-4f);                     // cancellation in along^2 - r^2
+        if (disc < -tol) continue;                                     // the line misses the sphere
+        const float entry = along - mufu_sqrt(fmaxf(disc, 0.f)) * scene->inv_pancake_factor;
+        // the reference lets a photon that starts inside (or beyond) a sphere leave it: entry < 0 is no hit (quirk 9)
+        if (entry < -margin - tol || entry > travel + margin + tol) continue;
+        return true;
     }
     return false;
 }
@@ -987,7 +1021,7 @@ __device__ __forceinline__ void rotate_packed(float cosa, float sina2, float2 &d
 // R5, first part: a new flight (after creation or a scatter) draws its length in scattering lengths and, where the ice
 // is tilted or anisotropic, takes the layer and the absorption scaling of its direction (propagation_kernel.c.cl:599-631).
 template <bool TILT, bool ANISO>
-__device__ __forceinline__ void start_flight(Lane &L, const DevMedium &m, uint32_t layers, const float2 *tilt_dist, const float *tilt_corr, uint32_t rng_a)
+__device__ __forceinline__ void start_flight(Lane &L, const DevMedium &m, uint32_t layers, const float2 *tilt_dist, const float4 *tilt_corr, uint32_t rng_a)
 {
     if (L.bud.y <= 0.f) {
         Mwc rng{L.rng_x, rng_a};
@@ -1019,7 +1053,7 @@ __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, bool LOOK_ALWAYS, int V = 0>
 __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const DevScene &scene, const DevScene *scene_dev, uint32_t layers,
                                                const float4 *strings, uint32_t near, const float2 *tilt_dist,
-                                               const float *tilt_corr, uint32_t rng_a, float *st, float4 *ring)
+                                               const float4 *tilt_corr, uint32_t rng_a, float *st, float4 *ring)
 {
     const DevMedium &m = scene.medium;
 
@@ -1056,7 +1090,11 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
                 }
 #endif
 #ifndef CLSIMCU_NO_Z_PRETEST
+#ifdef CLSIMCU_Z_RANGE_PRETEST
                 if (walk || dom_within_reach(scene_dev, cell_string(g.cell), L.pz, L.dz, g.travel, t, dxy2, out2))
+#else
+                if (walk || dom_may_be_hit(scene_dev, cell_string(g.cell), L.pxy.x, L.pxy.y, L.pz, L.dxy.x, L.dxy.y, L.dz, g.travel))
+#endif
 #endif
                 {
                     L.status = kFrozen;
@@ -1471,8 +1509,7 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
     __syncwarp();
     if (n_idle == 32) return -1;                    // nothing in flight, nothing queued, nothing to fetch
     // idle lanes remain only when the work has run out: drain
-    // (flasher scenes: photons start inside a string's cylinder and park on their first leg -- batch them like save-all does)
-    return (n_idle > 0) ? n_idle + 1 : ((SAVE_ALL || scene->num_generators > 1) ? kIdleLimitSaveAll : kIdleLimit);
+    return (n_idle > 0) ? n_idle + 1 : (SAVE_ALL ? kIdleLimitSaveAll : kIdleLimit);
 }
 
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
@@ -1525,7 +1562,12 @@ propagate_persistent(const __grid_constant__ DevScene scene, const __grid_consta
             }
             lut[c] = make_float2(__int_as_float(below), inside);
         }
-        for (int i = tid; i < m.tilt_nd * m.tilt_nz; i += kThreads) sp.tilt_corr[i] = __ldg(m.tilt_corr + i);
+        for (int i = tid; i < (m.tilt_nd - 1) * (m.tilt_nz - 1); i += kThreads) {
+            const int j = i / (m.tilt_nz - 1), k = i - j * (m.tilt_nz - 1);   // column interval [j, j + 1], z interval [k, k + 1]
+            const float lo0 = __ldg(m.tilt_corr + j * m.tilt_nz + k), lo1 = __ldg(m.tilt_corr + j * m.tilt_nz + k + 1);
+            const float hi0 = __ldg(m.tilt_corr + (j + 1) * m.tilt_nz + k), hi1 = __ldg(m.tilt_corr + (j + 1) * m.tilt_nz + k + 1);
+            sp.tilt_corr[i] = make_float4(lo0, hi0, lo1 - lo0, hi1 - hi0);
+        }
     }
     if (lay.gen0_n) {
         const DevWlenGenerator &g0 = scene.generators[0];

@@ -17,6 +17,18 @@ for name in ("spice_mie", "spice_lea"):
             eng.enqueue(steps.muon_track_steps(n, photons_per_step=50, seed=1), 1)
             r = eng.get_result()
             print(name, mode, "hits", len(r.photons))
+    # the fast kernel's rare variants: non-stop detection, photon history (with and without stopping), both together
+    for stop, hist in ((False, 0), (True, 3), (False, 2)):
+        opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n, rng_seed=6, stop_detected_photons=stop, photon_history_entries=hist, output_photons_per_workitem=4)
+        with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
+            eng.enqueue(steps.muon_track_steps(n, photons_per_step=50, seed=5), 3)
+            r = eng.get_result()
+            print(name, "fast stop", stop, "history", hist, "hits", len(r.photons))
+    # a bunch small enough to be cut into step parts
+    opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=64, rng_seed=7)
+    with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
+        eng.enqueue(steps.muon_track_steps(64, photons_per_step=333, seed=6), 4)
+        print(name, "small bunch hits", len(eng.get_result().photons))
     opt = sc.options(kernel_mode=KERNEL_FAST, stop_detected_photons=False, save_all_photons=True, save_all_photons_prescale=0.01, max_num_workitems=n, rng_seed=4)
     with capi.Engine(sc.medium, None, sc.generators, sc.bias, opt) as eng:
         eng.enqueue(steps.muon_track_steps(n, photons_per_step=20, seed=2), 2)
@@ -39,5 +51,10 @@ medium = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_lea", useTiltIf
 tab = tabulator.I3CLSimStepToTableConverter(0, axes, 0, True, medium, None, math.pi * 0.1651 ** 2, ice.GetIceCubeDOMAcceptance(), ang, 3, maxNumWorkitems=256)
 tab.EnqueueSteps(steps.point_source_steps(256, 5, seed=3), (0, 0, 0, 0, 0, 0, 1))
 tab.Finish()
-print("table sum", float(tab.GetTable()[0].sum()))
+print("table sum (persistent kernel)" if tab.kernelMode == KERNEL_FAST else "table sum", float(tab.GetTable()[0].sum()))
+tab.close()
+tab = tabulator.I3CLSimStepToTableConverter(0, axes, 0, True, medium, None, math.pi * 0.1651 ** 2, ice.GetIceCubeDOMAcceptance(), ang, 3, maxNumWorkitems=256, kernelMode=KERNEL_REFERENCE)
+tab.EnqueueSteps(steps.point_source_steps(256, 5, seed=3), (0, 0, 0, 0, 0, 0, 1))
+tab.Finish()
+print("table sum (reference-order kernel)", float(tab.GetTable()[0].sum()))
 print("sanitize smoke: done")
