@@ -314,7 +314,7 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
             dist.barrier(group=gloo)
 
     # ---------------- (a) strong scaling -------------------------------------------------------------------------
-    total_steps = 8 * bunch_steps
+    total_steps = 16 * bunch_steps   # (16 pieces at most per rank: the size of the meta record below)
     series = steps.muon_bundle_steps(total_steps, num_muons=100, seed=3)   # the same series on every rank (seeded)
     shard = split_steps(series, world)[rank]
     pieces = [shard[i:i + bunch_steps] for i in range(0, len(shard), bunch_steps)]

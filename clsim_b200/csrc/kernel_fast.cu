@@ -1112,11 +1112,6 @@ __device__ __forceinline__ void advance_photon(Lane &L, float &clearance, const 
     finish_leg<TILT, ANISO, SAVE_ALL, MIXED, V>(L, g, scene, rng_a, ring);
 }
 
-// The rest of the iteration, once the leg is known to be free of DOMs: fly it, then scatter (or go on / end).
-// HIST: the last scene.history_entries scatter points of the photon are kept in the lane's ring in HBM (`ring` points at
-// the lane's column of [entry][thread] float4; the rings of all lanes together are a few tens of MB and live in L2):
-// (x, y, z, absorption lengths LEFT); the hit record turns the fourth into "absorption lengths used"
-// (propagation_kernel.c.cl:833-837).
 // The table-maker variant's sink (savePath, propagation_kernel.c.cl:226-304): every step_length metres along the leg
 // the photon adds  weight x angular acceptance x exp(-absorption lengths used so far)  to the bin of the table its
 // position and delay time fall into -- straight into the table in HBM (RED.ADD.F32), no entry buffers.  The
@@ -1194,6 +1189,11 @@ __device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, bool flying, c
     return ((stopped >> lane) & 1u) == 0u;
 }
 
+// The rest of the iteration, once the leg is known to be free of DOMs: fly it, then scatter (or go on / end).
+// HIST: the last scene.history_entries scatter points of the photon are kept in the lane's ring in HBM (`ring` points at
+// the lane's column of [entry][thread] float4; the rings of all lanes together are a few tens of MB and live in L2):
+// (x, y, z, absorption lengths LEFT); the hit record turns the fourth into "absorption lengths used"
+// (propagation_kernel.c.cl:833-837).
 template <bool TILT, bool ANISO, bool SAVE_ALL, bool MIXED, int V>
 __device__ __forceinline__ void finish_leg(Lane &L, const Leg &g, const DevScene &scene, uint32_t rng_a, float4 *ring)
 {
@@ -1766,9 +1766,6 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
         if (scene.history_entries > 0 || !scene.stop_detected) {
             if (scene.history_entries > 0 && !scene.stop_detected) return launch_mix<TILT, ANISO, false, false, kVarHist | kVarNonStop>(scene, args, blocks, stream);
             if (scene.history_entries > 0) return launch_mix<TILT, ANISO, false, false, kVarHist>(scene, args, blocks, stream);
-#ifdef CLSIMCU_NONSTOP_MIXED
-            if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) return launch_mix<TILT, ANISO, false, true, kVarNonStop>(scene, args, blocks, stream);
-#endif
             return launch_mix<TILT, ANISO, false, false, kVarNonStop>(scene, args, blocks, stream);
         }
         if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) {
