@@ -109,12 +109,12 @@ struct DevScene {
 // Per-launch arguments.
 // Table-maker variant of the reference-order kernel (-DTABULATE, propagation_kernel.c.cl:226-304): the binning
 // code the reference generates from its Axes (private/clsim/tabulator/Axes.cxx:71-93, Axis.cxx:44-60) as data.
-struct DevAxis {
+struct alignas(16) DevAxis {
     float scale, offset;   // index = clamp(floor(scale * inverse_transform(x) - offset), -1, n_bins) + 1
     int n_bins;
+    uint32_t stride;       // (the four numbers every point needs: one 16-byte load)
     int inverse;           // 0: x (linear, power 1)   1: constant 1 (power 0)   2: sqrt   3: cbrt   4: pow(x, inv_power)
     float inv_power;
-    uint32_t stride;
 };
 struct TabulateArgs {
     int geometry, ndim, full_azimuth;

@@ -83,7 +83,9 @@ __device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFr
     }
 }
 
-// ... of a four-axis table, unrolled (the coordinates stay in registers)
+// ... of a four-axis table, unrolled (the coordinates stay in registers).  FAST: the axes of the tables in use are linear
+// or quadratic (inverse transform: identity or root) -- selected without a branch; cube roots and general powers take the
+// library functions behind a branch that is uniform over the warp (the axes are the table's, not the point's).
 template <bool FAST = false>
 __device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float c[4])
 {
@@ -92,12 +94,20 @@ __device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float
     for (int i = 0; i < 4; ++i) {
         const DevAxis &ax = tb.axes[i];
         float v = c[i];
-        if (ax.inverse == 1) v = 1.f;
-        else if (ax.inverse == 2) v = tab_sqrt<FAST>(v);
-        else if (ax.inverse == 3) v = cbrtf(v);
-        else if (ax.inverse == 4) v = powf(v, ax.inv_power);
+        if (FAST) {
+            const int kind = ax.inverse;
+            if (kind >= 3) v = (kind == 3) ? cbrtf(v) : powf(v, ax.inv_power);
+            else v = (kind == 2) ? tab_sqrt<true>(v) : ((kind == 1) ? 1.f : v);
+        } else {
+            if (ax.inverse == 1) v = 1.f;
+            else if (ax.inverse == 2) v = sqrtf(v);
+            else if (ax.inverse == 3) v = cbrtf(v);
+            else if (ax.inverse == 4) v = powf(v, ax.inv_power);
+        }
         const float f = floorf(ax.scale * v - ax.offset);
-        int k = (f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f)));
+        // convert_int_sat_rtn: NaN -> 0, saturation (cvt.rmi.s32.f32 does exactly that)
+        int k = FAST ? __float2int_rd(ax.scale * v - ax.offset)
+                     : ((f != f) ? 0 : ((f >= 2147483648.f) ? 2147483647 : ((f <= -2147483648.f) ? (-2147483647 - 1) : static_cast<int>(f))));
         k = min(max(k, -1), ax.n_bins) + 1;
         index += ax.stride * static_cast<uint32_t>(k);
     }
