@@ -114,3 +114,118 @@ def test_guide_table_and_forward_scan_find_the_bin_of_the_linear_scan(mie):
     for r in rs:
         c = min(int(np.float32(r) * np.float32(cells)), cells - 1)
         assert linear_scan(r, int(guide[c])) == linear_scan(r) == int(np.searchsorted(cum[1:n - 1], r, side="left"))
+
+
+# ---- round 2 re-formulations ----------------------------------------------------------------------------------------
+
+def _reference_tilt_shift(t, x, y, z):
+    """I3CLSimScalarFieldIceTiltZShift.cxx:145-216 in double."""
+    dist, zc, corr = t["distancesFromOriginAlongTilt"], t["zCoordinates"], t["zCorrections"]
+    az = t["directionOfTiltAzimuth"]
+    lnx, lny = np.cos(az), np.sin(az)
+    z0, dz = zc[0], zc[1] - zc[0]
+    zr = (z - z0) / dz
+    k = np.clip(np.floor(zr).astype(int), 0, len(zc) - 2)
+    above = zr - k
+    nr = lnx * x + lny * y
+    out = np.zeros_like(x)
+    for i in range(len(x)):
+        for j in range(1, len(dist)):
+            if nr[i] < dist[j] or j == len(dist) - 1:
+                w_lo = (dist[j] - nr[i]) / (dist[j] - dist[j - 1])
+                v_lo = corr[j - 1][k[i] + 1] * above[i] + corr[j - 1][k[i]] * (1 - above[i])
+                v_hi = corr[j][k[i] + 1] * above[i] + corr[j][k[i]] * (1 - above[i])
+                out[i] = v_hi * (1 - w_lo) + v_lo * w_lo
+                break
+    return out, nr
+
+
+def test_tilt_interval_grid_and_cells_equal_the_reference_interpolation():
+    """kernel_fast.cu tilt_shift: the column interval from a uniform grid over the distance along the tilt direction (cells of
+    at most one node, widened by a margin; host part in engine.cu, cell records in the kernel's staging code) and the z
+    interpolation of both columns from one float4 cell record == the reference's scan and bilinear formula."""
+    t = make_scene("spice_lea").medium.tilt
+    dist = np.asarray(t["distancesFromOriginAlongTilt"], dtype=np.float32)
+    corr = np.asarray(t["zCorrections"], dtype=np.float32)
+    nd, nz = corr.shape
+    # host (engine.cu): cell width below the smallest gap between interior nodes
+    gap = min(float(dist[i]) - float(dist[i - 1]) for i in range(2, nd - 1))
+    width = gap * 0.99
+    cells = int(np.ceil((float(dist[nd - 2]) - float(dist[1])) / width)) + 2
+    assert cells <= 64
+    scale, offset = np.float32(1.0 / width), np.float32(1.0 - float(dist[1]) / width)
+    # staging: (nodes below the cell, the node inside it)
+    w, d1, margin = 1.0 / float(scale), float(dist[1]), 1e-3 / float(scale)
+    lut = []
+    for c in range(cells):
+        lo, hi = d1 + (c - 1) * w - margin, d1 + c * w + margin
+        below, inside = 1, np.inf
+        for i in range(1, nd - 1):
+            d = float(dist[i])
+            if c > 0 and d < lo:
+                below += 1
+            elif c == cells - 1 or d <= hi:
+                inside = min(inside, d)
+        lut.append((below, inside))
+    rng = np.random.default_rng(11)
+    nr = np.concatenate([rng.uniform(-800, 800, 200000), np.repeat(dist.astype(np.float64), 3) + np.tile([-1e-4, 0.0, 1e-4], nd),
+                         d1 + w * np.arange(-2, cells + 2), d1 + w * np.arange(-2, cells + 2) + 1e-5]).astype(np.float32)
+    cell = np.clip(np.trunc(nr * scale + offset).astype(int), 0, cells - 1)
+    j_fast = np.array([lut[c][0] + (0 if v < lut[c][1] else 1) for c, v in zip(cell, nr)])
+    j_ref = 1 + (nr[:, None] >= dist[None, 1:nd - 1]).sum(1)           # first j in [1, nd-1] with nr < dist[j], else nd-1
+    assert np.array_equal(j_fast, j_ref)
+    # the interpolation from cell records against the reference formula, on points across the table
+    n = 4000
+    x, y = rng.uniform(-600, 600, n), rng.uniform(-600, 600, n)
+    z = rng.uniform(t["zCoordinates"][0] - 20, t["zCoordinates"][-1] + 20, n)
+    want, nr64 = _reference_tilt_shift(t, x, y, z)
+    zc = t["zCoordinates"]
+    inv_dz = np.float32(1.0 / (zc[1] - zc[0]))
+    zr = np.float32(z) * inv_dz + np.float32(-zc[0] / (zc[1] - zc[0]))
+    k = np.clip(np.floor(zr).astype(int), 0, nz - 2)
+    above = (zr - k).astype(np.float32)
+    nr32 = nr64.astype(np.float32)
+    j = 1 + (nr32[:, None] >= dist[None, 1:nd - 1]).sum(1)
+    here_x, here_y = dist[j], (1.0 / (dist[j] - dist[j - 1])).astype(np.float32)
+    w_lo = (here_x - nr32) * here_y
+    lo0, hi0 = corr[j - 1, k], corr[j, k]
+    v_lo = lo0 + (corr[j - 1, k + 1] - lo0) * above
+    v_hi = hi0 + (corr[j, k + 1] - hi0) * above
+    got = v_hi + w_lo * (v_lo - v_hi)
+    assert np.abs(got - want).max() < 2e-3 and np.abs(got - want).mean() < 1e-4       # metres, on shifts of up to +-60 m; fp32 of z / dz
+
+
+def test_block_transform_equals_the_full_matrix_and_the_reference_renormalisation():
+    """kernel_fast.cu apply_block_matrix (five products) == I3CLSimVectorTransformMatrix.cxx:101-133 for the ppc matrices."""
+    m = make_scene("spice_lea").medium
+    rng = np.random.default_rng(12)
+    d = rng.normal(size=(20000, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    for M in (np.asarray(m.preMatrix, dtype=np.float64), np.asarray(m.postMatrix, dtype=np.float64)):
+        assert M[0, 2] == 0 and M[1, 2] == 0 and M[2, 0] == 0 and M[2, 1] == 0           # what launch_variant checks
+        want = d @ M.T
+        want /= np.linalg.norm(want, axis=1)[:, None]
+        M32, d32 = M.astype(np.float32), d.astype(np.float32)
+        nx = M32[0, 1] * d32[:, 1] + M32[0, 0] * d32[:, 0]
+        ny = M32[1, 1] * d32[:, 1] + M32[1, 0] * d32[:, 0]
+        nzv = M32[2, 2] * d32[:, 2]
+        inv = 1.0 / np.sqrt(nx * nx + ny * ny + nzv * nzv)
+        got = np.stack([nx * inv, ny * inv, nzv * inv], axis=1)
+        assert np.abs(got - want).max() < 5e-7
+
+
+def test_table_maker_fast_arc_cosine_and_step_parts():
+    """tabulate_device.h tab_acos (Abramowitz & Stegun 4.4.46) against acos; fill_queue's split of a step into parts."""
+    x = np.linspace(-1, 1, 400001)
+    a = np.minimum(np.abs(x), 1.0)
+    p = -0.0012624911
+    for c in (0.0066700901, -0.0170881256, 0.0308918810, -0.0501743046, 0.0889789874, -0.2145988016, 1.5707963050):
+        p = p * a + c
+    r = np.sqrt(1 - a) * p
+    got = np.where(x < 0, 3.14159265359 - r, r)
+    assert np.abs(got - np.arccos(x)).max() < 1e-7            # the azimuth bins are degrees wide
+    # part k of C covers photons [n k / C, n (k + 1) / C): the parts of a step add up to its photon count, none is negative
+    for n in (0, 1, 7, 199, 200, 333, 65539, 2 ** 32 - 1):
+        for C_ in (1, 2, 4, 8):
+            parts = [n * (k + 1) // C_ - n * k // C_ for k in range(C_)]
+            assert sum(parts) == n and min(parts) >= 0 and max(parts) - min(parts) <= 1
