@@ -55,6 +55,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
@@ -1771,7 +1772,9 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
         if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) {
             if constexpr (ANISO) {
                 const float *a = scene.medium.pre, *b = scene.medium.post;
-                if (a[2] == 0.f && a[5] == 0.f && a[6] == 0.f && a[7] == 0.f && b[2] == 0.f && b[5] == 0.f && b[6] == 0.f && b[7] == 0.f)
+                // (CLSIMCU_GENERIC_TRANSFORMS: test hook, takes the nine-product form for matrices that would qualify)
+                if (a[2] == 0.f && a[5] == 0.f && a[6] == 0.f && a[7] == 0.f && b[2] == 0.f && b[5] == 0.f && b[6] == 0.f && b[7] == 0.f &&
+                    std::getenv("CLSIMCU_GENERIC_TRANSFORMS") == nullptr)
                     return launch_mix<TILT, ANISO, false, true, kVarBlockTransforms>(scene, args, blocks, stream);
             }
             return launch_mix<TILT, ANISO, false, true, 0>(scene, args, blocks, stream);

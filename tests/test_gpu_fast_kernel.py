@@ -507,3 +507,22 @@ def test_photon_history_of_detected_photons_through_the_converter():
     w = hist[some, :, 3]
     assert np.all(np.nan_to_num(np.diff(w, axis=1), nan=1.0) > -1e-4)
     assert np.all(np.nanmax(w, axis=1) <= ph["dist_in_abs_lens"][some] + 1e-3)
+
+
+def test_generic_direction_transforms_agree_with_the_block_form(monkeypatch):
+    """The ppc anisotropy matrices take the five-product block form (kVarBlockTransforms); the nine-product form that any
+    other matrix takes must describe the same physics: the usual family of statistics, block form against generic form
+    (CLSIMCU_GENERIC_TRANSFORMS is the kernel launcher's test hook)."""
+    sc = make_scene("spice_lea")
+    bunch = steps.muon_track_steps(1 << 17, seed=71)
+
+    def attempt(k):
+        monkeypatch.delenv("CLSIMCU_GENERIC_TRANSFORMS", raising=False)
+        block, tot_b = _run_resident(sc, bunch, KERNEL_FAST, seed=77 + 1000 * k)
+        monkeypatch.setenv("CLSIMCU_GENERIC_TRANSFORMS", "1")
+        generic, tot_g = _run_resident(sc, bunch, KERNEL_FAST, seed=78 + 1000 * k)
+        monkeypatch.delenv("CLSIMCU_GENERIC_TRANSFORMS")
+        assert tot_b["photons"] == tot_g["photons"] and len(block) > 1e4
+        return _compare_distributions(block, generic, tot_b, tot_g)
+
+    _assert_same_distributions(attempt, 2e-3)
