@@ -925,6 +925,11 @@ __device__ __forceinline__ bool cell_walk(uint32_t cell) { return (cell & 0xffff
 __device__ __forceinline__ float4 lds128(uint32_t a) { float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ float lds32f(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// fire-and-forget float add to global memory (RED.E.ADD.F32)
+__device__ __forceinline__ void red_add(float *p, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
 // the shared-memory address of dynamic shared memory's first byte, opaque to the optimiser (so that it is computed once)
 __device__ __forceinline__ uint32_t smem_address()
 {
@@ -1178,8 +1183,10 @@ __device__ __forceinline__ bool sample_leg(Lane &L, const Leg &g, bool flying, c
         if (valid && !out) {
             const uint32_t index = table_bin_index_4<true>(tb, c);
             const float w = w0 * __expf(-depth);
-            atomicAdd(tb.table + index, w);
-            if (tb.squared) atomicAdd(tb.squared + index, w * w);
+            // (the table is in global memory: a reduction without a return value, not the generic-address atomic with its
+            // address-space query and compare-and-swap fall-backs)
+            red_add(tb.table + index, w);
+            if (tb.squared) red_add(tb.squared + index, w * w);
         }
         stopped |= __reduce_or_sync(0xffffffffu, out ? (1u << src) : 0u);
     }
