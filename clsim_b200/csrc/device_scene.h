@@ -124,8 +124,18 @@ struct TabulateArgs {
     float min_inv_group_vel, tan_theta_c;
     int num_angular;
     float angular[24];                   // getAngularAcceptance, Horner form of I3CLSimFunctionPolynomial.cxx:139-153
-    float ref_pos[4], ref_dir[4], ref_perp[4];   // I3CLSimReferenceParticle
+    alignas(16) float ref_pos[4];        // I3CLSimReferenceParticle
+    alignas(16) float ref_dir[4];
+    alignas(16) float ref_perp[4];
     float *table, *squared;              // HBM, added to atomically
+    // persistent kernel, four-axis tables whose axes are all linear or quadratic (`simple4`): the axes again, one array per
+    // quantity, so that the four bin indices of a point take five 16-byte loads and no branch
+    int simple4;
+    alignas(16) float scale4[4];
+    alignas(16) float neg_offset4[4];
+    alignas(16) int n_bins4[4];
+    alignas(16) uint32_t stride4[4];
+    alignas(16) float root4[4];          // 1: the inverse transform of this axis is the square root, 0: the identity
 };
 
 struct LaunchArgs {

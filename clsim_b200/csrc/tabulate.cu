@@ -244,6 +244,15 @@ int clsimcu_tabulator_create(const clsimcu_config *scene, const clsimcu_tabulato
                 else { a.axes[i].inverse = 4; a.axes[i].inv_power = float_literal(1. / ax.power); }
             }
         }
+        a.simple4 = (nd == 4) ? 1 : 0;
+        for (int i = 0; i < 4 && i < nd; ++i) {
+            a.scale4[i] = a.axes[i].scale;
+            a.neg_offset4[i] = -a.axes[i].offset;
+            a.n_bins4[i] = a.axes[i].n_bins;
+            a.stride4[i] = a.axes[i].stride;
+            a.root4[i] = (a.axes[i].inverse == 2) ? 1.f : 0.f;
+            if (a.axes[i].inverse != 0 && a.axes[i].inverse != 2) a.simple4 = 0;
+        }
         a.max0 = float_literal(cfg->axes[0].max);
         a.max3 = float_literal(cfg->axes[3].max);
         a.step_length = float_literal(cfg->step_length);

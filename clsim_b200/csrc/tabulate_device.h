@@ -89,6 +89,22 @@ __device__ inline void table_coordinates_4(const TabulateArgs &tb, const TableFr
 template <bool FAST = false>
 __device__ inline uint32_t table_bin_index_4(const TabulateArgs &tb, const float c[4])
 {
+    if (FAST && tb.simple4) {
+        // linear and quadratic axes only (the layouts in use): no branch, the axes' numbers in five 16-byte loads
+        const float4 scale = *reinterpret_cast<const float4 *>(tb.scale4), shift = *reinterpret_cast<const float4 *>(tb.neg_offset4);
+        const float4 root = *reinterpret_cast<const float4 *>(tb.root4);
+        const int4 bins = *reinterpret_cast<const int4 *>(tb.n_bins4);
+        const uint4 stride = *reinterpret_cast<const uint4 *>(tb.stride4);
+        const float v0 = (root.x != 0.f) ? tab_sqrt<true>(c[0]) : c[0], v1 = (root.y != 0.f) ? tab_sqrt<true>(c[1]) : c[1];
+        const float v2 = (root.z != 0.f) ? tab_sqrt<true>(c[2]) : c[2], v3 = (root.w != 0.f) ? tab_sqrt<true>(c[3]) : c[3];
+        // convert_int_sat_rtn: cvt.rmi.s32.f32 (NaN -> 0, saturating), then Axis::GetIndexCode's clamp to the under- / overflow bins
+        const int k0 = min(max(__float2int_rd(fmaf(scale.x, v0, shift.x)), -1), bins.x) + 1;
+        const int k1 = min(max(__float2int_rd(fmaf(scale.y, v1, shift.y)), -1), bins.y) + 1;
+        const int k2 = min(max(__float2int_rd(fmaf(scale.z, v2, shift.z)), -1), bins.z) + 1;
+        const int k3 = min(max(__float2int_rd(fmaf(scale.w, v3, shift.w)), -1), bins.w) + 1;
+        return stride.x * static_cast<uint32_t>(k0) + stride.y * static_cast<uint32_t>(k1) + stride.z * static_cast<uint32_t>(k2) +
+               stride.w * static_cast<uint32_t>(k3);
+    }
     uint32_t index = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
