@@ -286,7 +286,28 @@ def e2e_through_engine(eng, bunches, first_id=100):
     return time.perf_counter() - t0, got
 
 
-def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks):
+def run_guarded(fn, deadline_s, out):
+    """Run `fn(out)` in a worker thread and give up after `deadline_s`: the side legs must not be able to take the
+    headline line down with them (a rank that never reaches a collective would hold every other rank for NCCL's ten
+    minutes).  -> None, or the reason the legs did not finish; `out` keeps what finished."""
+    import threading
+    box = {}
+
+    def work():
+        try:
+            fn(out)
+        except BaseException as ex:   # noqa: B902 -- reported, not swallowed
+            box["error"] = "%s: %s" % (type(ex).__name__, ex)
+
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    t.join(deadline_s)
+    if t.is_alive():
+        return "no result within %d s (legs finished before that are kept)" % deadline_s
+    return box.get("error")
+
+
+def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks, out):
     """What the weak-scaling headline cannot show (every rank its own feeder, nothing shared):
     (a) STRONG scaling: ONE fixed step series of config 3 (muon bundle, SpiceLea + tilt + anisotropy) split over the
         ranks (sharding.split_steps), propagated end to end from host buffers, hit lists gathered on rank 0 and merged
@@ -302,7 +323,7 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
     from clsim_b200.description import KERNEL_FAST, ConverterOptions
     from clsim_b200.server import I3CLSimServerInProcess
     from clsim_b200.sharding import RNG_ROWS_PER_DEVICE, mcpe_row_offset, merge_results, rng_row_offset, split_steps, stepgen_row_offset
-    out = {}
+    torch.cuda.set_device(local)   # (called from a worker thread, see run_guarded)
     lea = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_lea", useTiltIfAvailable=True)
     geo = geometry.make_ic86_like_geometry(oversize=5.0)
     bias = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0)
@@ -609,13 +630,23 @@ def main():
     other = None
     if world == 1 and not args.no_variants and args.ice == "spice_mie" and not args.tilt:
         other = run_other_configs(args, local, sms, peaks["sm_max_mhz"])
-    multi = None
+    multi, legs_failed = None, None
     if not args.no_variants and args.ice == "spice_mie" and not args.tilt and (world > 1 or args.multi_gpu_legs):
-        multi = run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks)
+        multi = {}
+        legs_failed = run_guarded(lambda out: run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks, out),
+                                  240.0, multi)
+        if legs_failed:
+            multi["error"] = legs_failed
 
-    if rank != 0:
+    def leave():
+        sys.stdout.flush()
+        if legs_failed:
+            os._exit(0)   # a leg is still stuck in a worker thread (or in a collective): no teardown that could wait for it
         if world > 1:
             dist.destroy_process_group()
+
+    if rank != 0:
+        leave()
         return
 
     peak_ops = sms * 128 * peaks["sm_max_mhz"] * 1e6 * world
@@ -661,8 +692,7 @@ def main():
         rate, dt, _, _ = arm.run(sample, 78)
         line["cpu_baseline"] = arm.describe(rate, "%d steps x %d photons of the same workload, %.1f s" % (sample, PHOTONS_PER_STEP, dt))
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == "__main__":

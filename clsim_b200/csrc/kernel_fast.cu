@@ -1473,6 +1473,10 @@ __device__ __noinline__ int slow_phase(const DevScene *scene, float *st, float *
         }
         status = kDead;
     }
+    // ---- safety net: a photon whose state is no longer a number would never end (every comparison that ends a photon
+    //      is false for a NaN) and would hold its warp, and with it the launch, for ever: dropped here.  (No input is known
+    //      to produce one; a path of 1e9 m is 3 s of light.)
+    if (status == kActive && !(st[kPath * kThreads] < 1e9f)) status = kDead;
     __syncwarp();
 
     // ---- lanes without a photon take the next ones of the warp's queue; an empty queue is refilled

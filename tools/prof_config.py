@@ -21,9 +21,16 @@ elif name == "config5":
     gens = [ice.makeCherenkovWavelengthGenerator(bias, False, lea), ice.makeWavelengthGenerator(wl, val, bias, lea)]
     i = int(np.argmin((geo.posX - 0.0) ** 2 + (geo.posY - 0.0) ** 2 + (geo.posZ + 200.0) ** 2))
     bunch, pancake = steps.flasher_steps(n, np.array([geo.posX[i], geo.posY[i], geo.posZ[i]]), seed=5), 1.0
+elif name in ("config2", "config2_nonstop", "config2_history"):
+    lea = ice.MakeIceCubeMediumProperties(iceDataDirectory="spice_mie", useTiltIfAvailable=False)   # (config 2's ice)
+    geo = geometry.make_ic86_like_geometry(oversize=5.0)
+    bias = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0)
+    gens = [ice.makeCherenkovWavelengthGenerator(bias, False, lea)]
+    bunch, pancake = steps.muon_track_steps(n, seed=1000), 5.0
 else:
-    raise SystemExit("config3 | config5")
-opt = ConverterOptions(device=0, stop_detected_photons=True, pancake_factor=pancake, kernel_mode=KERNEL_FAST, max_num_workitems=len(bunch), rng_seed=777)
+    raise SystemExit("config2 | config2_nonstop | config2_history | config3 | config5")
+opt = ConverterOptions(device=0, stop_detected_photons=(name != "config2_nonstop"), pancake_factor=pancake, kernel_mode=KERNEL_FAST, max_num_workitems=len(bunch),
+                       rng_seed=777, photon_history_entries=(4 if name == "config2_history" else 0), output_photons_per_workitem=2)
 with capi.Engine(lea, geo, gens, bias, opt) as eng:
     eng.upload_resident(bunch)
     eng.run_resident(2)
