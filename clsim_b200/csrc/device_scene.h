@@ -104,6 +104,7 @@ struct DevScene {
     DevGeometry geo;
     int stop_detected, save_all, fixed_abs, pancake, history_entries;
     float prescale, fixed_abs_lens, pancake_factor, inv_pancake_factor;
+    int generic_transforms;   // test hook (environment CLSIMCU_GENERIC_TRANSFORMS, read when the engine is created): no block-matrix form
 };
 
 // Per-launch arguments.

@@ -420,6 +420,7 @@ void upload_tables(clsimcu_engine &e, int near_pixel_budget)
     s.history_entries = t.history_entries;
     s.prescale = t.prescale; s.fixed_abs_lens = t.fixed_abs_lens; s.pancake_factor = t.pancake_factor;
     s.inv_pancake_factor = t.pancake ? 1.f / t.pancake_factor : 1.f;
+    s.generic_transforms = std::getenv("CLSIMCU_GENERIC_TRANSFORMS") ? 1 : 0;   // (here, once, in the creating thread: not per launch)
 
     if (e.d_arena) { cudaFree(e.d_arena); e.d_arena = nullptr; }
     if (e.d_scene) { cudaFree(e.d_scene); e.d_scene = nullptr; }

@@ -55,7 +55,6 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
-#include <cstdlib>
 
 #include "../../include/clsimcuda.h"
 #include "device_scene.h"
@@ -1783,9 +1782,9 @@ int launch_variant(const DevScene &scene, const LaunchArgs &args, int blocks, cu
         if (scene.medium.scat_kind == CLSIMCU_SCAT_MIXED_SL_HG && scene.medium.mix_folded) {
             if constexpr (ANISO) {
                 const float *a = scene.medium.pre, *b = scene.medium.post;
-                // (CLSIMCU_GENERIC_TRANSFORMS: test hook, takes the nine-product form for matrices that would qualify)
+                // (scene.generic_transforms: test hook, takes the nine-product form for matrices that would qualify)
                 if (a[2] == 0.f && a[5] == 0.f && a[6] == 0.f && a[7] == 0.f && b[2] == 0.f && b[5] == 0.f && b[6] == 0.f && b[7] == 0.f &&
-                    std::getenv("CLSIMCU_GENERIC_TRANSFORMS") == nullptr)
+                    !scene.generic_transforms)
                     return launch_mix<TILT, ANISO, false, true, kVarBlockTransforms>(scene, args, blocks, stream);
             }
             return launch_mix<TILT, ANISO, false, true, 0>(scene, args, blocks, stream);
