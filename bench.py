@@ -307,6 +307,20 @@ def run_guarded(fn, deadline_s, out):
     return box.get("error")
 
 
+def first_error(dist, group, world, err):
+    """-> `err` (this rank's error text or None), or what another rank said.  Every rank learns, over the CPU-side group,
+    whether all of them got through their own part BEFORE anyone enters the collectives that follow: a rank that failed
+    would be missing there, and the others would wait for it until the watchdog."""
+    if world == 1:
+        return err
+    said = [None] * world
+    dist.all_gather_object(said, err, group=group)
+    for r, e in enumerate(said):
+        if e:
+            return err or ("rank %d: %s" % (r, e))
+    return None
+
+
 def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_ranks, sum_over_ranks, out):
     """What the weak-scaling headline cannot show (every rank its own feeder, nothing shared):
     (a) STRONG scaling: ONE fixed step series of config 3 (muon bundle, SpiceLea + tilt + anisotropy) split over the
@@ -334,6 +348,13 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
         if world > 1:
             dist.barrier(group=gloo)
 
+    def any_failed(err):
+        return first_error(dist, gloo, world, err)
+
+    def text(ex):
+        sys.stderr.write("bench.py rank %d: %s: %s\n" % (rank, type(ex).__name__, ex))
+        return "%s: %s" % (type(ex).__name__, ex)
+
     # ---------------- (a) strong scaling -------------------------------------------------------------------------
     total_steps = 16 * bunch_steps   # (16 pieces at most per rank: the size of the meta record below)
     series = steps.muon_bundle_steps(total_steps, num_muons=100, seed=3)   # the same series on every rank (seeded)
@@ -341,13 +362,24 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
     pieces = [shard[i:i + bunch_steps] for i in range(0, len(shard), bunch_steps)]
     opt = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=5.0, kernel_mode=KERNEL_FAST, enable_double_buffering=True,
                            max_num_workitems=bunch_steps, rng_seed=5150 + rank, rng_first_multiplier=rng_row_offset(rank))
-    with capi.Engine(lea, geo, gens, bias, opt) as eng:
+    err, eng, got = None, None, []
+    try:
+        eng = capi.Engine(lea, geo, gens, bias, opt)
         e2e_through_engine(eng, pieces[:1] * 2)   # warm the staging pool
+    except Exception as ex:   # noqa: BLE001 -- reported in the line, the other legs still run
+        err = text(ex)
+    err = any_failed(err)
+    if not err:
         barrier()
         t0 = time.perf_counter()
-        # bunch identifiers name (rank, piece): the caller's key for putting results back together (I3CLSimClientModule.cxx:359-439)
-        _, got = e2e_through_engine(eng, pieces, first_id=1000 * rank)
+        try:
+            # bunch identifiers name (rank, piece): the caller's key for putting results back together (I3CLSimClientModule.cxx:359-439)
+            _, got = e2e_through_engine(eng, pieces, first_id=1000 * rank)
+        except Exception as ex:   # noqa: BLE001
+            err = text(ex)
         t_prop = time.perf_counter() - t0
+        err = any_failed(err)
+    if not err:
         # hand the hit lists to rank 0: lengths first, then the records as bytes over NCCL (padded to the longest)
         ids = np.array([i for i, _ in got], dtype=np.int64)
         lens = np.array([len(p) for _, p in got], dtype=np.int64)
@@ -382,65 +414,76 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
             merged = merge_results(results)
             merged_bunches, merged_hits = len(merged), int(sum(len(v) for v in merged.values()))
         t_all = time.perf_counter() - t0
-    t_prop = max_over_ranks(t_prop)
-    t_all = max_over_ranks(t_all)
-    photons_total = float(series["num_photons"].sum())
-    out["strong_scaling_config3"] = {
-        "workload": "ONE muon-bundle step series (config 3: SpiceLea + tilt + anisotropy), %d steps x %d photons, split over the ranks; host buffers in, hit lists handed to rank 0 and merged by bunch identifier" % (total_steps, PHOTONS_PER_STEP),
-        "value": photons_total / t_all, "unit": "photons/s", "scaling": "strong", "seconds_to_merged_result": t_all,
-        "seconds_to_last_rank_result": t_prop, "bunches_merged": merged_bunches, "hits_merged": merged_hits, "photons": photons_total}
+        t_prop = max_over_ranks(t_prop)
+        t_all = max_over_ranks(t_all)
+        photons_total = float(series["num_photons"].sum())
+        out["strong_scaling_config3"] = {
+            "workload": "ONE muon-bundle step series (config 3: SpiceLea + tilt + anisotropy), %d steps x %d photons, split over the ranks; host buffers in, hit lists handed to rank 0 and merged by bunch identifier" % (total_steps, PHOTONS_PER_STEP),
+            "value": photons_total / t_all, "unit": "photons/s", "scaling": "strong", "seconds_to_merged_result": t_all,
+            "seconds_to_last_rank_result": t_prop, "bunches_merged": merged_bunches, "hits_merged": merged_hits, "photons": photons_total}
+    else:
+        out["strong_scaling_config3"] = {"error": err}
+    if eng is not None:
+        eng.close()
 
     # ---------------- (b) one process, N converters behind the server seam ------------------------------------------
     cpu_barrier()
     if rank == 0:
-        c2 = build_scene()
-        devices = configureCUDADevices(UseGPUs=True, OverrideApproximateNumberOfWorkItems=bunch_steps, numDevices=world)
-        converters = [initializeCUDA(dev, 6000 + i, c2[1], c2[0], c2[3], c2[2], enableDoubleBuffering=True, stopDetectedPhotons=True, pancakeFactor=5.0,
-                                     kernelMode=KERNEL_FAST, rngFirstMultiplierRow=i * RNG_ROWS_PER_DEVICE) for i, dev in enumerate(devices)]
-        server = I3CLSimServerInProcess(converters)
-        client = server.Connect()
-        bunch = make_bunch(bunch_steps, seed=4000)
-        per_gpu = 6
-        for i in range(2 * world):   # warm every converter's staging pool
-            client.EnqueueSteps(bunch, i)
-        for i in range(2 * world):
-            client.GetConversionResult()
-        t0 = time.perf_counter()
-        hits, sent, received, window = 0, 0, 0, 4 * world   # one feeder: at most `window` bunches in flight
-        total = per_gpu * world
-        while received < total:
-            while sent < total and sent - received < window:
-                client.EnqueueSteps(bunch, sent)
-                sent += 1
-            hits += len(client.GetConversionResult().photons)
-            received += 1
-        dt = time.perf_counter() - t0
-        st = server.GetStatistics()
-        calls = [st.get("NumKernelCalls" + ("" if world == 1 else "_%d" % i), 0.0) for i in range(world)]
-        server.Close()
-        for c in converters:
-            c.Close()
-        out["one_process_n_converters"] = {
-            "workload": "config 2 bunches (2^20 steps x 200 photons) from ONE feeder thread through I3CLSimServerInProcess to %d converters, one per GPU, host buffers in and hit lists out" % world,
-            "value": total * float(bunch["num_photons"].sum()) / dt, "unit": "photons/s", "bunches": total, "seconds": dt, "hits": hits,
-            "kernel_calls_per_converter": calls}
+        try:
+            c2 = build_scene()
+            devices = configureCUDADevices(UseGPUs=True, OverrideApproximateNumberOfWorkItems=bunch_steps, numDevices=world)
+            converters = [initializeCUDA(dev, 6000 + i, c2[1], c2[0], c2[3], c2[2], enableDoubleBuffering=True, stopDetectedPhotons=True, pancakeFactor=5.0,
+                                         kernelMode=KERNEL_FAST, rngFirstMultiplierRow=i * RNG_ROWS_PER_DEVICE) for i, dev in enumerate(devices)]
+            server = I3CLSimServerInProcess(converters)
+            client = server.Connect()
+            bunch = make_bunch(bunch_steps, seed=4000)
+            per_gpu = 6
+            for i in range(2 * world):   # warm every converter's staging pool
+                client.EnqueueSteps(bunch, i)
+            for i in range(2 * world):
+                client.GetConversionResult()
+            t0 = time.perf_counter()
+            hits, sent, received, window = 0, 0, 0, 4 * world   # one feeder: at most `window` bunches in flight
+            total = per_gpu * world
+            while received < total:
+                while sent < total and sent - received < window:
+                    client.EnqueueSteps(bunch, sent)
+                    sent += 1
+                hits += len(client.GetConversionResult().photons)
+                received += 1
+            dt = time.perf_counter() - t0
+            st = server.GetStatistics()
+            calls = [st.get("NumKernelCalls" + ("" if world == 1 else "_%d" % i), 0.0) for i in range(world)]
+            server.Close()
+            for c in converters:
+                c.Close()
+            out["one_process_n_converters"] = {
+                "workload": "config 2 bunches (2^20 steps x 200 photons) from ONE feeder thread through I3CLSimServerInProcess to %d converters, one per GPU, host buffers in and hit lists out" % world,
+                "value": total * float(bunch["num_photons"].sum()) / dt, "unit": "photons/s", "bunches": total, "seconds": dt, "hits": hits,
+                "kernel_calls_per_converter": calls}
+        except Exception as ex:   # noqa: BLE001
+            out["one_process_n_converters"] = {"error": text(ex)}
     cpu_barrier()
 
     # ---------------- (c) config 4 at its stated size -----------------------------------------------------------------
-    ang = mcpe.GetIceCubeDOMAngularSensitivity()
-    acc = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0, efficiency=0.9 * mcpe.GetHoleIcePeak())
-    gen4 = ice.makeCherenkovWavelengthGenerator(acc, False, lea)
-    opt4 = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=5.0, kernel_mode=KERNEL_FAST, enable_double_buffering=True,
-                            max_num_workitems=bunch_steps, rng_seed=7000 + rank, output_photons_per_workitem=2, rng_first_multiplier=rng_row_offset(rank))
-    conv = stepgen.I3CLSimLightSourceToStepConverterPPC(photonsPerStep=PHOTONS_PER_STEP, device=local)
-    conv.SetMediumProperties(lea)
-    conv.SetWlenBias(acc)
-    conv.SetRandomService(40 + rank)
-    conv.Initialize(rngFirstMultiplierRow=stepgen_row_offset(rank))
-    pe = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(50 + rank, {(int(s), int(o)): acc for s, o in zip(geo.stringIDs, geo.domIDs)}, ang,
-                                                 device=local, rngFirstMultiplierRow=mcpe_row_offset(rank))
     want_photons = 1.25e10
-    with capi.Engine(lea, geo, [gen4], acc, opt4) as eng:
+    err, conv, pe, eng = None, None, None, None
+    sent = photons = hits = pes = 0
+    energy, dt = 0.0, 0.0
+    try:
+        ang = mcpe.GetIceCubeDOMAngularSensitivity()
+        acc = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * 5.0, efficiency=0.9 * mcpe.GetHoleIcePeak())
+        gen4 = ice.makeCherenkovWavelengthGenerator(acc, False, lea)
+        opt4 = ConverterOptions(device=local, stop_detected_photons=True, pancake_factor=5.0, kernel_mode=KERNEL_FAST, enable_double_buffering=True,
+                                max_num_workitems=bunch_steps, rng_seed=7000 + rank, output_photons_per_workitem=2, rng_first_multiplier=rng_row_offset(rank))
+        conv = stepgen.I3CLSimLightSourceToStepConverterPPC(photonsPerStep=PHOTONS_PER_STEP, device=local)
+        conv.SetMediumProperties(lea)
+        conv.SetWlenBias(acc)
+        conv.SetRandomService(40 + rank)
+        conv.Initialize(rngFirstMultiplierRow=stepgen_row_offset(rank))
+        pe = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(50 + rank, {(int(s), int(o)): acc for s, o in zip(geo.stringIDs, geo.domIDs)}, ang,
+                                                     device=local, rngFirstMultiplierRow=mcpe_row_offset(rank))
+        eng = capi.Engine(lea, geo, [gen4], acc, opt4)
         pe.attach_to(eng)
         vertex, axis = (20.0, -30.0, -250.0), (0.3, 0.2, -0.93)
         conv.EnqueueLightSource(stepgen.Particle("EMinus", 1e3, vertex, axis), 0)   # warm-up, and the yield per GeV
@@ -450,22 +493,38 @@ def run_multi_gpu_legs(args, rank, world, local, dist, gloo, barrier, max_over_r
         energy = 1e3 * want_photons / max(1.0, small)
         conv.EnqueueLightSource(stepgen.Particle("EMinus", energy, vertex, axis), 1)
         conv.EnqueueBarrier()
+    except Exception as ex:   # noqa: BLE001
+        err = text(ex)
+    err = any_failed(err)
+    if not err:
         barrier()
         t0 = time.perf_counter()
-        sent = pending = photons = hits = pes = 0
-        while True:
-            if conv.EnqueueInto(eng, 100 + sent) == 0:
-                break
-            sent += 1
-            pending += 1
-            while eng.more_photons_available():
+        try:
+            pending = 0
+            while True:
+                if conv.EnqueueInto(eng, 100 + sent) == 0:
+                    break
+                sent += 1
+                pending += 1
+                while eng.more_photons_available():
+                    r = eng.get_result(); pending -= 1
+                    photons += r.num_photons_generated; hits += r.num_hits_counted; pes += len(r.mcpes)
+            while pending:
                 r = eng.get_result(); pending -= 1
                 photons += r.num_photons_generated; hits += r.num_hits_counted; pes += len(r.mcpes)
-        while pending:
-            r = eng.get_result(); pending -= 1
-            photons += r.num_photons_generated; hits += r.num_hits_counted; pes += len(r.mcpes)
+        except Exception as ex:   # noqa: BLE001
+            err = text(ex)
         dt = time.perf_counter() - t0
-    pe.close()
+        err = any_failed(err)
+    for thing in (eng, pe):
+        try:
+            if thing is not None:
+                thing.close()
+        except Exception as ex:   # noqa: BLE001 -- (an engine that died of a device error cannot free its buffers either)
+            text(ex)
+    if err:
+        out["config4_cascade"] = {"error": err}
+        return out
     dt = max_over_ranks(dt)
     out["config4_cascade"] = {
         "workload": "config 4: e- cascade in SpiceLea + tilt + anisotropy, steps made on the device from the step-generation queue entry, photo-electrons out; %.3g propagated photons per GPU (a %.3g GeV e- with the DOM-acceptance bias; the config's ~1e11 photons on eight GPUs)" % (want_photons, energy),

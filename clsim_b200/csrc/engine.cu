@@ -272,6 +272,18 @@ struct clsimcu_engine {
         m = async_error;
         return !async_error.empty();
     }
+    // An error in one of the two worker threads ends the engine for good (the reference's threads log_fatal).  Everybody
+    // who waits on one of the engine's queues is woken up with a failure: a caller blocked in EnqueueSteps for a staging
+    // buffer, the submit thread waiting for a slot the dead drain thread would have freed, the drain thread waiting for a
+    // launch the dead submit thread would have made.  (Results that were finished before can still be fetched.)
+    void abort_pipeline(const std::string &m)
+    {
+        set_async_error(m);
+        inbox.close();
+        free_slots.close();
+        free_staging.close();
+        in_flight.close();
+    }
 };
 
 namespace clsimcu {
@@ -552,7 +564,7 @@ void submit_loop(clsimcu_engine *e)
             if (!e->in_flight.put(si)) break;
         }
     } catch (const std::exception &ex) {
-        e->set_async_error(ex.what());
+        e->abort_pipeline(ex.what());
     }
     e->in_flight.close();
 }
@@ -628,7 +640,7 @@ void drain_loop(clsimcu_engine *e)
             e->outbox.put(res);
         }
     } catch (const std::exception &ex) {
-        e->set_async_error(ex.what());
+        e->abort_pipeline(ex.what());
     }
     e->outbox.close();
 }
@@ -887,9 +899,16 @@ int clsimcu_destroy(clsimcu_engine *e)
 }
 
 // A pinned staging buffer for an incoming bunch; waits for one to come back when all are in use.
+static int interrupted(clsimcu_engine *e)
+{
+    std::string err;
+    if (e->check_async_error(err)) return fail(CLSIMCU_ERR_CUDA, err);
+    return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+}
+
 static int acquire_staging(clsimcu_engine *e, int &index)
 {
-    if (!e->free_staging.get(index)) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    if (!e->free_staging.get(index)) return interrupted(e);
     return CLSIMCU_OK;
 }
 
@@ -925,7 +944,7 @@ int clsimcu_enqueue_sources(clsimcu_engine *e, clsimcu_step_generator *g, const 
     uint8_t *dst = reinterpret_cast<uint8_t *>(e->staging[b.staging]);
     std::memcpy(dst, sources, n * sizeof(clsimcu_step_source));
     std::memcpy(dst + source_bytes, first.data(), (n + 1) * sizeof(uint64_t));
-    if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    if (!e->inbox.put(std::move(b))) return interrupted(e);
     return CLSIMCU_OK;
 }
 
@@ -946,7 +965,7 @@ int clsimcu_enqueue(clsimcu_engine *e, const clsimcu_step *steps, size_t n, uint
     if (int rc = acquire_staging(e, b.staging)) return rc;
     parallel_copy(e->staging[b.staging], steps, n * sizeof(clsimcu_step));
     for (size_t i = 0; i < n; ++i) b.generated += steps[i].num_photons;
-    if (!e->inbox.put(std::move(b))) return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
+    if (!e->inbox.put(std::move(b))) return interrupted(e);
     return CLSIMCU_OK;
 }
 
@@ -955,11 +974,7 @@ int clsimcu_get_result(clsimcu_engine *e, clsimcu_result *r)
     if (!e) return fail(CLSIMCU_ERR_STATE, "I3CLSimStepToPhotonConverterCUDA is not initialized!");
     if (!r) return fail(CLSIMCU_ERR_INVALID, "result pointer is NULL");
     std::shared_ptr<HostResult> res;
-    if (!e->outbox.get(res)) {
-        std::string err;
-        if (e->check_async_error(err)) return fail(CLSIMCU_ERR_CUDA, err);
-        return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
-    }
+    if (!e->outbox.get(res)) return interrupted(e);
     auto *holder = new std::shared_ptr<HostResult>(res);
     static clsimcu_photon empty_photon;
     r->identifier = res->identifier;

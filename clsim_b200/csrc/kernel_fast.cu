@@ -1376,6 +1376,17 @@ __device__ __noinline__ void fill_queue(const DevScene *scene, float *warp_regio
                 const unsigned long long n = w_left;
                 w_left = static_cast<uint32_t>(n * (part + 1u) / chunks) - static_cast<uint32_t>(n * part / chunks);
             }
+            // A step whose position, time, direction, length or beta is not a finite number (or is beyond 2^63: the layer table
+            // ends at +-1e30) has its photons counted as created and absorbed on the spot.  The reference flies such photons
+            // through its outermost layer until they are absorbed -- no hit either way -- but a photon at infinity has no
+            // boundary ahead in this kernel's layer walk: it would step off the layer table and never end.  The reference's
+            // own step generator makes such a step once in 2^32 draws (gammaDistributedNumber's log(ry / (1 - ry)) at
+            // ry == 1, I3CLSimLightSourceToStepConverterUtils.h:100-108): about one step in fifty runs of 1e10 photons.
+            const bool out_of_this_world = lane < 8 && (wstep[lane] & 0x7f800000u) >= 0x5f000000u;
+            if (__any_sync(0xffffffffu, out_of_this_world)) {
+                w_created += w_left;
+                w_left = 0;
+            }
             if (lane == 0) {
                 const V3 axis = step_axis(__uint_as_float(wstep[4]), __uint_as_float(wstep[5]));
                 wstep[12] = __float_as_uint(axis.x);

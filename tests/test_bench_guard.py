@@ -36,3 +36,62 @@ def test_guard_keeps_finished_legs_and_reports_the_rest():
         raise RuntimeError("converter failed")
 
     assert "RuntimeError: converter failed" in bench.run_guarded(broken, 5.0, {})
+
+
+def _two_rank_worker(rank, world, port, out_dir):
+    import json
+    import sys
+
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    group = dist.new_group(backend="gloo")
+    bench = _bench()
+    seen = {}
+    # nobody failed; then rank 1 fails its own part of a leg: both ranks must know before the leg's collectives
+    seen["clean"] = bench.first_error(dist, group, world, None)
+    seen["one_failed"] = bench.first_error(dist, group, world, "ClsimCudaError: boom" if rank == 1 else None)
+    # a rank that never arrives: the others sit in a collective behind it, the watchdog lets every rank go with what it has
+    out = {}
+
+    def legs(o):
+        o["first"] = rank
+        if rank == 1:
+            time.sleep(60.0)
+        dist.barrier(group=group)
+        o["second"] = rank
+
+    t0 = time.perf_counter()
+    seen["why"] = bench.run_guarded(legs, 2.0, out)
+    seen["waited"] = time.perf_counter() - t0
+    seen["out"] = out
+    with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
+        json.dump(seen, f)
+    sys.stdout.flush()
+    os._exit(0)   # what bench.py's leave() does after a failed leg: no teardown that could wait for the stuck thread
+
+
+def test_ranks_agree_on_a_failed_leg_and_leave_a_stuck_one(tmp_path):
+    import json
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(90.0)
+        assert p.exitcode == 0
+    for r in range(2):
+        with open(os.path.join(str(tmp_path), "rank%d.json" % r)) as f:
+            seen = json.load(f)
+        assert seen["clean"] is None
+        assert "boom" in seen["one_failed"] and (r == 1 or seen["one_failed"].startswith("rank 1:"))
+        assert "no result within" in seen["why"] and seen["waited"] < 30.0
+        assert seen["out"] == {"first": r}
