@@ -95,3 +95,20 @@ def test_ranks_agree_on_a_failed_leg_and_leave_a_stuck_one(tmp_path):
         assert "boom" in seen["one_failed"] and (r == 1 or seen["one_failed"].startswith("rank 1:"))
         assert "no result within" in seen["why"] and seen["waited"] < 30.0
         assert seen["out"] == {"first": r}
+
+
+def test_the_step_at_infinity_that_stopped_the_eight_gpu_run():
+    """profiles/bench_r02_v38_n8_config4_hang.err: rank 6 of 8 never came back from the config-4 leg.  The step generator is
+    deterministic, so the leg's steps can be replayed on the CPU (tools/replay_config4_stepgen.py): with rank 6's seeds the
+    reference's gamma sampler draws ry == 1 in the fifteenth launch and puts one cascade step at infinity -- on no other
+    rank (profiles/replay_config4_stepgen_r02.txt).  The fast kernel now ends such steps on the spot
+    (tests/test_zz_gpu_steps_at_infinity.py); this test keeps the diagnosis reproducible."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(HERE), "tools", "replay_config4_stepgen.py")
+    text = subprocess.run([sys.executable, tool, "--rank", "6", "--launches", "15"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                          timeout=300).stdout
+    assert "launch 14: 1 step(s) at infinity, the first is step 497015 (thread 42359)" in text, text
+    text = subprocess.run([sys.executable, tool, "--rank", "5", "--launches", "15"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                          timeout=300).stdout
+    assert "no step at infinity" in text, text

@@ -172,3 +172,4 @@ def test_translation_is_the_vector_literal_rewrite_only():
     lit = re.compile(r"\(\s*(?:const\s+)?(floating4_t|float4|float2|double4)\s*\)")
     for a, b in zip(minus, plus):
         assert lit.sub(lambda m: m.group(1), a).replace(" ", "") == b.replace(" ", "")
+
