@@ -467,6 +467,19 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
     const Output out{scene, args, step, ring};
 
     uint32_t left = step.num_photons;
+    unsigned long long n_created = 0, n_segments = 0;
+    {
+        // the one place where this kernel leaves the reference's order: a step that is not a finite number (or beyond 2^63)
+        // is counted and ended here, as in the fast kernel (kernel_fast.cu, fill_queue).  The reference's text either flies
+        // such photons through its outermost layer or -- inf - inf in the absorption budget -- never ends them.
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&step);
+        bool out_of_this_world = false;
+        for (int i = 0; i < 8; ++i) out_of_this_world |= (w[i] & 0x7f800000u) >= 0x5f000000u;
+        if (out_of_this_world) {
+            n_created = left;
+            left = 0;
+        }
+    }
     float abs_left = 0.f;
     Flight f;
     f.scatters = 0;
@@ -477,7 +490,6 @@ __global__ void __launch_bounds__(64) propagate_reference_order(const __grid_con
     int layer = 0;
     const TabulateArgs *tab = args.tabulate;   // table-maker variant
     float depth = 0.f, prev_remainder = 0.f;
-    unsigned long long n_created = 0, n_segments = 0;
 
     while (left > 0) {
         if (abs_left < kEpsilon) {

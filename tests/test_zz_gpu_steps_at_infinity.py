@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from clsim_b200 import capi, steps
-from clsim_b200.description import KERNEL_FAST
+from clsim_b200.description import KERNEL_FAST, KERNEL_REFERENCE
 from tests.scenes import make_scene
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
@@ -40,13 +40,14 @@ def _poisoned(bunch):
     return bad, sorted(where)
 
 
-@pytest.mark.parametrize("name", ["spice_mie", "spice_lea"])   # plain layers; tilt + anisotropy (the ice of configs 3-5)
-def test_steps_at_infinity_end_at_once(name):
+@pytest.mark.parametrize("mode", [KERNEL_FAST, KERNEL_REFERENCE])   # (the reference-order kernel takes the same way out)
+@pytest.mark.parametrize("name", ["spice_mie", "spice_lea"])     # plain layers; tilt + anisotropy (the ice of configs 3-5)
+def test_steps_at_infinity_end_at_once(name, mode):
     sc = make_scene(name)
     bunch = steps.muon_track_steps(1 << 15, seed=91)   # ~7000 hits (oracle, both ice models)
     bunch["identifier"] = np.arange(len(bunch))
     bad, where = _poisoned(bunch)
-    opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=len(bunch), rng_seed=17, output_photons_per_workitem=4)
+    opt = sc.options(kernel_mode=mode, max_num_workitems=len(bunch), rng_seed=17, output_photons_per_workitem=4)
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         eng.upload_resident(bunch)
         clean = eng.run_resident(1)
