@@ -78,10 +78,15 @@ __device__ double gamma_distributed(double shape, Mwc64 &rng)
             const double rx = rng.oc();
             const double ry = rng.oc();
             y = static_cast<float>(log(ry / (1. - ry)) / l);
-            x = shape * exp(static_cast<double>(y));
+            // y and z are floats in the reference, so its std::exp(y) and std::log(z) are the single-precision overloads
+            // (pinned against the reference's own function: tests/test_stepgen_oracle.py).  Taken here as the double
+            // function rounded to float, i.e. the correctly rounded value, which glibc's expf / logf return in all but
+            // about one call in a thousand (CUDA's expf / logf are 1-2 ulp functions).
+            x = shape * static_cast<double>(static_cast<float>(exp(static_cast<double>(y))));
             z = static_cast<float>(rx * ry * ry);
             r = static_cast<float>(b + (shape + l) * static_cast<double>(y) - x);
-        } while (static_cast<double>(r) < 4.5 * static_cast<double>(z) - cheng && static_cast<double>(r) < log(static_cast<double>(z)));
+        } while (static_cast<double>(r) < 4.5 * static_cast<double>(z) - cheng &&
+                 static_cast<double>(r) < static_cast<double>(static_cast<float>(log(static_cast<double>(z)))));
     }
     return x;
 }

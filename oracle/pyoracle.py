@@ -284,3 +284,109 @@ class RefScene(object):
 
     def oracle_propagate(self, steps, rng_x, rng_a, cap=None, num_threads=1):
         return self._run("oracle", steps, rng_x, rng_a, cap, num_threads)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_geometry.so: the reference's own geometry source generator
+# (private/opencl/I3CLSimHelperGenerateGeometrySource.cxx) compiled unmodified (oracle/ref_shim/ref_geometry.cpp).
+# ---------------------------------------------------------------------------------------------------------
+_REF_GEOMETRY_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_geometry.so")
+_ref_geometry_lib = None
+
+
+def ref_geometry_available():
+    return os.path.isfile(_REF_GEOMETRY_LIB)
+
+
+def ref_geometry_source(geometry):
+    """-> (OpenCL source text the reference generates for `geometry`, geoLayerToOMNumIndexPerStringSet buffer,
+    stringIndex -> string ID, per string: DOM index -> DOM ID).  Raises RuntimeError with the reference's message."""
+    global _ref_geometry_lib
+    if _ref_geometry_lib is None:
+        L = C.CDLL(_REF_GEOMETRY_LIB)
+        L.ref_geometry_generate.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.c_double]
+        L.ref_geometry_error.restype = C.c_char_p
+        L.ref_geometry_text.restype = C.c_char_p
+        for name in ("ref_geometry_layer_to_om", "ref_geometry_string_ids"):
+            getattr(L, name).restype = C.c_size_t
+            getattr(L, name).argtypes = [C.POINTER(C.c_void_p)]
+        L.ref_geometry_dom_ids.restype = C.c_size_t
+        L.ref_geometry_dom_ids.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        _ref_geometry_lib = L
+    L = _ref_geometry_lib
+    g = geometry
+    n = g.size()
+    names = (C.c_char_p * max(1, n))(*[s.encode() for s in g.subdetectorNames])
+    rc = L.ref_geometry_generate(n, g.stringIDs.ctypes.data, g.domIDs.ctypes.data, g.posX.ctypes.data, g.posY.ctypes.data, g.posZ.ctypes.data,
+                                 names, float(g.OMRadius))
+    if rc != 0:
+        raise RuntimeError(L.ref_geometry_error().decode())
+    text = L.ref_geometry_text().decode()
+    p = C.c_void_p()
+    k = L.ref_geometry_layer_to_om(C.byref(p))
+    layer_to_om = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint16)), shape=(k,)).copy() if k else np.zeros(0, np.uint16)
+    k = L.ref_geometry_string_ids(C.byref(p))
+    string_ids = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(k,)).copy() if k else np.zeros(0, np.int32)
+    q = C.c_void_p()
+    k = L.ref_geometry_dom_ids(C.byref(p), C.byref(q))
+    start = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint32)), shape=(k + 1,)).copy()
+    flat = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(int(start[-1]),)).copy() if start[-1] else np.zeros(0, np.uint32)
+    dom_ids = [flat[start[i]:start[i + 1]].tolist() for i in range(k)]
+    return text, layer_to_om, string_ids.tolist(), dom_ids
+
+
+def parse_generated_source(text):
+    """#define NAME value  and  __constant TYPE name[...] = { ... };  of a generated OpenCL snippet -> (defines, arrays).
+    Numbers are read the way an OpenCL compiler reads them: `1.5e+00f` is the float nearest to 1.5, `0xFFFF` is 65535."""
+    import re
+
+    def number(tok, as_float):
+        tok = tok.strip()
+        if tok.lower().startswith("0x"):
+            return int(tok, 16)
+        if tok.endswith("f"):
+            return float(np.float32(float(tok[:-1])))
+        if as_float or any(c in tok for c in ".eE"):
+            return float(tok)
+        return int(tok)
+
+    defines = {}
+    for m in re.finditer(r"^#define\s+(\w+)\s+(\S+)\s*$", text, re.M):
+        try:
+            defines[m.group(1)] = number(m.group(2), False)
+        except ValueError:
+            defines[m.group(1)] = m.group(2)
+    arrays = {}
+    for m in re.finditer(r"__constant\s+(?:const\s+)?([\w ]+?)\s+(\w+)\s*\[[^\]]*\]\s*=\s*\{(.*?)\};", text, re.S):
+        is_float = m.group(1).strip() in ("float", "double")
+        arrays[m.group(2)] = [number(t, is_float) for t in m.group(3).replace("\n", " ").split(",") if t.strip()]
+    return defines, arrays
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_stepgen.so: the inline samplers of the reference's step generator
+# (private/clsim/I3CLSimLightSourceToStepConverterUtils.h) compiled unmodified (oracle/ref_shim/ref_stepgen_utils.cpp).
+# ---------------------------------------------------------------------------------------------------------
+_REF_STEPGEN_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_stepgen.so")
+_ref_stepgen_lib = None
+
+
+def ref_stepgen_available():
+    return os.path.isfile(_REF_STEPGEN_LIB)
+
+
+def ref_stepgen_lib():
+    global _ref_stepgen_lib
+    if _ref_stepgen_lib is None:
+        L = C.CDLL(_REF_STEPGEN_LIB)
+        for name in ("ref_mwc_co", "ref_mwc_oc"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.POINTER(C.c_uint64), C.c_uint32]
+        L.ref_gamma_distributed.restype = C.c_double
+        L.ref_gamma_distributed.argtypes = [C.c_double, C.POINTER(C.c_uint64), C.c_uint32]
+        L.ref_scatter_direction_by_angle.restype = None
+        L.ref_scatter_direction_by_angle.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.c_double]
+        L.ref_mwc_init_state.restype = C.c_uint64
+        L.ref_mwc_init_state.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t)]
+        _ref_stepgen_lib = L
+    return _ref_stepgen_lib

@@ -12,9 +12,13 @@ TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing under clsim_b200/).  F
   dataclasses, un-vendored: theta = pi - zenith, phi = pi + azimuth of the direction the particle comes from)
 
 The reference has no known-answer test for its step generator and draws from racing feeder threads, so the
-exact step sequence is not defined by it: parity unpinned for whole sequences.  What is pinned: the gamma and
-angular samplers against their analytic distributions (tests/test_stepgen_oracle.py), and the record layout.
+exact step sequence is not defined by it: parity unpinned for whole sequences.  What is pinned: the samplers
+(MWC draws, gammaDistributedNumber, scatterDirectionByAngle) BIT FOR BIT against the reference's own inline
+functions, compiled unmodified into oracle/_ref/libclsim_ref_stepgen.so (oracle/ref_shim/ref_stepgen_utils.cpp;
+tests/test_stepgen_oracle.py), the gamma and angular samplers against their analytic distributions, and the record
+layout.
 """
+import ctypes as C
 import math
 
 import numpy as np
@@ -27,6 +31,21 @@ SOURCE_DTYPE = np.dtype([
     ("pa", "<f8"), ("pb", "<f8"), ("num_steps", "<u8"), ("photons_per_step", "<u4"), ("photons_in_last_step", "<u4"),
     ("identifier", "<u4"), ("kind", "<i4")])
 assert SOURCE_DTYPE.itemsize == 104
+
+
+# glibc's single-precision exp and log, the functions the reference's float temporaries select (same libm as the reference
+# library this oracle is held against; numpy's float32 exp/log are its own SIMD kernels and differ in the last bit)
+_libm = C.CDLL("libm.so.6")
+_libm.expf.restype = _libm.logf.restype = C.c_float
+_libm.expf.argtypes = _libm.logf.argtypes = [C.c_float]
+
+
+def _expf(v):
+    return float(_libm.expf(v))
+
+
+def _logf(v):
+    return float(_libm.logf(v))
 
 
 class Mwc(object):
@@ -58,12 +77,14 @@ def gamma_distributed(shape, rng):
     while True:
         rx = rng.oc()
         ry = rng.oc()
-        y = float(f32(math.log(ry / (1.0 - ry)) / l))          # the reference keeps y, z, r in float
-        x = shape * math.exp(y)
+        # (ry == 1, one draw in 2^32: the reference divides by zero and goes on with y = +inf, x = +inf and a NaN in the
+        # rejection test, which accepts -- a step at infinity; Python would raise instead, so it is spelled out)
+        odds = ry / (1.0 - ry) if ry < 1.0 else math.inf
+        y = float(f32(math.log(odds) / l))                       # the reference keeps y, z, r in float ...
+        x = shape * _expf(y)                                     # ... so its std::exp(y) is the FLOAT overload (expf),
         z = float(f32(rx * ry * ry))
         r = float(f32(b + (shape + l) * y - x))
-        log_z = math.log(z) if z > 0.0 else -math.inf
-        if not (r < 4.5 * z - cheng and r < log_z):
+        if not (r < 4.5 * z - cheng and r < _logf(z)):           # and its std::log(z) is logf
             return x
 
 

@@ -130,3 +130,121 @@ def test_abi_argument_checks():
     n = C.c_size_t(0)
     assert lib.clsimcu_stepgen_generate(None, None, 0, None, 0, C.byref(n)) == -4
     assert lib.clsimcu_enqueue_sources(None, None, None, 0, 0) == -4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The samplers against the reference's own inline functions (private/clsim/I3CLSimLightSourceToStepConverterUtils.h),
+# compiled unmodified into oracle/_ref/libclsim_ref_stepgen.so.  Bit for bit: same libm, same float temporaries.
+# ---------------------------------------------------------------------------------------------------------------------
+from oracle import pyoracle  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not pyoracle.ref_stepgen_available(), reason="oracle/_ref/libclsim_ref_stepgen.so not built (no /root/reference at build time)")
+
+
+@needs_ref
+def test_mwc_draws_equal_the_reference():
+    L = pyoracle.ref_stepgen_lib()
+    x, a = streams(32, seed=5)
+    for i in range(32):
+        rng = so.Mwc(x[i], a[i])
+        state = C.c_uint64(int(x[i]))
+        for k in range(200):
+            if k % 2:
+                assert rng.co() == L.ref_mwc_co(C.byref(state), int(a[i]))
+            else:
+                assert rng.oc() == L.ref_mwc_oc(C.byref(state), int(a[i]))
+            assert rng.x == state.value
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [0.05, 0.3, 0.5, 0.99, 1.0, 1.5, 2.03, 4.7, 6.5, 17.2, 250.0])
+def test_gamma_sampler_equals_the_reference_bit_for_bit(shape):
+    """Weibull branch below shape 1, Cheng's above, float temporaries and all (…Utils.h:78-111): the same value from the
+    same stream, and the same number of draws consumed (the rejection loops leave the stream in the same state)."""
+    L = pyoracle.ref_stepgen_lib()
+    x, a = streams(16, seed=int(shape * 100) + 1)
+    for i in range(16):
+        rng = so.Mwc(x[i], a[i])
+        state = C.c_uint64(int(x[i]))
+        for _ in range(500):
+            ours = so.gamma_distributed(shape, rng)
+            theirs = L.ref_gamma_distributed(shape, C.byref(state), int(a[i]))
+            assert ours == theirs and rng.x == state.value
+
+
+@needs_ref
+def test_rotation_equals_the_reference_bit_for_bit():
+    L = pyoracle.ref_stepgen_lib()
+    rng = np.random.default_rng(8)
+    cases = []
+    for _ in range(3000):
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        cosa = rng.uniform(-1.0, 1.0)
+        cases.append((cosa, math.sqrt(1.0 - cosa * cosa), d[0], d[1], d[2], rng.uniform()))
+    # vertical directions take the other branch (sin(theta) == 0), both signs of z, and the degenerate angles
+    cases += [(0.3, math.sqrt(1 - 0.09), 0.0, 0.0, 1.0, 0.123), (0.3, math.sqrt(1 - 0.09), 0.0, 0.0, -1.0, 0.9), (1.0, 0.0, 0.6, 0.0, 0.8, 0.5),
+              (-1.0, 0.0, 0.0, 0.6, -0.8, 0.25), (0.0, 1.0, 1.0, 0.0, 0.0, 0.0)]
+    for cosa, sina, x, y, z, r in cases:
+        xyz = (C.c_double * 3)(x, y, z)
+        L.ref_scatter_direction_by_angle(cosa, sina, xyz, r)
+        assert so.scatter_direction(cosa, sina, x, y, z, r) == (xyz[0], xyz[1], xyz[2])
+
+
+@needs_ref
+def test_stream_seeding_rule_equals_the_reference():
+    """mwcRngInitState (…Utils.h:49-61): x != 0, high word < a - 1, low word < 2^32 - 1, drawn as (high, low) until it
+    fits.  The repo draws the two words from one splitmix64 value (tables.cpp seed_rng_states, restated in the oracle);
+    handed the same words, the reference's function accepts the same candidate."""
+    L = pyoracle.ref_stepgen_lib()
+
+    def splitmix(seed, n):
+        out, state, mask = [], seed, (1 << 64) - 1
+        for _ in range(n):
+            state = (state + 0x9E3779B97F4A7C15) & mask
+            z = state
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+            out.append(z ^ (z >> 31))
+        return out
+
+    rejected = 0
+    for seed in range(40):
+        # real multipliers (a rejection in ~3 % of the draws) and small ones (255 of 256, 15 of 16 high words are too large)
+        a = np.concatenate([capi.safeprime_multipliers(100 * seed, 24), np.array([0x01000000, 0x10000000], dtype=np.uint32)]).astype(np.uint32)
+        ours = pyoracle.seed_states(seed, a)
+        words = splitmix(seed, 20000)
+        flat = np.array([w for v in words for w in (v >> 32, v & 0xFFFFFFFF)], dtype=np.uint32)
+        at = 0
+        for i in range(len(a)):
+            used = C.c_size_t(0)
+            theirs = L.ref_mwc_init_state(flat[at:].ctypes.data, len(flat) - at, int(a[i]), C.byref(used))
+            assert used.value >= 2 and used.value % 2 == 0 and at + used.value < len(flat)
+            rejected += used.value // 2 - 1
+            at += used.value
+            assert theirs == int(ours[i])
+    assert rejected > 40
+
+
+@needs_ref
+def test_the_draw_that_puts_a_step_at_infinity():
+    """ry = 1 - co() is exactly 1 when the draw's low word is 0 (once in 2^32): the reference's Cheng branch divides by
+    zero, carries +inf through exp() and a NaN through its rejection test, and returns +inf -- the position of the step
+    along the shower axis.  This is the step that held rank 6 of the 8-GPU run (DESIGN section 5,
+    tools/replay_config4_stepgen.py); the oracle restates it, the kernels end such a step on the spot."""
+    L = pyoracle.ref_stepgen_lib()
+    a = int(capi.safeprime_multipliers(7, 1)[0])
+    # a state whose SECOND draw (ry) has a zero low word: s1 = (h1, l1) with l1 a + h1 = 0 mod 2^32, s0 its predecessor
+    l1 = 0x12345678
+    h1 = (-(l1 * a)) & 0xFFFFFFFF
+    s1 = (h1 << 32) | l1
+    s0 = ((s1 % a) << 32) | (s1 // a)
+    assert s1 // a < (1 << 32)
+    check = so.Mwc(s0, a)
+    check.oc()
+    assert check.x == s1 and check.oc() == 1.0
+    state = C.c_uint64(s0)
+    theirs = L.ref_gamma_distributed(3.2, C.byref(state), a)
+    rng = so.Mwc(s0, a)
+    ours = so.gamma_distributed(3.2, rng)
+    assert math.isinf(theirs) and theirs > 0 and ours == theirs and rng.x == state.value

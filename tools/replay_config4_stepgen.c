@@ -28,10 +28,10 @@ static double gamma_distributed(double shape, Mwc *rng)
         do {
             const double rx = oc(rng), ry = oc(rng);
             y = (float)(log(ry / (1. - ry)) / l);
-            x = shape * exp((double)y);
+            x = shape * (double)(float)exp((double)y);
             z = (float)(rx * ry * ry);
             r = (float)(b + (shape + l) * (double)y - x);
-        } while ((double)r < 4.5 * (double)z - cheng && (double)r < log((double)z));
+        } while ((double)r < 4.5 * (double)z - cheng && (double)r < (double)(float)log((double)z));
     }
     return x;
 }
