@@ -867,6 +867,9 @@ int clsimcu_create(const clsimcu_config *config, clsimcu_engine **out)
             e->staging_count = i + 1;
             e->free_staging.put(static_cast<int>(i));
         }
+        // the tables, the scene and the RNG rows went up from pageable memory on the default stream, which the engine's
+        // streams do not synchronise with: everything has arrived before the first launch can be made
+        CUDA_OK(cudaDeviceSynchronize());
         e->last_stamp = std::chrono::steady_clock::now();
         e->submit_thread = std::thread(submit_loop, e);
         e->drain_thread = std::thread(drain_loop, e);
@@ -898,7 +901,8 @@ int clsimcu_destroy(clsimcu_engine *e)
     return CLSIMCU_OK;
 }
 
-// A pinned staging buffer for an incoming bunch; waits for one to come back when all are in use.
+// A wait on one of the engine's queues ended without an item: a worker thread died of an error (its text is the
+// answer), or the engine is being destroyed.
 static int interrupted(clsimcu_engine *e)
 {
     std::string err;
@@ -906,6 +910,7 @@ static int interrupted(clsimcu_engine *e)
     return fail(CLSIMCU_ERR_INTERRUPTED, "engine is shutting down");
 }
 
+// A pinned staging buffer for an incoming bunch; waits for one to come back when all are in use.
 static int acquire_staging(clsimcu_engine *e, int &index)
 {
     if (!e->free_staging.get(index)) return interrupted(e);
@@ -1091,6 +1096,9 @@ int clsimcu_upload_resident(clsimcu_engine *e, const clsimcu_step *steps, size_t
             }
         }
         CUDA_OK(cudaMemcpy(e->d_res_steps, steps, n * sizeof(clsimcu_step), cudaMemcpyHostToDevice));
+        // (a copy from pageable memory may return while its last piece is still on its way from the driver's staging
+        // buffer, and the compute stream does not synchronise with the default stream: wait for it here)
+        CUDA_OK(cudaStreamSynchronize(nullptr));
         e->res_steps = n;
         uint64_t gen = 0;
         for (size_t i = 0; i < n; ++i) gen += steps[i].num_photons;
@@ -1250,6 +1258,7 @@ int clsimcu_rng_set(clsimcu_engine *e, const uint64_t *x, const uint32_t *a, siz
         CUDA_OK(cudaStreamSynchronize(e->compute));
         if (x) CUDA_OK(cudaMemcpy(e->d_rng_x, x, n * sizeof(uint64_t), cudaMemcpyHostToDevice));
         if (a) CUDA_OK(cudaMemcpy(e->d_rng_a, a, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaStreamSynchronize(nullptr));   // (pageable source: see clsimcu_upload_resident)
     } catch (const std::exception &ex) {
         return fail(CLSIMCU_ERR_CUDA, ex.what());
     }

@@ -348,6 +348,7 @@ int clsimcu_mcpe_create(const clsimcu_mcpe_config *cfg, clsimcu_mcpe_converter *
         CUDA_OK(cudaMemcpy(c->d_rng_x, x.data(), c->streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUDA_OK(cudaEventCreateWithFlags(&c->last_use, cudaEventDisableTiming));
         CUDA_OK(cudaMemcpy(c->d_rng_a, a.data(), c->streams * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaDeviceSynchronize());   // (pageable sources on the default stream; the object's launches run on non-blocking streams)
     } catch (const std::invalid_argument &ex) {
         free_converter(c);
         return report_error(CLSIMCU_ERR_INVALID, ex.what());

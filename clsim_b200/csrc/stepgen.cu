@@ -291,6 +291,7 @@ int clsimcu_stepgen_create(const clsimcu_step_generator_config *cfg, clsimcu_ste
         CUDA_OK(cudaMemcpy(g->d_rng_x, x.data(), g->streams * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUDA_OK(cudaEventCreateWithFlags(&g->last_use, cudaEventDisableTiming));
         CUDA_OK(cudaMemcpy(g->d_rng_a, a.data(), g->streams * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaDeviceSynchronize());   // (pageable sources on the default stream; the object's launches run on non-blocking streams)
     } catch (const std::exception &ex) {
         free_generator(g);
         return report_error(CLSIMCU_ERR_CUDA, ex.what());

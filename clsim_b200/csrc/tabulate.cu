@@ -271,6 +271,7 @@ int clsimcu_tabulator_create(const clsimcu_config *scene, const clsimcu_tabulato
         a.table = t->d_table;
         a.squared = t->d_squared;
         for (TabulateArgs *&p : t->d_args) CUDA_OK(cudaMalloc(&p, sizeof(TabulateArgs)));
+        CUDA_OK(cudaDeviceSynchronize());   // (the tables are zeroed on the default stream, the engine launches on a non-blocking one)
     } catch (const std::invalid_argument &ex) {
         const std::string msg = ex.what();
         free_tabulator(t);
