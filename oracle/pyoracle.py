@@ -350,6 +350,7 @@ def parse_generated_source(text):
             return float(tok)
         return int(tok)
 
+    text = re.sub(r"//[^\n]*", "", text)
     defines = {}
     for m in re.finditer(r"^#define\s+(\w+)\s+(\S+)\s*$", text, re.M):
         try:
@@ -390,3 +391,208 @@ def ref_stepgen_lib():
         L.ref_mwc_init_state.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_size_t)]
         _ref_stepgen_lib = L
     return _ref_stepgen_lib
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_medium.so: the reference's medium / wavelength SOURCE GENERATORS (function, random-value
+# and medium-properties classes plus I3CLSimHelperGenerateMediumPropertiesSource{,_Optimizers}.cxx) compiled
+# unmodified (oracle/ref_shim/ref_medium.cpp).  Returns the OpenCL text the reference would generate.
+# ---------------------------------------------------------------------------------------------------------
+_REF_MEDIUM_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_medium.so")
+_ref_medium_lib = None
+
+
+def ref_medium_available():
+    return os.path.isfile(_REF_MEDIUM_LIB)
+
+
+def ref_medium_lib():
+    global _ref_medium_lib
+    if _ref_medium_lib is None:
+        L = C.CDLL(_REF_MEDIUM_LIB)
+        L.ref_medium_last_error.restype = C.c_char_p
+        L.ref_medium_source.restype = C.c_int64
+        L.ref_medium_source.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ref_wlen_generator_source.restype = C.c_int64
+        L.ref_wlen_generator_source.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]
+        L.ref_wlen_bias_source.restype = C.c_int64
+        L.ref_wlen_bias_source.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.ref_medium_host_value.restype = C.c_double
+        L.ref_medium_host_value.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double]
+        _ref_medium_lib = L
+    return _ref_medium_lib
+
+
+def _text_of(call):
+    L = ref_medium_lib()
+    n = call(None, 0)
+    if n < 0:
+        raise RuntimeError(L.ref_medium_last_error().decode())
+    buf = C.create_string_buffer(n + 1)
+    call(buf, n + 1)
+    return buf.value.decode()
+
+
+class RefGeneratedSource(object):
+    """The three generated snippets of the reference's OpenCL program for (medium, wavelength generators, bias):
+    .medium, .wlen_generators, .wlen_bias -- text, exactly as the reference's generators write it."""
+
+    def __init__(self, medium, wlen_generators, wlen_bias):
+        from clsim_b200.description import ConverterOptions
+        self._cfg, self._keep = build_config(medium, None, wlen_generators, wlen_bias, ConverterOptions())
+        L = ref_medium_lib()
+        m = C.byref(self._cfg.medium)
+        self._tilt_z = None if medium.tilt is None else np.ascontiguousarray(medium.tilt["zCoordinates"], dtype=np.float64)
+        tz = None if self._tilt_z is None else self._tilt_z.ctypes.data
+        self.medium = _text_of(lambda out, cap: L.ref_medium_source(m, tz, out, cap))
+        self.wlen_generators = _text_of(lambda out, cap: L.ref_wlen_generator_source(self._cfg.wlen_generators, self._cfg.num_wlen_generators, out, cap))
+        self.wlen_bias = _text_of(lambda out, cap: L.ref_wlen_bias_source(C.byref(self._cfg.wlen_bias), out, cap))
+
+    def host_value(self, what, layer=0, a=0.0, b=0.0, c=0.0):
+        """GetValue of the reference's host-side class: what = 0 phase index, 1 group index, 2 scattering length,
+        3 absorption length (a = wavelength), 4 tilt shift, 5 absorption anisotropy factor (a, b, c = vector), 6 / 7 min / max wavelength."""
+        tz = None if self._tilt_z is None else self._tilt_z.ctypes.data
+        return ref_medium_lib().ref_medium_host_value(C.byref(self._cfg.medium), tz, what, layer, a, b, c)
+
+    @staticmethod
+    def preamble(options):
+        L = ref_medium_lib()
+        L.ref_preamble_source.restype = C.c_int64
+        L.ref_preamble_source.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_char_p, C.c_size_t]
+        o = options
+        return _text_of(lambda out, cap: L.ref_preamble_source(int(bool(o.stop_detected_photons)), int(bool(o.save_all_photons)),
+                                                               float(o.save_all_photons_prescale), int(o.photon_history_entries),
+                                                               float(o.fixed_number_of_absorption_lengths), float(o.pancake_factor), out, cap))
+
+
+_REF_KERNEL_DIR = "/root/reference/resources/kernels"
+
+
+def ref_program_available():
+    """A whole program of the reference can be assembled and compiled where its kernel text lies (this container)."""
+    return ref_medium_available() and ref_geometry_available() and os.path.isfile(os.path.join(_REF_KERNEL_DIR, "propagation_kernel.c.cl"))
+
+
+class RefProgram(object):
+    """ONE complete OpenCL program of the reference for (medium, geometry, generators, bias, options), every byte of it
+    text the reference ships (resources/kernels/*.cl) or writes with its own generators (libclsim_ref_medium.so,
+    libclsim_ref_geometry.so), in the order I3CLSimStepToPhotonConverterOpenCL.cxx:655-667 joins them, compiled for the
+    host under oracle/ref_shim/ref_program.cpp.  Nothing in it comes from the oracle's restatements.  Compiled
+    libraries are cached under oracle/_ref/programs/ by the hash of the program text and of the shim."""
+
+    def __init__(self, medium, geometry, wlen_generators, wlen_bias, options, save_all_dom_stub=False):
+        """save_all_dom_stub: in SAVE_ALL_PHOTONS mode the reference joins no geometry source although saveHit names
+        geometryGetDomPosition -- the program does not compile (RuntimeError with the compiler's message).  With the
+        stub, a one-line stand-in of that function (a DOM at the origin; the oracle's reading) is put where the geometry
+        source would be, so that the rest of the program can still be run in that mode."""
+        import hashlib
+        import sys
+        import tempfile
+        sys.path.insert(0, os.path.join(_HERE, "ref_shim"))
+        try:
+            import translate
+        finally:
+            sys.path.pop(0)
+        self.options = options
+        self.generated = RefGeneratedSource(medium, wlen_generators, wlen_bias)
+
+        def kernel(name):
+            with open(os.path.join(_REF_KERNEL_DIR, name)) as f:
+                return f.read()
+
+        parts = [RefGeneratedSource.preamble(options), kernel("mwcrng_kernel.cl"), self.generated.wlen_generators, self.generated.wlen_bias,
+                 self.generated.medium]
+        self.layer_to_om = np.zeros(1, np.uint16)
+        self.string_ids, self.dom_ids = [], []
+        if not options.save_all_photons:
+            geo_text, self.layer_to_om, self.string_ids, self.dom_ids = ref_geometry_source(geometry)
+            parts.append(geo_text)
+        elif save_all_dom_stub:
+            parts.append("inline void geometryGetDomPosition(unsigned short stringNum, unsigned short domNum, floating_t *domPosX, "
+                         "floating_t *domPosY, floating_t *domPosZ) { *domPosX = ZERO; *domPosY = ZERO; *domPosZ = ZERO; }   // NOT reference text\n")
+        # :522-527: header, collision detection (header, body), kernel body
+        tail = kernel("propagation_kernel.h.cl")
+        if not options.save_all_photons:
+            tail += kernel("sparse_collision_kernel.h.cl") + kernel("sparse_collision_kernel.c.cl")
+        tail += kernel("propagation_kernel.c.cl")
+        parts.append(tail)
+        self.text = "".join(p + "\n" for p in parts)
+        flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"]
+        if len(wlen_generators) <= 1:
+            flags.append("-DNO_FLASHER")        # :649
+        shim = b""
+        for name in ("ref_program.cpp", "opencl_c_shim.inc", "opencl_c_shim_generated.inc", "translate.py"):
+            with open(os.path.join(_HERE, "ref_shim", name), "rb") as f:
+                shim += f.read()
+        key = hashlib.sha256(self.text.encode() + shim + " ".join(flags).encode()).hexdigest()[:24]
+        cache = os.path.join(_HERE, "_ref", "programs")
+        so = os.path.join(cache, key + ".so")
+        if not os.path.isfile(so):
+            os.makedirs(cache, exist_ok=True)
+            with tempfile.TemporaryDirectory() as tmp:
+                with open(os.path.join(tmp, "program.cl.inc"), "w") as f:
+                    f.write(translate.translate(self.text))
+                out = os.path.join(tmp, "prog.so")
+                cc = subprocess.run(["g++"] + flags + ["-I" + tmp, "-I" + os.path.join(_HERE, "ref_shim"), "-shared", "-o", out,
+                                     os.path.join(_HERE, "ref_shim", "ref_program.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+                if cc.returncode != 0:
+                    raise RuntimeError("the reference's program does not compile:\n" + cc.stdout.decode(errors="replace")[-4000:])
+                os.replace(out, so)
+        L = C.CDLL(so)
+        L.prog_eval_wlen_function.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.prog_eval_scalar_field.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.prog_eval_vector_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.prog_sample.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_uint32, C.c_void_p, C.c_size_t]
+        L.prog_propagate.restype = C.c_uint32
+        L.prog_propagate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        self._lib = L
+
+    # ---- the generated functions, one by one (same conventions as Scene.eval_* / Scene.sample)
+    def eval_wlen_function(self, which, layers, wlens):
+        arr = np.ascontiguousarray(np.stack([np.asarray(layers, dtype=np.float32), np.asarray(wlens, dtype=np.float32)], axis=-1))
+        out = np.zeros(len(arr), dtype=np.float32)
+        self._lib.prog_eval_wlen_function(which, arr.ctypes.data, out.ctypes.data, len(arr))
+        return out
+
+    def eval_scalar_field(self, which, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.zeros(len(xyz), dtype=np.float32)
+        self._lib.prog_eval_scalar_field(which, xyz.ctypes.data, out.ctypes.data, len(xyz))
+        return out
+
+    def eval_vector_transform(self, which, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        out = np.zeros_like(xyz)
+        self._lib.prog_eval_vector_transform(which, xyz.ctypes.data, out.ctypes.data, len(xyz))
+        return out
+
+    def sample(self, which, x, a, n):
+        out = np.zeros(n, dtype=np.float32)
+        xs = C.c_uint64(int(x))
+        self._lib.prog_sample(which, C.byref(xs), int(a), out.ctypes.data, n)
+        return out, xs.value
+
+    # ---- the kernel: one launch over the steps in work-item order
+    def propagate(self, steps, rng_x, rng_a, cap=None):
+        """-> (hit records with string / DOM IDs, hit counter, final RNG states, history or None); the contract of
+        Scene.propagate with num_threads = 1."""
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        n = len(steps)
+        x = np.array(rng_x[:n], dtype=np.uint64)
+        a = np.array(rng_a[:n], dtype=np.uint32)
+        if cap is None:
+            cap = int(steps["num_photons"].sum()) + 16
+        out = np.zeros(cap, dtype=PHOTON_DTYPE)
+        H = int(self.options.photon_history_entries)
+        hist = np.zeros((cap, H, 4), dtype=np.float32) if H > 0 else None
+        count = self._lib.prog_propagate(steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, out.ctypes.data, cap,
+                                         self.layer_to_om.ctypes.data, hist.ctypes.data if hist is not None else None)
+        got = out[:min(count, cap)]
+        if not self.options.save_all_photons:
+            # I3CLSimStepToPhotonConverterOpenCL.cxx:1565-1602: indices -> IDs on the host after the launch
+            s = got["string_id"].astype(np.uint16).astype(np.int64)
+            d = got["om_id"].astype(np.int64)
+            sid = np.array([self.string_ids[i] for i in s], dtype=np.int16)
+            did = np.array([self.dom_ids[i][j] for i, j in zip(s, d)], dtype=np.uint16)
+            got["string_id"], got["om_id"] = sid, did
+        return got, int(count), x, (hist[:len(got)] if hist is not None else None)

@@ -3,6 +3,7 @@
 // typedef macro.  Test infrastructure (oracle/_ref), not product code.
 #ifndef CLSIM_REF_SHIM_I3TRAYHEADERS_H
 #define CLSIM_REF_SHIM_I3TRAYHEADERS_H
+#include <cmath>     // (NAN, std::isnan: the real umbrella header brings <cmath> in)
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -11,6 +12,8 @@
 #include <map>
 #include <set>
 #include <vector>
+
+#include "boost/shared_ptr.hpp"
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -34,6 +37,6 @@ inline void fatal(const char *msg) { throw std::runtime_error(msg); }
 #define log_trace(...) ((void)0)
 
 #define I3_POINTER_TYPEDEFS(C)               \
-    typedef std::shared_ptr<C> C##Ptr;       \
-    typedef std::shared_ptr<const C> C##ConstPtr
+    typedef boost::shared_ptr<C> C##Ptr;     \
+    typedef boost::shared_ptr<const C> C##ConstPtr
 #endif

@@ -1,0 +1,263 @@
+// ref_medium.cpp -- the reference's own medium / wavelength source GENERATORS, compiled for the host.
+// TEST INFRASTRUCTURE (oracle/_ref).  Nothing under clsim_b200/ links this.
+//
+// What this is: the reference builds the "generated" part of its OpenCL program at run time, as text, from a tree of
+// parameter objects: private/clsim/function/*.cxx (wavelength-dependent functions, scalar fields, direction
+// transforms), private/clsim/random_value/*.cxx (samplers), private/clsim/I3CLSimMediumProperties.cxx (the
+// container) and private/opencl/I3CLSimHelperGenerateMediumPropertiesSource{,_Optimizers}.cxx (the text generator
+// with its per-layer folding).  Those 33 files are compiled here UNMODIFIED, read where they lie (unity build:
+// each is an #include below); the IceTray / boost headers they name are the stand-ins under oracle/ref_shim/host/.
+//
+// The extern "C" functions at the bottom put the objects together the way the reference's Python does
+// (python/MakeIceCubeMediumProperties.py:185-244, python/util/__init__.py GetSpiceLeaAnisotropyTransforms /
+// GetIceTiltZShift, private/clsim/I3CLSimModuleHelper.cxx:75-330 for the generators) from the oracle's plain parameter
+// structs and return the text the reference would hand to its OpenCL compiler.  tests/test_ref_medium.py compiles
+// that text for the host under the same OpenCL-C shim as the kernel text and holds the oracle's restatements against
+// it value for value; tests/test_ref_program.py runs the reference's kernel on top of it.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../clsim_oracle.h"
+
+// ---- the reference's sources (unity build; order: bases first)
+#include "clsim/function/I3CLSimFunction.cxx"
+#include "clsim/function/I3CLSimFunctionAbsLenIceCube.cxx"
+#include "clsim/function/I3CLSimFunctionConstant.cxx"
+#include "clsim/function/I3CLSimFunctionDeltaPeak.cxx"
+#include "clsim/function/I3CLSimFunctionFromTable.cxx"
+#include "clsim/function/I3CLSimFunctionPolynomial.cxx"
+#include "clsim/function/I3CLSimFunctionRefIndexIceCube.cxx"
+#include "clsim/function/I3CLSimFunctionRefIndexQuanFry.cxx"
+#include "clsim/function/I3CLSimFunctionScatLenIceCube.cxx"
+#include "clsim/function/I3CLSimFunctionScatLenPartic.cxx"
+#include "clsim/function/I3CLSimScalarField.cxx"
+#include "clsim/function/I3CLSimScalarFieldAnisotropyAbsLenScaling.cxx"
+#include "clsim/function/I3CLSimScalarFieldConstant.cxx"
+#include "clsim/function/I3CLSimScalarFieldIceTiltZShift.cxx"
+#include "clsim/function/I3CLSimVectorTransform.cxx"
+#include "clsim/function/I3CLSimVectorTransformConstant.cxx"
+#include "clsim/function/I3CLSimVectorTransformMatrix.cxx"
+#include "clsim/random_value/I3CLSimRandomValue.cxx"
+#include "clsim/random_value/I3CLSimRandomValueApplyFunction.cxx"
+#include "clsim/random_value/I3CLSimRandomValueConstant.cxx"
+#include "clsim/random_value/I3CLSimRandomValueFixParameter.cxx"
+#include "clsim/random_value/I3CLSimRandomValueHenyeyGreenstein.cxx"
+#include "clsim/random_value/I3CLSimRandomValueInterpolatedDistribution.cxx"
+#include "clsim/random_value/I3CLSimRandomValueMixed.cxx"
+#include "clsim/random_value/I3CLSimRandomValueNormalDistribution.cxx"
+#include "clsim/random_value/I3CLSimRandomValueRayleighScatteringCosAngle.cxx"
+#include "clsim/random_value/I3CLSimRandomValueSimplifiedLiu.cxx"
+#include "clsim/random_value/I3CLSimRandomValueUniform.cxx"
+#include "clsim/random_value/I3CLSimRandomValueWlenCherenkovNoDispersion.cxx"
+// (two files of the unity build name a file-local serialization helper alike; serialization is not exercised here)
+#define LoadFromArchiveIntoConstPtr LoadFromArchiveIntoConstPtr_of_medium_properties
+#include "clsim/I3CLSimMediumProperties.cxx"
+#undef LoadFromArchiveIntoConstPtr
+#include "opencl/ieeehalfprecision.cxx"
+#include "opencl/I3CLSimHelperGenerateMediumPropertiesSource_Optimizers.cxx"
+#include "opencl/I3CLSimHelperGenerateMediumPropertiesSource.cxx"
+
+namespace {
+
+thread_local std::string g_error;
+
+// python/MakeIceCubeMediumProperties.py:185-244 with the arguments the oracle's parameter struct carries
+I3CLSimMediumPropertiesPtr make_medium(const oracle_medium &m, const double *tilt_z)
+{
+    // rock and air levels are not part of the generated text (the step generators read them); IceCube's where the layers
+    // fit between them, else the layer range itself, as the class defaults have it (I3CLSimMediumProperties.cxx:43-48)
+    const double top = m.layers_zstart + m.num_layers * m.layers_height;
+    I3CLSimMediumPropertiesPtr med(new I3CLSimMediumProperties(0.9216 * I3Units::g / I3Units::cm3, static_cast<uint32_t>(m.num_layers), m.layers_zstart,
+                                                               m.layers_height, std::min(-870. * I3Units::m, m.layers_zstart),
+                                                               std::max(1940. * I3Units::m, top)));
+    med->SetForcedMinWlen(265. * I3Units::nanometer);
+    med->SetForcedMaxWlen(675. * I3Units::nanometer);
+
+    I3CLSimRandomValueConstPtr scat;
+    if (m.scat_kind == 1)
+        scat = I3CLSimRandomValueConstPtr(new I3CLSimRandomValueHenyeyGreenstein(m.mean_cos));
+    else if (m.scat_kind == 2)
+        scat = I3CLSimRandomValueConstPtr(new I3CLSimRandomValueSimplifiedLiu(m.mean_cos));
+    else
+        scat = I3CLSimRandomValueConstPtr(new I3CLSimRandomValueMixed(m.f_sl, I3CLSimRandomValueConstPtr(new I3CLSimRandomValueSimplifiedLiu(m.mean_cos)),
+                                                                      I3CLSimRandomValueConstPtr(new I3CLSimRandomValueHenyeyGreenstein(m.mean_cos))));
+    med->SetScatteringCosAngleDistribution(scat);
+
+    if (!m.has_anisotropy) {
+        med->SetDirectionalAbsorptionLengthCorrection(I3CLSimScalarFieldConstPtr(new I3CLSimScalarFieldConstant(1.)));
+        med->SetPreScatterDirectionTransform(I3CLSimVectorTransformConstPtr(new I3CLSimVectorTransformConstant()));
+        med->SetPostScatterDirectionTransform(I3CLSimVectorTransformConstPtr(new I3CLSimVectorTransformConstant()));
+    } else {
+        // python/util/__init__.py GetSpiceLeaAnisotropyTransforms: the matrices are its numpy products, passed through
+        med->SetDirectionalAbsorptionLengthCorrection(
+            I3CLSimScalarFieldConstPtr(new I3CLSimScalarFieldAnisotropyAbsLenScaling(m.aniso_azimuth, m.aniso_along, m.aniso_perp)));
+        I3Matrix pre(3, 3), post(3, 3);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                pre(i, j) = m.pre_matrix[3 * i + j];
+                post(i, j) = m.post_matrix[3 * i + j];
+            }
+        med->SetPreScatterDirectionTransform(I3CLSimVectorTransformConstPtr(new I3CLSimVectorTransformMatrix(pre, m.pre_renormalize != 0)));
+        med->SetPostScatterDirectionTransform(I3CLSimVectorTransformConstPtr(new I3CLSimVectorTransformMatrix(post, m.post_renormalize != 0)));
+    }
+
+    if (m.tilt_num_dist > 0) {
+        // python/util/__init__.py GetIceTiltZShift: distances, equally spaced z coordinates, corrections[dist][z]
+        std::vector<double> dist(m.tilt_dist, m.tilt_dist + m.tilt_num_dist), zs(m.tilt_num_z);
+        for (int k = 0; k < m.tilt_num_z; ++k) zs[k] = tilt_z ? tilt_z[k] : m.tilt_z0 + k * m.tilt_dz;   // (the struct carries first + mean spacing)
+        I3Matrix corr(m.tilt_num_dist, m.tilt_num_z);
+        for (int j = 0; j < m.tilt_num_dist; ++j)
+            for (int k = 0; k < m.tilt_num_z; ++k) corr(j, k) = m.tilt_corr[j * m.tilt_num_z + k];
+        med->SetIceTiltZShift(I3CLSimScalarFieldConstPtr(new I3CLSimScalarFieldIceTiltZShift(dist, zs, corr, m.tilt_azimuth)));
+    } else {
+        med->SetIceTiltZShift(I3CLSimScalarFieldConstPtr(new I3CLSimScalarFieldConstant(0.)));
+    }
+
+    I3CLSimFunctionConstPtr phase(new I3CLSimFunctionRefIndexIceCube("phase", m.n_phase[0], m.n_phase[1], m.n_phase[2], m.n_phase[3], m.n_phase[4],
+                                                                     m.n_group[0], m.n_group[1], m.n_group[2], m.n_group[3], m.n_group[4]));
+    I3CLSimFunctionConstPtr group(new I3CLSimFunctionRefIndexIceCube("group", m.n_phase[0], m.n_phase[1], m.n_phase[2], m.n_phase[3], m.n_phase[4],
+                                                                     m.n_group[0], m.n_group[1], m.n_group[2], m.n_group[3], m.n_group[4]));
+    for (int i = 0; i < m.num_layers; ++i) {
+        med->SetPhaseRefractiveIndex(i, phase);
+        med->SetGroupRefractiveIndexOverride(i, group);
+        med->SetAbsorptionLength(i, I3CLSimFunctionConstPtr(new I3CLSimFunctionAbsLenIceCube(m.kappa, m.A, m.B, m.D, m.E, m.a_dust400[i], m.delta_tau[i])));
+        med->SetScatteringLength(i, I3CLSimFunctionConstPtr(new I3CLSimFunctionScatLenIceCube(m.alpha, m.b400[i])));
+    }
+    return med;
+}
+
+// the objects private/clsim/I3CLSimModuleHelper.cxx:75-330 ends up with, from the oracle's description of each
+I3CLSimRandomValueConstPtr make_generator(const oracle_wlen_generator &g)
+{
+    switch (g.kind) {
+    case 0:
+        return I3CLSimRandomValueConstPtr(new I3CLSimRandomValueInterpolatedDistribution(g.x0, g.dx, std::vector<double>(g.y, g.y + g.n)));
+    case 1:
+        return I3CLSimRandomValueConstPtr(
+            new I3CLSimRandomValueInterpolatedDistribution(std::vector<double>(g.x, g.x + g.n), std::vector<double>(g.y, g.y + g.n)));
+    case 2:
+        return I3CLSimRandomValueConstPtr(new I3CLSimRandomValueWlenCherenkovNoDispersion(g.from_wlen, g.to_wlen));
+    case 3:
+        return I3CLSimRandomValueConstPtr(new I3CLSimRandomValueConstant(g.value));
+    }
+    throw std::runtime_error("unknown wavelength generator kind");
+}
+
+int64_t give(const std::string &s, char *out, size_t cap)
+{
+    if (out && cap > 0) {
+        const size_t n = std::min(s.size(), cap - 1);
+        std::memcpy(out, s.data(), n);
+        out[n] = 0;
+    }
+    return static_cast<int64_t>(s.size());
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ref_medium_last_error() { return g_error.c_str(); }
+
+// Text of I3CLSimHelper::GenerateMediumPropertiesSource for the medium `m` describes.  Returns the length of the text
+// (call with out == NULL to size the buffer; tilt_z: the tilt table's z coordinates, tilt_num_z of them, or NULL), or -1 with ref_medium_last_error() set.
+int64_t ref_medium_source(const oracle_medium *m, const double *tilt_z, char *out, size_t cap)
+{
+    try {
+        I3CLSimMediumPropertiesPtr med = make_medium(*m, tilt_z);
+        if (!med->IsReady()) throw std::runtime_error("medium is not ready");
+        return give(I3CLSimHelper::GenerateMediumPropertiesSource(*med), out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Text of I3CLSimHelper::GenerateWavelengthGeneratorSource for n generators.
+int64_t ref_wlen_generator_source(const oracle_wlen_generator *gens, int32_t n, char *out, size_t cap)
+{
+    try {
+        std::vector<I3CLSimRandomValueConstPtr> v;
+        for (int32_t i = 0; i < n; ++i) v.push_back(make_generator(gens[i]));
+        return give(I3CLSimHelper::GenerateWavelengthGeneratorSource(v), out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// Text of the wavelength bias function as I3CLSimStepToPhotonConverterOpenCL::GetWlenBiasSource asks for it
+// (private/opencl/I3CLSimStepToPhotonConverterOpenCL.cxx:444-449: GetOpenCLFunction("getWavelengthBias")).
+int64_t ref_wlen_bias_source(const oracle_wlen_bias *b, char *out, size_t cap)
+{
+    try {
+        I3CLSimFunctionConstPtr f;
+        if (b->kind == 0)
+            f = I3CLSimFunctionConstPtr(new I3CLSimFunctionConstant(b->value));
+        else
+            f = I3CLSimFunctionConstPtr(new I3CLSimFunctionFromTable(b->x0, b->dx, std::vector<double>(b->v, b->v + b->n)));
+        return give(f->GetOpenCLFunction("getWavelengthBias"), out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// The option #defines I3CLSimStepToPhotonConverterOpenCL::GetPreambleSource puts in front of the program
+// (private/opencl/I3CLSimStepToPhotonConverterOpenCL.cxx:390-442, single precision; the six lines of
+// I3CLSimHelper::GetMathPreamble, private/opencl/I3CLSimHelperMath.cxx:32-37, first).  That file needs an OpenCL
+// runtime and cannot be compiled here, so the sequence is restated; the numbers are written by the reference's own
+// ToFloatString (private/clsim/I3CLSimHelperToFloatString.h).  fixed_abs_lengths: NaN = option off.
+int64_t ref_preamble_source(int32_t stop_detected_photons, int32_t save_all_photons, double save_all_prescale, int32_t history_entries,
+                            double fixed_abs_lengths, double pancake_factor, char *out, size_t cap)
+{
+    using I3CLSimHelper::ToFloatString;
+    std::string p = "typedef float floating_t;\n"
+                    "typedef float2 floating2_t;\n"
+                    "typedef float4 floating4_t;\n"
+                    "#define convert_floating_t convert_float\n"
+                    "#define ZERO 0.f\n"
+                    "#define ONE 1.f\n"
+                    "\n";
+    if (stop_detected_photons) p += "#define STOP_PHOTONS_ON_DETECTION\n";
+    if (save_all_photons) {
+        p += "#define SAVE_ALL_PHOTONS\n";
+        p += "#define SAVE_ALL_PHOTONS_PRESCALE " + ToFloatString(save_all_prescale) + "\n";
+    }
+    if (history_entries > 0) {
+        p += "#define SAVE_PHOTON_HISTORY\n";
+        p += "#define NUM_PHOTONS_IN_HISTORY " + std::to_string(history_entries) + "\n";
+    }
+    if (!std::isnan(fixed_abs_lengths)) p += "#define PROPAGATE_FOR_FIXED_NUMBER_OF_ABSORPTION_LENGTHS " + ToFloatString(fixed_abs_lengths) + "\n";
+    if (pancake_factor != 1.) p += "#define PANCAKE_FACTOR " + ToFloatString(pancake_factor) + "\n";
+    return give(p, out, cap);
+}
+
+// The host-side twins the reference's classes carry (GetValue / ApplyTransform in double): evaluated for completeness
+// of the pin -- the device text and the host method of one class are meant to agree.
+double ref_medium_host_value(const oracle_medium *m, const double *tilt_z, int32_t what, int32_t layer, double a, double b, double c)
+{
+    try {
+        I3CLSimMediumPropertiesPtr med = make_medium(*m, tilt_z);
+        switch (what) {
+        case 0: return med->GetPhaseRefractiveIndex(layer)->GetValue(a);
+        case 1: return med->GetGroupRefractiveIndexOverride(layer)->GetValue(a);
+        case 2: return med->GetScatteringLength(layer)->GetValue(a);
+        case 3: return med->GetAbsorptionLength(layer)->GetValue(a);
+        case 4: return med->GetIceTiltZShift()->GetValue(a, b, c);
+        case 5: return med->GetDirectionalAbsorptionLengthCorrection()->GetValue(a, b, c);
+        case 6: return med->GetMinWavelength();
+        case 7: return med->GetMaxWavelength();
+        }
+        throw std::runtime_error("unknown quantity");
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return NAN;
+    }
+}
+
+} // extern "C"
