@@ -596,3 +596,119 @@ class RefProgram(object):
             did = np.array([self.dom_ids[i][j] for i, j in zip(s, d)], dtype=np.uint16)
             got["string_id"], got["om_id"] = sid, did
         return got, int(count), x, (hist[:len(got)] if hist is not None else None)
+
+
+class RefTableProgram(object):
+    """ONE complete TABLE-MAKER program of the reference (private/clsim/tabulator/I3CLSimStepToTableConverter.cxx:178-212):
+    preamble with -DTABULATE, mwcrng_kernel.cl, generated wavelength generator / bias / medium / angular acceptance,
+    propagation_kernel.h.cl, the binning code Axes::GenerateBinningCode writes (with the coordinate kernel it loads) and
+    propagation_kernel.c.cl, compiled for the host under oracle/ref_shim/ref_table_program.cpp.
+
+    At this revision saveHit (compiled, never called with TABULATE) names geometryGetDomPosition, which no part of the
+    table-maker's program declares: as in save-all mode the text is ill-formed without a declaration of that function.
+    dom_stub=True adds the one-line stand-in (NOT reference text); dom_stub=False shows the compiler's message."""
+
+    def __init__(self, medium, wlen_generators, wlen_bias, axes, angular_coefficients, entries_per_stream=4096, step_length=1.0, dom_stub=True):
+        import hashlib
+        import sys
+        import tempfile
+        sys.path.insert(0, os.path.join(_HERE, "ref_shim"))
+        try:
+            import translate
+        finally:
+            sys.path.pop(0)
+        L = ref_medium_lib()
+        self.generated = RefGeneratedSource(medium, wlen_generators, wlen_bias)
+        self.axes = axes
+        n = len(axes.axes)
+        kind = (C.c_int32 * n)(*[ax.kind for ax in axes.axes])
+        power = (C.c_uint32 * n)(*[ax.power for ax in axes.axes])
+        bins = (C.c_uint32 * n)(*[ax.n_bins for ax in axes.axes])
+        lo = (C.c_double * n)(*[ax.min for ax in axes.axes])
+        hi = (C.c_double * n)(*[ax.max for ax in axes.axes])
+        nb = C.c_uint64(0)
+        L.ref_binning_source.restype = C.c_int64
+        L.ref_angular_acceptance_source.restype = C.c_int64
+        L.ref_table_preamble_source.restype = C.c_int64
+        L.ref_table_preamble_source.argtypes = [C.c_int32, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_char_p, C.c_size_t]
+        with tempfile.TemporaryDirectory() as build_root:
+            # Axes.cxx:36-43 reads $I3_BUILD/clsim/resources/kernels/<name>.c.cl
+            os.symlink("/root/reference", os.path.join(build_root, "clsim"))
+            old = os.environ.get("I3_BUILD")
+            os.environ["I3_BUILD"] = build_root
+            try:
+                self.binning = _text_of(lambda out, cap: L.ref_binning_source(int(axes.geometry), n, kind, power, bins, lo, hi, C.byref(nb), out, C.c_size_t(cap)))
+            finally:
+                if old is None:
+                    del os.environ["I3_BUILD"]
+                else:
+                    os.environ["I3_BUILD"] = old
+        self.num_bins = int(nb.value)
+        idx = (C.c_double * 2)()
+        if L.ref_minimum_refractive_index(C.byref(self.generated._cfg.medium), idx) != 0:
+            raise RuntimeError(L.ref_medium_last_error().decode())
+        self.n_group, self.n_phase = float(idx[0]), float(idx[1])
+        coef = np.ascontiguousarray(angular_coefficients, dtype=np.float64)
+        self.angular = _text_of(lambda out, cap: L.ref_angular_acceptance_source(coef.ctypes.data_as(C.POINTER(C.c_double)), len(coef), out, C.c_size_t(cap)))
+        self.preamble = _text_of(lambda out, cap: L.ref_table_preamble_source(n, int(entries_per_stream), float(step_length), self.n_group, self.n_phase, out, cap))
+
+        def kernel(name):
+            with open(os.path.join(_REF_KERNEL_DIR, name)) as f:
+                return f.read()
+
+        parts = [self.preamble, kernel("mwcrng_kernel.cl"), self.generated.wlen_generators, self.generated.wlen_bias, self.generated.medium, self.angular]
+        if dom_stub:
+            parts.append("inline void geometryGetDomPosition(unsigned short stringNum, unsigned short domNum, floating_t *domPosX, "
+                         "floating_t *domPosY, floating_t *domPosZ) { *domPosX = ZERO; *domPosY = ZERO; *domPosZ = ZERO; }   // NOT reference text\n")
+        parts += [kernel("propagation_kernel.h.cl"), self.binning, kernel("propagation_kernel.c.cl")]
+        self.text = "".join(parts)      # (the table-maker hands the parts over as separate strings: no separators)
+        flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"]
+        shim = b""
+        for name in ("ref_table_program.cpp", "opencl_c_shim.inc", "opencl_c_shim_generated.inc", "translate.py"):
+            with open(os.path.join(_HERE, "ref_shim", name), "rb") as f:
+                shim += f.read()
+        key = hashlib.sha256(self.text.encode() + shim + " ".join(flags).encode()).hexdigest()[:24]
+        cache = os.path.join(_HERE, "_ref", "programs")
+        so = os.path.join(cache, key + ".so")
+        if not os.path.isfile(so):
+            os.makedirs(cache, exist_ok=True)
+            with tempfile.TemporaryDirectory() as tmp:
+                with open(os.path.join(tmp, "program.cl.inc"), "w") as f:
+                    f.write(translate.translate(self.text))
+                out = os.path.join(tmp, "prog.so")
+                cc = subprocess.run(["g++"] + flags + ["-I" + tmp, "-I" + os.path.join(_HERE, "ref_shim"), "-shared", "-o", out,
+                                     os.path.join(_HERE, "ref_shim", "ref_table_program.cpp")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+                if cc.returncode != 0:
+                    raise RuntimeError("the reference's program does not compile:\n" + cc.stdout.decode(errors="replace")[-4000:])
+                os.replace(out, so)
+        self._lib = C.CDLL(so)
+        self._lib.prog_tabulate.restype = C.c_uint64
+        self._lib.prog_tabulate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+
+    @staticmethod
+    def reference_particle(reference):
+        """I3CLSimReferenceParticle (…StepToTableConverter.cxx:64-91) from (x, y, z, t, dx, dy, dz): twelve floats."""
+        x, y, z, t, dx, dy, dz = [float(v) for v in reference]
+        perpz = float(np.hypot(dx, dy))
+        if perpz > 0.:
+            p = np.array([-dx * dz / perpz, -dy * dz / perpz, perpz])
+            p = p / np.sqrt((p * p).sum())       # I3Direction normalises
+        else:
+            p = np.array([1., 0., 0.])
+        return np.array([x, y, z, t, dx, dy, dz, 0., p[0], p[1], p[2], 0.], dtype=np.float32)
+
+    def tabulate(self, steps, rng_x, rng_a, reference, squared=False):
+        """-> (bins[float64], squared or None, entries, new rng_x, launches): the contract of Scene.tabulate."""
+        steps = np.ascontiguousarray(steps, dtype=STEP_DTYPE)
+        n = len(steps)
+        x = np.array(rng_x[:n], dtype=np.uint64, copy=True)
+        a = np.array(rng_a[:n], dtype=np.uint32, copy=True)
+        bins = np.zeros(self.num_bins, dtype=np.float64)
+        sq = np.zeros(self.num_bins, dtype=np.float64) if squared else None
+        ref = self.reference_particle(reference)
+        launches = C.c_uint64(0)
+        entries = self._lib.prog_tabulate(steps.ctypes.data, n, x.ctypes.data, a.ctypes.data, ref.ctypes.data, bins.ctypes.data,
+                                          sq.ctypes.data if squared else None, C.byref(launches))
+        if entries == 0xFFFFFFFFFFFFFFFF:
+            raise RuntimeError("a single photon needs more than TABLE_ENTRIES_PER_STREAM entries")
+        return bins, sq, int(entries), x, int(launches.value)

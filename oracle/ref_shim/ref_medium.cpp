@@ -17,6 +17,8 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <limits>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -60,6 +62,9 @@
 #include "opencl/ieeehalfprecision.cxx"
 #include "opencl/I3CLSimHelperGenerateMediumPropertiesSource_Optimizers.cxx"
 #include "opencl/I3CLSimHelperGenerateMediumPropertiesSource.cxx"
+// ... and the table-maker's binning-code generators (they read the coordinate kernels from $I3_BUILD/clsim/resources/kernels/)
+#include "clsim/tabulator/Axis.cxx"
+#include "clsim/tabulator/Axes.cxx"
 
 namespace {
 
@@ -235,6 +240,104 @@ int64_t ref_preamble_source(int32_t stop_detected_photons, int32_t save_all_phot
     if (!std::isnan(fixed_abs_lengths)) p += "#define PROPAGATE_FOR_FIXED_NUMBER_OF_ABSORPTION_LENGTHS " + ToFloatString(fixed_abs_lengths) + "\n";
     if (pancake_factor != 1.) p += "#define PANCAKE_FACTOR " + ToFloatString(pancake_factor) + "\n";
     return give(p, out, cap);
+}
+
+// ---- table-maker (private/clsim/tabulator/): the parts of the program I3CLSimStepToTableConverter joins that differ
+//      from the step-to-photon program
+
+// Axes::GenerateBinningCode for the axes the oracle's table description names (kind 0 linear, 1 power).  The generator
+// loads {spherical,cylindrical}_coordinates.c.cl from $I3_BUILD/clsim/resources/kernels/: the caller sets I3_BUILD to a
+// directory in which `clsim` is a link to the reference tree.  n_bins_out: Axes::GetNBins() (with under/overflow).
+int64_t ref_binning_source(int32_t geometry, int32_t num_axes, const int32_t *kind, const uint32_t *power, const uint32_t *bins, const double *lo,
+                           const double *hi, uint64_t *n_bins_out, char *out, size_t cap)
+{
+    using namespace clsim::tabulator;
+    try {
+        std::vector<Axes::value_type> ax;
+        for (int32_t i = 0; i < num_axes; ++i) {
+            if (kind[i] == 0) ax.push_back(Axes::value_type(new LinearAxis(lo[i], hi[i], bins[i])));
+            else ax.push_back(Axes::value_type(new PowerAxis(lo[i], hi[i], bins[i], power[i])));
+        }
+        std::string text;
+        if (geometry == 0) {
+            SphericalAxes axes(ax);
+            if (n_bins_out) *n_bins_out = axes.GetNBins();
+            text = axes.GenerateBinningCode();
+        } else {
+            CylindricalAxes axes(ax);
+            if (n_bins_out) *n_bins_out = axes.GetNBins();
+            text = axes.GenerateBinningCode();
+        }
+        return give(text, out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// angularAcceptance->GetOpenCLFunction("getAngularAcceptance") for the polynomial python/GetIceCubeDOMAngularSensitivity.py:45 returns
+int64_t ref_angular_acceptance_source(const double *coefficients, int32_t n, char *out, size_t cap)
+{
+    try {
+        I3CLSimFunctionPolynomial f(std::vector<double>(coefficients, coefficients + n));
+        return give(f.GetOpenCLFunction("getAngularAcceptance"), out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// GetMinimumRefractiveIndex (private/clsim/tabulator/I3CLSimStepToTableConverter.cxx:95-119; that file needs an OpenCL
+// runtime, so its fifteen lines are restated on the reference's own classes -- including the scan `wmin + i*(wmax-wmin)`
+// that leaves the wavelength range after its first point).  out[0] = group index, out[1] = phase index.
+int32_t ref_minimum_refractive_index(const oracle_medium *m, double *out)
+{
+    try {
+        I3CLSimMediumPropertiesPtr medp = make_medium(*m, nullptr);
+        const I3CLSimMediumProperties &med = *medp;
+        std::pair<double, double> n_min(std::numeric_limits<double>::infinity(), std::numeric_limits<double>::infinity());
+        for (unsigned j = 0; j < med.GetLayersNum(); j++) {
+            const I3CLSimFunction &groupIndex = *(med.GetGroupRefractiveIndexOverride(j));
+            const I3CLSimFunction &phaseIndex = *(med.GetPhaseRefractiveIndex(j));
+            double wmin = std::max(med.GetMinWavelength(), groupIndex.GetMinWlen());
+            double wmax = std::min(med.GetMaxWavelength(), groupIndex.GetMaxWlen());
+            for (unsigned i = 0; i < 1000; i++) {
+                double n = groupIndex.GetValue(wmin + i * (wmax - wmin));
+                if (n > 1 && n < n_min.first) n_min = std::make_pair(n, phaseIndex.GetValue(wmin + i * (wmax - wmin)));
+            }
+        }
+        out[0] = n_min.first;
+        out[1] = n_min.second;
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+// The table-maker's preamble (…StepToTableConverter.cxx:178-199, after the six lines of GetMathPreamble).
+int64_t ref_table_preamble_source(int32_t num_axes, uint64_t entries_per_stream, double step_length, double n_group, double n_phase, char *out, size_t cap)
+{
+    std::ostringstream preamble;
+    preamble << "typedef float floating_t;\n"
+                "typedef float2 floating2_t;\n"
+                "typedef float4 floating4_t;\n"
+                "#define convert_floating_t convert_float\n"
+                "#define ZERO 0.f\n"
+                "#define ONE 1.f\n"
+                "\n";
+    preamble << "#define SAVE_ALL_PHOTONS\n"
+                "#define SAVE_ALL_PHOTONS_PRESCALE 1\n"
+                "#define PROPAGATE_FOR_FIXED_NUMBER_OF_ABSORPTION_LENGTHS 42\n"
+                "#define TABULATE\n"
+                "//#define DOM_RADIUS " << I3CLSimHelper::ToFloatString(0.16510 * I3Units::m) << "\n"
+                "//#define PRINTF_ENABLED\n";
+    if (num_axes > 4) preamble << "#define TABULATE_IMPACT_ANGLE\n";
+    preamble << "#define TABLE_ENTRIES_PER_STREAM " << entries_per_stream << "\n";
+    preamble << "#define VOLUME_MODE_STEP " << I3CLSimHelper::ToFloatString(step_length) << "\n";
+    preamble << "__constant floating_t min_invGroupVel = " << I3CLSimHelper::ToFloatString(n_group / I3Constants::c) << ";\n";
+    preamble << "__constant floating_t tan_thetaC = " << I3CLSimHelper::ToFloatString(std::sqrt(n_phase * n_phase - 1.)) << ";\n";
+    return give(preamble.str(), out, cap);
 }
 
 // The host-side twins the reference's classes carry (GetValue / ApplyTransform in double): evaluated for completeness
