@@ -16,6 +16,12 @@ Integers are written the way the portable binary archive does it (eos portable a
 ``icecube::archive::portable_binary_oarchive``): one signed size byte, then that many bytes of the value,
 least-significant first; zero is the single byte 0x00.
 
+Pinned (tests/test_wire_format.py): the reference's own records and serialize() members (public/clsim/I3CLSimStep.h,
+I3CLSimPhoton.h, private/clsim/I3CLSimStep.cxx, I3CLSimPhoton.cxx), compiled unmodified into oracle/_ref/libclsim_ref_wire.so,
+write the bytes ``pack_*`` writes and read what ``pack_*`` wrote; a record filled through the reference's setters is byte for
+byte ``clsimcu_step`` / ``clsimcu_photon``.  (The archive those members write to is a stand-in that restates the portable
+archive's encoding of one value; which values, of which C++ type, in which order is the reference's code.)
+
 NOT reproduced -- parity unpinned, and stated as such: the archive preamble and the object framing around the body
 (archive signature and version, class id / class name / tracking / object id of the shared pointer, the
 ``I3FrameObject`` base's class-info bytes).  They belong to IceTray's ``serialization`` project, which is not vendored

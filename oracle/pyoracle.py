@@ -712,3 +712,60 @@ class RefTableProgram(object):
         if entries == 0xFFFFFFFFFFFFFFFF:
             raise RuntimeError("a single photon needs more than TABLE_ENTRIES_PER_STREAM entries")
         return bins, sq, int(entries), x, int(launches.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_wire.so: the reference's step / photon records (public/clsim/I3CLSimStep.h, I3CLSimPhoton.h)
+# and their serialize() members (private/clsim/I3CLSimStep.cxx, I3CLSimPhoton.cxx) compiled unmodified
+# (oracle/ref_shim/ref_wire.cpp; the archives are stand-ins, see oracle/ref_shim/host_wire/icetray/serialization.h).
+# ---------------------------------------------------------------------------------------------------------
+_REF_WIRE_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_wire.so")
+_ref_wire_lib = None
+
+
+def ref_wire_available():
+    return os.path.isfile(_REF_WIRE_LIB)
+
+
+def ref_wire_lib():
+    global _ref_wire_lib
+    if _ref_wire_lib is None:
+        L = C.CDLL(_REF_WIRE_LIB)
+        L.ref_wire_error.restype = C.c_char_p
+        for name in ("ref_wire_step_size", "ref_wire_photon_size", "ref_wire_step_version", "ref_wire_photon_version"):
+            getattr(L, name).restype = C.c_uint32
+        L.ref_wire_make_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_wire_make_photon.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_wire_read_step_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for name in ("ref_wire_write_steps", "ref_wire_write_photons"):
+            getattr(L, name).restype = C.c_uint64
+            getattr(L, name).argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        for name in ("ref_wire_read_steps", "ref_wire_read_photons"):
+            getattr(L, name).restype = C.c_int64
+            getattr(L, name).argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        _ref_wire_lib = L
+    return _ref_wire_lib
+
+
+def ref_wire_write(records):
+    """Body the reference's I3Vector<...>::serialize(portable_binary_oarchive) writes for a step or photon series."""
+    L = ref_wire_lib()
+    records = np.ascontiguousarray(records)
+    fn = L.ref_wire_write_steps if records.dtype.itemsize == 48 else L.ref_wire_write_photons
+    p = C.c_void_p()
+    n = fn(records.ctypes.data if len(records) else None, len(records), C.byref(p))
+    return C.string_at(p, n)
+
+
+def ref_wire_read(body, dtype):
+    """Records the reference's I3Vector<...>::serialize(portable_binary_iarchive) reads from a body, and the bytes it left
+    unread.  RuntimeError with the reference's message when it refuses."""
+    L = ref_wire_lib()
+    fn = L.ref_wire_read_steps if np.dtype(dtype).itemsize == 48 else L.ref_wire_read_photons
+    left = C.c_uint64(0)
+    n = fn(bytes(body), len(body), None, 0, C.byref(left))
+    if n < 0:
+        raise RuntimeError(L.ref_wire_error().decode())
+    out = np.zeros(n, dtype=dtype)
+    fn(bytes(body), len(body), out.ctypes.data, n, C.byref(left))
+    return out, int(left.value)
