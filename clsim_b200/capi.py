@@ -24,7 +24,7 @@ SYMBOLS = [
     "clsimcu_get_statistics", "clsimcu_upload_resident", "clsimcu_run_resident", "clsimcu_download_resident",
     "clsimcu_download_resident_history", "clsimcu_rng_get", "clsimcu_rng_set", "clsimcu_describe_tables", "clsimcu_describe_tables_from_config",
     "clsimcu_describe_collision_map_from_config",
-    "clsimcu_safeprime_multipliers", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
+    "clsimcu_safeprime_multipliers", "clsimcu_seed_rng_states", "clsimcu_download_resident_rng_tags", "clsimcu_last_error", "clsimcu_version",
     "clsimcu_sizeof_config", "clsimcu_device_count",
     "clsimcu_mcpe_create", "clsimcu_mcpe_destroy", "clsimcu_mcpe_convert", "clsimcu_mcpe_rng_get", "clsimcu_attach_mcpe_converter",
     "clsimcu_stepgen_create", "clsimcu_stepgen_destroy", "clsimcu_stepgen_generate", "clsimcu_stepgen_rng_get", "clsimcu_enqueue_sources",
@@ -77,6 +77,7 @@ def lib():
         L.clsimcu_describe_tables_from_config.argtypes = [C.POINTER(ConfigStruct), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_describe_collision_map_from_config.argtypes = [C.POINTER(ConfigStruct), C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.clsimcu_safeprime_multipliers.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        L.clsimcu_seed_rng_states.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         if L.clsimcu_sizeof_config() != C.sizeof(ConfigStruct):
             raise ImportError("clsimcu_config layout mismatch between description.py and libclsimcuda.so")
         _lib = L
@@ -99,6 +100,14 @@ def safeprime_multipliers(first, n):
     a = np.zeros(n, dtype=np.uint32)
     _check(lib().clsimcu_safeprime_multipliers(int(first), int(n), a.ctypes.data))
     return a
+
+
+def seed_rng_states(seed, a):
+    """Start states of the MWC streams with multipliers `a`, as an engine created with rng_seed = seed draws them (host only)."""
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    x = np.zeros(len(a), dtype=np.uint64)
+    _check(lib().clsimcu_seed_rng_states(int(seed), a.ctypes.data, x.ctypes.data, len(a)))
+    return x
 
 
 def describe_tables(medium, geometry, wlen_generators, wlen_bias, options):

@@ -1321,4 +1321,11 @@ int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a)
     return CLSIMCU_OK;
 }
 
+int clsimcu_seed_rng_states(uint64_t seed, const uint32_t *a, uint64_t *x, uint64_t n)
+{
+    if ((!a || !x) && n) return fail(CLSIMCU_ERR_INVALID, "multiplier or state pointer is NULL");
+    seed_rng_states(seed, a, x, static_cast<size_t>(n));
+    return CLSIMCU_OK;
+}
+
 } // extern "C"

@@ -291,6 +291,12 @@ int clsimcu_describe_collision_map_from_config(const clsimcu_config *config, int
  * rows [first, first+n) of the descending sequence that starts at 4294967118. */
 int clsimcu_safeprime_multipliers(uint64_t first, uint64_t n, uint32_t *a);
 
+/* Start states x[0..n) of the MWC streams with multipliers a[0..n), as clsimcu_create draws them from config->rng_seed
+ * (host only, no GPU needed).  The acceptance rule is init_MWC_RNG's (private/opencl/mwcrng_init.h:107-113: x != 0,
+ * upper half < a - 1, lower half < 0xffffffff, two 32-bit draws per candidate); the draws come from splitmix64 in place
+ * of the reference's I3RandomService (IceTray's GSL service, un-vendored). */
+int clsimcu_seed_rng_states(uint64_t seed, const uint32_t *a, uint64_t *x, uint64_t n);
+
 /* In SAVE_ALL mode with kernel FAST: per saved photon i the two MWC stream states it was made
  * from, so a CPU checker can replay single photons.  The fast kernel keeps two streams per
  * lane, one for photon creation and one for propagation:

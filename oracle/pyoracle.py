@@ -769,3 +769,27 @@ def ref_wire_read(body, dtype):
     out = np.zeros(n, dtype=dtype)
     fn(bytes(body), len(body), out.ctypes.data, n, C.byref(left))
     return out, int(left.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_rng.so: init_MWC_RNG of private/opencl/mwcrng_init.h compiled unmodified (oracle/ref_shim/ref_rng_init.cpp)
+# ---------------------------------------------------------------------------------------------------------
+_REF_RNG_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_rng.so")
+
+
+def ref_rng_available():
+    return os.path.isfile(_REF_RNG_LIB)
+
+
+def ref_init_mwc_rng(n, safeprimes_file, values):
+    """-> (x, a, number of 64-bit values used): the reference's init_MWC_RNG reading `safeprimes_file`, its random service
+    handing out the upper, then the lower 32 bits of each of `values`.  RuntimeError when it reports failure."""
+    L = C.CDLL(_REF_RNG_LIB)
+    L.ref_init_mwc_rng.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    values = np.ascontiguousarray(values, dtype=np.uint64)
+    x, a = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
+    used = C.c_size_t(0)
+    rc = L.ref_init_mwc_rng(x.ctypes.data, a.ctypes.data, n, safeprimes_file.encode(), values.ctypes.data, len(values), C.byref(used))
+    if rc != 0:
+        raise RuntimeError("init_MWC_RNG returned %d" % rc)
+    return x, a, int(used.value)

@@ -240,3 +240,51 @@ def test_dom_hits_are_on_the_pancaked_surface(mie):
     ids = set(zip(sc.geo.stringIDs.tolist(), sc.geo.domIDs.tolist()))
     assert all((int(s), int(d)) in ids for s, d in zip(ph["string_id"], ph["om_id"]))
     assert np.all(ph["weight"] > 0)
+
+
+@pytest.mark.skipif(not pyoracle.ref_rng_available(), reason="oracle/_ref not built (no /root/reference at build time)")
+def test_seeding_against_the_references_init_mwc_rng(tmp_path):
+    """R2, the seeding half: init_MWC_RNG (private/opencl/mwcrng_init.h, compiled unmodified into oracle/_ref/libclsim_ref_rng.so)
+    reads the multipliers from a table in the reference's text format and draws the start states; with a random service that
+    hands out splitmix64's values 32 bits at a time it makes the multipliers and the states the product (clsimcu_seed_rng_states,
+    clsimcu_safeprime_multipliers) and the oracle make.  Multipliers chosen so that the rejection rule fires: the table's own,
+    and small ones for which half of the candidates are refused."""
+    from clsim_b200 import capi
+
+    def splitmix64(seed, n):
+        out, s, m = [], seed, (1 << 64) - 1
+        for _ in range(n):
+            s = (s + 0x9E3779B97F4A7C15) & m
+            z = s
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+            out.append(z ^ (z >> 31))
+        return np.array(out, dtype=np.uint64)
+
+    n = 3000
+    table = capi.safeprime_multipliers(0, n)
+    # the reference's text format (resources/.../rnd.txt): the multiplier first, the rest of the line is skipped
+    path = tmp_path / "safeprimes_base32.txt"
+    path.write_text("".join("%d %d %d\n" % (a, a * (1 << 32) - 1, a * (1 << 31) - 1) for a in map(int, table)))
+    for seed in (0, 5, 123456789):
+        x, a, used = pyoracle.ref_init_mwc_rng(n, str(path), splitmix64(seed, n + 64))
+        assert np.array_equal(a, table)
+        assert np.array_equal(x, capi.seed_rng_states(seed, table))          # the product's rule
+        assert np.array_equal(x, pyoracle.seed_states(seed, table))          # the oracle's
+        assert used >= n
+    # multipliers near 2^31: every second candidate has an upper half >= a - 1 and is refused
+    small = (np.arange(500, dtype=np.uint64) * 2 + (1 << 31)).astype(np.uint32)
+    path.write_text("".join("%d\n" % a for a in small))
+    x, a, used = pyoracle.ref_init_mwc_rng(len(small), str(path), splitmix64(77, 4 * len(small)))
+    assert np.array_equal(a, small) and used > 1.7 * len(small)
+    assert np.array_equal(x, capi.seed_rng_states(77, small)) and np.array_equal(x, pyoracle.seed_states(77, small))
+    # the reference's own shipped table: same first rows as the product generates
+    ref_table = "/root/reference/resources/scripts/compareToPPCredux/test_ice_models/lea/rnd.txt"
+    import os
+    if os.path.isfile(ref_table):
+        x, a, _ = pyoracle.ref_init_mwc_rng(2000, ref_table, splitmix64(1, 2100))
+        assert np.array_equal(a, capi.safeprime_multipliers(0, 2000)) and np.array_equal(x, capi.seed_rng_states(1, a))
+    # a value that does not fit 32 bits is refused by the reference's range check (:97-100)
+    path.write_text("4294967296\n")
+    with pytest.raises(RuntimeError):
+        pyoracle.ref_init_mwc_rng(1, str(path), splitmix64(1, 8))
