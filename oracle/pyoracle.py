@@ -793,3 +793,26 @@ def ref_init_mwc_rng(n, safeprimes_file, values):
     if rc != 0:
         raise RuntimeError("init_MWC_RNG returned %d" % rc)
     return x, a, int(used.value)
+
+
+def ref_made_wlen_generator_source(medium, wlen_bias, without_dispersion=False, spectrum=None):
+    """Text of the wavelength generator the REFERENCE'S OWN FACTORY makes for (bias, medium): makeCherenkovWavelengthGenerator, or
+    makeWavelengthGenerator for a tabulated spectrum = (wavelengths, values) (private/clsim/I3CLSimModuleHelper.cxx:75-300,
+    compiled unmodified into libclsim_ref_medium.so)."""
+    from clsim_b200.description import ConverterOptions
+    from clsim_b200.description import WlenGenerator
+    L = ref_medium_lib()
+    cfg, keep = build_config(medium, None, [WlenGenerator.constant(4e-7)], wlen_bias, ConverterOptions())
+    tz = None if medium.tilt is None else np.ascontiguousarray(medium.tilt["zCoordinates"], dtype=np.float64)
+    sx = sy = None
+    n = 0
+    if spectrum is not None:
+        sx, sy = [np.ascontiguousarray(v, dtype=np.float64) for v in spectrum]
+        n = len(sx)
+    L.ref_made_wlen_generator_source.restype = C.c_int64
+    L.ref_made_wlen_generator_source.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]
+    text = _text_of(lambda out, cap: L.ref_made_wlen_generator_source(C.byref(cfg.medium), None if tz is None else tz.ctypes.data, C.byref(cfg.wlen_bias),
+                                                                     int(bool(without_dispersion)), None if sx is None else sx.ctypes.data,
+                                                                     None if sy is None else sy.ctypes.data, n, out, cap))
+    del keep
+    return text

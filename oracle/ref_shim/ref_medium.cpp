@@ -62,6 +62,9 @@
 #include "opencl/ieeehalfprecision.cxx"
 #include "opencl/I3CLSimHelperGenerateMediumPropertiesSource_Optimizers.cxx"
 #include "opencl/I3CLSimHelperGenerateMediumPropertiesSource.cxx"
+// ... and the factories that MAKE the wavelength generators from a bias and a medium (private/clsim/I3CLSimModuleHelper.cxx:75-300;
+// the converter / device classes its third function, initializeOpenCL, talks to are stand-ins: that function is not run)
+#include "clsim/I3CLSimModuleHelper.cxx"
 // ... and the table-maker's binning-code generators (they read the coordinate kernels from $I3_BUILD/clsim/resources/kernels/)
 #include "clsim/tabulator/Axis.cxx"
 #include "clsim/tabulator/Axes.cxx"
@@ -240,6 +243,32 @@ int64_t ref_preamble_source(int32_t stop_detected_photons, int32_t save_all_phot
     if (!std::isnan(fixed_abs_lengths)) p += "#define PROPAGATE_FOR_FIXED_NUMBER_OF_ABSORPTION_LENGTHS " + ToFloatString(fixed_abs_lengths) + "\n";
     if (pancake_factor != 1.) p += "#define PANCAKE_FACTOR " + ToFloatString(pancake_factor) + "\n";
     return give(p, out, cap);
+}
+
+// Text of the wavelength generator the reference's own factory makes for (bias, medium): makeCherenkovWavelengthGenerator
+// (I3CLSimModuleHelper.cxx:176-300) when n_spectrum == 0, else makeWavelengthGenerator (:75-173) for the tabulated spectrum
+// (spectrum_x, spectrum_y), e.g. a flasher LED.  The product's clsim_b200/ice.py restates both factories.
+int64_t ref_made_wlen_generator_source(const oracle_medium *m, const double *tilt_z, const oracle_wlen_bias *b, int32_t without_dispersion,
+                                       const double *spectrum_x, const double *spectrum_y, int32_t n_spectrum, char *out, size_t cap)
+{
+    try {
+        I3CLSimMediumPropertiesPtr med = make_medium(*m, tilt_z);
+        I3CLSimFunctionConstPtr bias;
+        if (b->kind == 0) bias = I3CLSimFunctionConstPtr(new I3CLSimFunctionConstant(b->value));
+        else bias = I3CLSimFunctionConstPtr(new I3CLSimFunctionFromTable(b->x0, b->dx, std::vector<double>(b->v, b->v + b->n)));
+        I3CLSimRandomValueConstPtr gen;
+        if (n_spectrum == 0) {
+            gen = I3CLSimModuleHelper::makeCherenkovWavelengthGenerator(bias, without_dispersion != 0, med);
+        } else {
+            I3CLSimFunctionConstPtr spectrum(new I3CLSimFunctionFromTable(std::vector<double>(spectrum_x, spectrum_x + n_spectrum),
+                                                                          std::vector<double>(spectrum_y, spectrum_y + n_spectrum)));
+            gen = I3CLSimModuleHelper::makeWavelengthGenerator(spectrum, bias, med);
+        }
+        return give(I3CLSimHelper::GenerateWavelengthGeneratorSource(std::vector<I3CLSimRandomValueConstPtr>(1, gen)), out, cap);
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
 }
 
 // ---- table-maker (private/clsim/tabulator/): the parts of the program I3CLSimStepToTableConverter joins that differ

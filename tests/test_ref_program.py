@@ -249,3 +249,42 @@ def test_whole_program_save_all_with_the_one_line_stand_in(name):
     got, want, _ = run_both(prog, ora, bunch, cap=len(bunch) * 100)
     assert 0.2 * 25600 < got[1] < 0.3 * 25600
     assert_identical(got, want)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the factories that make the wavelength generators (row R3a)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("medium_name", ["spice_mie", "spice_lea"])
+def test_wavelength_generator_factories_against_the_references(medium_name):
+    """clsim_b200/ice.py restates I3CLSimModuleHelper::makeCherenkovWavelengthGenerator / makeWavelengthGenerator
+    (private/clsim/I3CLSimModuleHelper.cxx:75-300, compiled unmodified into libclsim_ref_medium.so).  The text the reference
+    generates for the object ITS factory makes equals, character for character, the text it generates for the object built from
+    the arrays ice.py computes -- i.e. every table entry agrees to the ten digits the text carries -- on every branch of the
+    factories: tabulated bias with and without dispersion, no bias without dispersion (the closed-form sampler), a constant
+    bias other than 1 (the made-up 10 nm binning), and a tabulated LED spectrum on unequal bins."""
+    from clsim_b200 import ice
+    from clsim_b200.description import WlenBias
+    sc = make_scene(medium_name)
+    medium, table_bias = sc.medium, sc.bias
+    cases = [
+        ("tabulated bias, dispersion", table_bias, False, None),
+        ("tabulated bias, no dispersion", table_bias, True, None),
+        ("no bias, no dispersion", WlenBias(constant=1.0), True, None),
+        ("no bias, dispersion", WlenBias(constant=1.0), False, None),
+        ("constant bias 0.3, dispersion", WlenBias(constant=0.3), False, None),
+        ("constant bias 0.3, no dispersion", WlenBias(constant=0.3), True, None),
+        ("LED spectrum, tabulated bias", table_bias, False, ice.GetFlasherLED405Spectrum()),
+        ("LED spectrum, constant bias", WlenBias(constant=0.5), False, ice.GetFlasherLED405Spectrum()),
+    ]
+    kinds = set()
+    for what, bias, nodisp, spectrum in cases:
+        if spectrum is None:
+            ours = ice.makeCherenkovWavelengthGenerator(bias, nodisp, medium)
+        else:
+            ours = ice.makeWavelengthGenerator(spectrum[0], spectrum[1], bias, medium)
+        kinds.add(ours.kind)
+        text_ours = pyoracle.RefGeneratedSource(medium, [ours], bias).wlen_generators
+        text_ref = pyoracle.ref_made_wlen_generator_source(medium, bias, nodisp, spectrum)
+        assert text_ours == text_ref, what
+        assert "generateWavelength_0" in text_ref
+    assert len(kinds) == 3        # equally spaced table, unequally spaced table, closed form
