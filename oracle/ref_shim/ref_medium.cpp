@@ -304,6 +304,36 @@ int64_t ref_binning_source(int32_t geometry, int32_t num_axes, const int32_t *ki
     }
 }
 
+// Axes::GetBinVolume (tabulator/Axes.cxx:121-166; what I3CLSimStepToTableConverter::Normalize divides the bin content by) for
+// n index triples (the three spatial axes), and Axis::GetBinEdges of one axis: edges_out has bins[axis] + 1 entries.
+int32_t ref_bin_volumes(int32_t geometry, int32_t num_axes, const int32_t *kind, const uint32_t *power, const uint32_t *bins, const double *lo,
+                        const double *hi, const uint64_t *idx3, uint64_t n, double *volumes_out, int32_t edges_axis, double *edges_out)
+{
+    using namespace clsim::tabulator;
+    try {
+        std::vector<Axes::value_type> ax;
+        for (int32_t i = 0; i < num_axes; ++i) {
+            if (kind[i] == 0) ax.push_back(Axes::value_type(new LinearAxis(lo[i], hi[i], bins[i])));
+            else ax.push_back(Axes::value_type(new PowerAxis(lo[i], hi[i], bins[i], power[i])));
+        }
+        boost::shared_ptr<Axes> axes;
+        if (geometry == 0) axes.reset(new SphericalAxes(ax));
+        else axes.reset(new CylindricalAxes(ax));
+        for (uint64_t k = 0; k < n; ++k) {
+            std::vector<size_t> idxs(idx3 + 3 * k, idx3 + 3 * k + 3);
+            volumes_out[k] = axes->GetBinVolume(idxs);
+        }
+        if (edges_out && edges_axis >= 0 && edges_axis < num_axes) {
+            const std::vector<double> e = axes->at(edges_axis)->GetBinEdges();
+            for (size_t i = 0; i < e.size(); ++i) edges_out[i] = e[i];
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 // angularAcceptance->GetOpenCLFunction("getAngularAcceptance") for the polynomial python/GetIceCubeDOMAngularSensitivity.py:45 returns
 int64_t ref_angular_acceptance_source(const double *coefficients, int32_t n, char *out, size_t cap)
 {

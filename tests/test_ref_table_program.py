@@ -167,3 +167,33 @@ def test_the_table_maker_program_needs_a_declaration_it_does_not_have():
                                     tabulator.PowerAxis(0, 2000, 20, 2)])
     with pytest.raises(RuntimeError, match="geometryGetDomPosition"):
         pyoracle.RefTableProgram(medium, [gen], acc, axes, ANGULAR, dom_stub=False)
+
+
+def test_bin_edges_and_volumes_against_the_references_axes():
+    """Axis::GetBinEdges and Axes::GetBinVolume of the reference (tabulator/Axis.cxx, Axes.cxx, compiled unmodified) against
+    clsim_b200/tabulator.py -- the quantities Normalize() divides by.  Default spherical and cylindrical tables and a
+    full-azimuth table (whose azimuthal bins count once, not twice: Axes.cxx:129)."""
+    import ctypes as C
+    L = pyoracle.ref_medium_lib()
+    rng = np.random.default_rng(11)
+    full = tabulator.SphericalAxes([tabulator.PowerAxis(0, 580, 200, 2), tabulator.LinearAxis(0, 360, 72), tabulator.LinearAxis(-1, 1, 100),
+                                    tabulator.PowerAxis(0, 7000, 105, 2)])
+    for axes in (tabulator.default_axes(), tabulator.default_axes(infinite_muon=True, impact_angle=True), full):
+        n = len(axes.axes)
+        kind = (C.c_int32 * n)(*[ax.kind for ax in axes.axes])
+        power = (C.c_uint32 * n)(*[ax.power for ax in axes.axes])
+        bins = (C.c_uint32 * n)(*[ax.n_bins for ax in axes.axes])
+        lo = (C.c_double * n)(*[ax.min for ax in axes.axes])
+        hi = (C.c_double * n)(*[ax.max for ax in axes.axes])
+        idx = np.stack([rng.integers(0, axes.axes[k].n_bins, 400) for k in range(3)], axis=1).astype(np.uint64)
+        idx[0], idx[1] = 0, [axes.axes[k].n_bins - 1 for k in range(3)]
+        vol = np.zeros(len(idx))
+        for k in range(n):
+            edges = np.zeros(axes.axes[k].n_bins + 1)
+            rc = L.ref_bin_volumes(int(axes.geometry), n, kind, power, bins, lo, hi, idx.ctypes.data_as(C.c_void_p), C.c_uint64(len(idx)),
+                                   vol.ctypes.data_as(C.c_void_p), k, edges.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            np.testing.assert_allclose(axes.at(k).GetBinEdges(), edges, rtol=1e-13, atol=1e-13)
+        ours = np.array([axes.GetBinVolume(tuple(int(v) for v in row)) for row in idx])
+        np.testing.assert_allclose(ours, vol, rtol=1e-12)
+        assert (vol > 0).all()
