@@ -288,3 +288,24 @@ def test_wavelength_generator_factories_against_the_references(medium_name):
         assert text_ours == text_ref, what
         assert "generateWavelength_0" in text_ref
     assert len(kinds) == 3        # equally spaced table, unequally spaced table, closed form
+
+
+def test_product_tables_hold_the_numbers_of_the_generated_text():
+    """The PRODUCT's host-side flattening (csrc/tables.cpp, through clsimcu_describe_tables_from_config, no GPU) against the
+    numbers inside the reference's generated text: per-layer medium tables and the wavelength generators' density and
+    cumulative tables (the reference normalises and accumulates them in I3CLSimRandomValueInterpolatedDistribution.cxx), as floats."""
+    from clsim_b200 import capi
+    sc = add_flasher_generator(make_scene("spice_lea"))
+    t = capi.describe_tables(sc.medium, sc.geo, sc.generators, sc.bias, sc.options())
+    g = pyoracle.RefGeneratedSource(sc.medium, sc.generators, sc.bias)
+    _, med = pyoracle.parse_generated_source(g.medium)
+    f32 = lambda v: np.asarray(v, dtype=np.float32)   # noqa: E731
+    assert np.array_equal(f32(t["medium"]["b400"]), f32(med["getScatteringLength_b400"]))
+    assert np.array_equal(f32(t["medium"]["a_dust400"]), f32(med["getAbsorptionLength_aDust400"]))
+    assert np.array_equal(f32(t["medium"]["delta_tau"]), f32(med["getAbsorptionLength_deltaTau"]))
+    _, gen = pyoracle.parse_generated_source(g.wlen_generators)
+    for i, tab in enumerate(t["wlen_generators"]):
+        assert np.array_equal(f32(tab["beta"]), f32(gen["_generateWavelength_%ddistYValues" % i])), i
+        assert np.array_equal(f32(tab["acu"]), f32(gen["_generateWavelength_%ddistYCumulativeValues" % i])), i
+        if tab["xs"]:
+            assert np.array_equal(f32(tab["xs"]), f32(gen["_generateWavelength_%ddistXValues" % i])), i
