@@ -11,9 +11,11 @@ TEST INFRASTRUCTURE ONLY: imported by tests/ (and nothing under clsim_b200/).  F
   (private/clsim/I3CLSimClientModule.cxx:341-346).
 
 Pinned by reference data: the DOM acceptance table and the hole-ice polynomial are golden fixtures generated
-from the reference's own Python (tests/golden/make_golden.py).  The reference has no known-answer test for
-the conversion itself and draws its thinning numbers from an un-vendored I3RandomService, so the survivors
-are pinned only as a function of explicitly given uniforms: "parity unpinned" for whole-converter outputs.
+from the reference's own Python (tests/golden/make_golden.py).  Pinned to the reference's own code: the source above is
+compiled unmodified into oracle/_ref/libclsim_ref_mcpe.so (oracle/ref_shim/ref_mcpe.cpp; IceTray's module protocol and
+data classes are stand-ins, its random service hands out the uniforms the test supplies), and tests/test_mcpe_oracle.py
+holds both functions below against it: the same survivors and times from the same uniforms, the same fatal conditions,
+the module's per-DOM time ordering.  Not pinned: hit merging (MCHitMerging, sim-services, un-vendored; off by default).
 """
 import numpy as np
 

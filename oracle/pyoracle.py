@@ -816,3 +816,82 @@ def ref_made_wlen_generator_source(medium, wlen_bias, without_dispersion=False, 
                                                                      None if sy is None else sy.ctypes.data, n, out, cap))
     del keep
     return text
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_ref_mcpe.so: the reference's photon -> photo-electron converters
+# (private/clsim/dom/I3PhotonToMCPEConverter.cxx) compiled unmodified (oracle/ref_shim/ref_mcpe.cpp)
+# ---------------------------------------------------------------------------------------------------------
+_REF_MCPE_LIB = os.path.join(_HERE, "_ref", "libclsim_ref_mcpe.so")
+_ref_mcpe_lib = None
+
+
+def ref_mcpe_available():
+    return os.path.isfile(_REF_MCPE_LIB)
+
+
+def _ref_mcpe():
+    global _ref_mcpe_lib
+    if _ref_mcpe_lib is None:
+        L = C.CDLL(_REF_MCPE_LIB)
+        L.ref_mcpe_error.restype = C.c_char_p
+        L.ref_mcpe_convert_inloop.restype = C.c_int64
+        L.ref_mcpe_convert_inloop.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.ref_mcpe_convert_module.restype = C.c_int64
+        L.ref_mcpe_convert_module.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                              C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                              C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                              C.POINTER(C.c_uint64)]
+        _ref_mcpe_lib = L
+    return _ref_mcpe_lib
+
+
+def _acceptance_args(acc):
+    if acc.values is None:
+        return None, None, 0, 0.0, 0.0, float(acc.constant)
+    v = np.ascontiguousarray(acc.values, dtype=np.float64)
+    return v, v.ctypes.data, len(v), float(acc.start_wlen), float(acc.wlen_step), 0.0
+
+
+def ref_mcpe_convert_inloop(photons, acceptance, angular_coefficients, uniforms):
+    """I3CLSimPhotonToMCPEConverterForDOMs::Convert of the reference, photon by photon (photon i is offered uniforms[i]).
+    -> (survivor mask, times of the survivors' photo-electrons (0 elsewhere), uniforms drawn).  RuntimeError = log_fatal."""
+    L = _ref_mcpe()
+    photons = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
+    n = len(photons)
+    keep_v, vp, vn, x0, dx, const = _acceptance_args(acceptance)
+    ang = np.ascontiguousarray(angular_coefficients, dtype=np.float64)
+    u = np.ascontiguousarray(uniforms, dtype=np.float64)
+    survive, t = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.float64)
+    used = C.c_uint64(0)
+    rc = L.ref_mcpe_convert_inloop(photons.ctypes.data, n, vp, vn, x0, dx, const, ang.ctypes.data, len(ang), u.ctypes.data, survive.ctypes.data,
+                                   t.ctypes.data, C.byref(used))
+    if rc < 0:
+        raise RuntimeError(L.ref_mcpe_error().decode())
+    return survive.astype(bool), t, int(used.value)
+
+
+def ref_mcpe_convert_module(photons, dom_positions, acceptance, angular_coefficients, efficiency, uniforms_in_order, oversize=1.0, pancake=1.0,
+                            dom_radius=0.1651, default_efficiency=1.0, replace_with_default=False, only_warn=False):
+    """The reference's I3PhotonToMCPEConverter MODULE on one frame.  photons: DOM-relative records; dom_positions[n, 3]: where
+    each photon's DOM sits; efficiency[n]: relative DOM efficiency from the calibration for each photon's DOM (NaN = no entry).
+    uniforms_in_order: handed out as the module asks (DOMs in key order, photons of a DOM in input order, weight 0 skipped).
+    -> (string[k], om[k], time[k], input photon index[k]) in the module's output order, and the number of uniforms drawn."""
+    L = _ref_mcpe()
+    photons = np.ascontiguousarray(photons, dtype=PHOTON_DTYPE)
+    n = len(photons)
+    keep_v, vp, vn, x0, dx, const = _acceptance_args(acceptance)
+    ang = np.ascontiguousarray(angular_coefficients, dtype=np.float64)
+    u = np.ascontiguousarray(uniforms_in_order, dtype=np.float64)
+    pos = np.ascontiguousarray(dom_positions, dtype=np.float64)
+    eff = np.ascontiguousarray(efficiency, dtype=np.float64)
+    s, o, t, idx = np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.float64), np.zeros(n, np.int64)
+    used = C.c_uint64(0)
+    k = L.ref_mcpe_convert_module(photons.ctypes.data, n, pos.ctypes.data, vp, vn, x0, dx, const, ang.ctypes.data, len(ang), eff.ctypes.data,
+                                  float(default_efficiency), int(bool(replace_with_default)), float(oversize), float(pancake), float(dom_radius),
+                                  int(bool(only_warn)), u.ctypes.data, len(u), s.ctypes.data, o.ctypes.data, t.ctypes.data, idx.ctypes.data, n,
+                                  C.byref(used))
+    if k < 0:
+        raise RuntimeError(L.ref_mcpe_error().decode())
+    return s[:k], o[:k], t[:k], idx[:k], int(used.value)

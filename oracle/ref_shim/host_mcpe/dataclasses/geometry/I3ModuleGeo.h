@@ -1,0 +1,1 @@
+#include "dataclasses/geometry/I3Geometry.h"
