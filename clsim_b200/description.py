@@ -226,8 +226,9 @@ class MediumProperties(object):
     def GetAbsorptionLength(self, layer, wlen):
         """I3CLSimFunctionAbsLenIceCube::GetValue (…AbsLenIceCube.cxx:63-67)."""
         x = wlen / 1e-9
+        # (`1.f + 0.01f*deltaTau_` in the reference: the literal is a float, 0.00999999977648...)
         return 1.0 / ((self.D * self.aDust400[layer] + self.E) * x ** (-self.kappa)
-                      + self.A * math.exp(-self.B / x) * (1.0 + 0.01 * self.deltaTau[layer]))
+                      + self.A * math.exp(-self.B / x) * (1.0 + 0.009999999776482582 * self.deltaTau[layer]))
 
     def GetScatteringLength(self, layer, wlen):
         """I3CLSimFunctionScatLenIceCube::GetValue (…ScatLenIceCube.cxx:53-57)."""

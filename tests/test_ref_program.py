@@ -309,3 +309,17 @@ def test_product_tables_hold_the_numbers_of_the_generated_text():
         assert np.array_equal(f32(tab["acu"]), f32(gen["_generateWavelength_%ddistYCumulativeValues" % i])), i
         if tab["xs"]:
             assert np.array_equal(f32(tab["xs"]), f32(gen["_generateWavelength_%ddistXValues" % i])), i
+
+
+def test_python_host_twins_against_the_references_host_methods():
+    """clsim_b200.description.MediumProperties carries double-precision host twins of the medium functions (used by ice.py's
+    generator factories and by the table-maker's normalisation): the same doubles as GetValue of the reference's classes."""
+    sc, prog, _ = program("spice_lea")
+    g, m = prog.generated, sc.medium
+    for w in np.linspace(265e-9, 675e-9, 83):
+        assert m.GetPhaseRefractiveIndex(w) == pytest.approx(g.host_value(0, 0, w), rel=1e-15)
+        assert m.GetGroupRefractiveIndex(w) == pytest.approx(g.host_value(1, 0, w), rel=1e-15)
+        for layer in (0, 40, 170):
+            assert m.GetScatteringLength(layer, w) == pytest.approx(g.host_value(2, layer, w), rel=1e-13)
+            assert m.GetAbsorptionLength(layer, w) == pytest.approx(g.host_value(3, layer, w), rel=1e-13)
+    assert m.GetMinWavelength() == g.host_value(6) and m.GetMaxWavelength() == g.host_value(7)
