@@ -13,6 +13,28 @@
 
 #include "clsimcuda.h"
 
+#ifdef CLSIM_CUDA_IN_ICETRAY
+// the concrete description classes the flattening recognises (stand-alone they are all in clsim_compat.h)
+#include "clsim/I3CLSimPhoton.h"
+#include "clsim/I3CLSimStep.h"
+#include "clsim/function/I3CLSimFunctionAbsLenIceCube.h"
+#include "clsim/function/I3CLSimFunctionConstant.h"
+#include "clsim/function/I3CLSimFunctionFromTable.h"
+#include "clsim/function/I3CLSimFunctionRefIndexIceCube.h"
+#include "clsim/function/I3CLSimFunctionScatLenIceCube.h"
+#include "clsim/function/I3CLSimScalarFieldAnisotropyAbsLenScaling.h"
+#include "clsim/function/I3CLSimScalarFieldConstant.h"
+#include "clsim/function/I3CLSimScalarFieldIceTiltZShift.h"
+#include "clsim/function/I3CLSimVectorTransformConstant.h"
+#include "clsim/function/I3CLSimVectorTransformMatrix.h"
+#include "clsim/random_value/I3CLSimRandomValueConstant.h"
+#include "clsim/random_value/I3CLSimRandomValueHenyeyGreenstein.h"
+#include "clsim/random_value/I3CLSimRandomValueInterpolatedDistribution.h"
+#include "clsim/random_value/I3CLSimRandomValueMixed.h"
+#include "clsim/random_value/I3CLSimRandomValueSimplifiedLiu.h"
+#include "clsim/random_value/I3CLSimRandomValueWlenCherenkovNoDispersion.h"
+#endif
+
 static_assert(sizeof(I3CLSimStep) == sizeof(clsimcu_step), "step record layouts must agree");
 static_assert(sizeof(I3CLSimPhoton) == sizeof(clsimcu_photon), "photon record layouts must agree");
 
@@ -21,9 +43,14 @@ const bool I3CLSimStepToPhotonConverterCUDA::default_useNativeMath = true;
 namespace {
 typedef I3CLSimStepToPhotonConverter_exception Err;
 
+#ifdef CLSIM_CUDA_IN_ICETRAY
+// (IceTray's pointer typedefs are boost::shared_ptr)
+template <class T, class B> boost::shared_ptr<const T> as(const boost::shared_ptr<const B> &p) { return boost::dynamic_pointer_cast<const T>(p); }
+template <class B> std::string class_name(const boost::shared_ptr<const B> &p)
+#else
 template <class T, class B> std::shared_ptr<const T> as(const std::shared_ptr<const B> &p) { return std::dynamic_pointer_cast<const T>(p); }
-
 template <class B> std::string class_name(const std::shared_ptr<const B> &p)
+#endif
 {
     if (!p) return "(null)";
     const B &ref = *p;
@@ -307,7 +334,11 @@ void I3CLSimStepToPhotonConverterCUDA::Flatten()
         f.tiltDist = t->GetDistancesFromOriginAlongTilt();
         const std::size_t nz = t->GetZCoordinates().size();
         for (std::size_t i = 0; i < f.tiltDist.size(); ++i)
+#ifdef CLSIM_CUDA_IN_ICETRAY
+            for (std::size_t k = 0; k < nz; ++k) f.tiltCorr.push_back(t->GetZCorrections()(i, k));   // I3Matrix (ublas)
+#else
             for (std::size_t k = 0; k < nz; ++k) f.tiltCorr.push_back(t->GetZCorrections()[i][k]);
+#endif
         m.tilt_num_dist = static_cast<int32_t>(f.tiltDist.size());
         m.tilt_num_z = static_cast<int32_t>(nz);
         m.tilt_dist = f.tiltDist.data();

@@ -895,3 +895,45 @@ def ref_mcpe_convert_module(photons, dom_positions, acceptance, angular_coeffici
     if k < 0:
         raise RuntimeError(L.ref_mcpe_error().decode())
     return s[:k], o[:k], t[:k], idx[:k], int(used.value)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle/_ref/libclsim_icetray_mode.so: the PRODUCT's converter class (clsim_b200/host/I3CLSimStepToPhotonConverterCUDA.cxx)
+# compiled with -DCLSIM_CUDA_IN_ICETRAY against the reference's own public headers (+ the getters of INTEGRATION.md section 2)
+# and linked with the reference's description-class sources (oracle/ref_shim/ref_icetray_mode.cpp)
+# ---------------------------------------------------------------------------------------------------------
+_ICETRAY_MODE_LIB = os.path.join(_HERE, "_ref", "libclsim_icetray_mode.so")
+
+
+def icetray_mode_available():
+    return os.path.isfile(_ICETRAY_MODE_LIB)
+
+
+def icetray_mode_describe_tables(medium, geometry, wlen_generators, wlen_bias, options):
+    """JSON of the device tables after SetWlenGenerators / SetWlenBias / SetMediumProperties / SetGeometry / Compile() on the
+    product's converter class, fed REFERENCE objects through the reference's abstract interface."""
+    L = C.CDLL(_ICETRAY_MODE_LIB)
+    L.icetray_mode_error.restype = C.c_char_p
+    L.icetray_mode_describe_tables.restype = C.c_int64
+    L.icetray_mode_describe_tables.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p)]
+    cfg, keep = build_config(medium, geometry, wlen_generators, wlen_bias, options)
+    tz = None if medium.tilt is None else np.ascontiguousarray(medium.tilt["zCoordinates"], dtype=np.float64)
+    names = (C.c_char_p * max(1, len(geometry.subdetectorNames)))(*[s.encode() for s in geometry.subdetectorNames])
+    out = C.c_char_p()
+    n = L.icetray_mode_describe_tables(C.byref(cfg), None if tz is None else tz.ctypes.data, names, C.byref(out))
+    if n < 0:
+        raise RuntimeError(L.icetray_mode_error().decode())
+    text = C.string_at(out, n).decode()
+    del keep
+    return json.loads(text)
+
+
+def icetray_mode_unknown_class_message(medium, wlen_generators, wlen_bias):
+    """What the class throws (as the reference's I3CLSimStepToPhotonConverter_exception) for a scattering model it does not know."""
+    from clsim_b200.description import ConverterOptions
+    L = C.CDLL(_ICETRAY_MODE_LIB)
+    L.icetray_mode_error.restype = C.c_char_p
+    cfg, keep = build_config(medium, None, wlen_generators, wlen_bias, ConverterOptions())
+    rc = L.icetray_mode_unknown_class_is_refused(C.byref(cfg))
+    del keep
+    return rc, L.icetray_mode_error().decode()

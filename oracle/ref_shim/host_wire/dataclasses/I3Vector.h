@@ -8,6 +8,8 @@ template <class T> class I3Vector : public I3FrameObject, public std::vector<T> 
 public:
     I3Vector() {}
     explicit I3Vector(std::size_t n) : std::vector<T>(n) {}
+    I3Vector(std::size_t n, const T &v) : std::vector<T>(n, v) {}
+    template <class Iterator> I3Vector(Iterator first, Iterator last) : std::vector<T>(first, last) {}
     template <class Archive> void serialize(Archive &ar, unsigned version);
 };
 #endif
