@@ -20,7 +20,12 @@
 #include "clsimcuda.h"
 #include "I3CLSimStepToPhotonConverterCUDA.h"
 
-#ifndef CLSIM_CUDA_IN_ICETRAY
+#ifdef CLSIM_CUDA_IN_ICETRAY
+#include "icetray/OMKey.h"
+#include "clsim/function/I3CLSimFunctionConstant.h"
+#include "clsim/function/I3CLSimFunctionFromTable.h"
+#include "clsim/function/I3CLSimFunctionPolynomial.h"
+#else
 // icetray/OMKey.h, the part used here
 struct OMKey {
     OMKey(int string = 0, unsigned om = 0, unsigned char pmt = 0) : string_(string), om_(om), pmt_(pmt) {}
