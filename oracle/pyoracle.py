@@ -937,3 +937,17 @@ def icetray_mode_unknown_class_message(medium, wlen_generators, wlen_bias):
     rc = L.icetray_mode_unknown_class_is_refused(C.byref(cfg))
     del keep
     return rc, L.icetray_mode_error().decode()
+
+
+def ref_medium_host_values(generated, what, abc, layer=0):
+    """GetValue / ApplyTransform of the reference's host-side classes for many arguments at once: `generated` is a
+    RefGeneratedSource; what as in RefGeneratedSource.host_value, plus 8 / 9 = pre / post scattering direction transform
+    (three values out per triple)."""
+    L = ref_medium_lib()
+    abc = np.ascontiguousarray(abc, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((len(abc), 3) if what in (8, 9) else len(abc), dtype=np.float64)
+    tz = None if generated._tilt_z is None else generated._tilt_z.ctypes.data
+    L.ref_medium_host_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64]
+    if L.ref_medium_host_values(C.byref(generated._cfg.medium), tz, what, layer, abc.ctypes.data, out.ctypes.data, len(abc)) != 0:
+        raise RuntimeError(L.ref_medium_last_error().decode())
+    return out

@@ -342,4 +342,35 @@ double ref_medium_host_value(const oracle_medium *m, const double *tilt_z, int32
     }
 }
 
+// ... the same for n argument triples at once (one medium object): abc[3 * i ..], out[i]
+int32_t ref_medium_host_values(const oracle_medium *m, const double *tilt_z, int32_t what, int32_t layer, const double *abc, double *out, uint64_t n)
+{
+    try {
+        I3CLSimMediumPropertiesPtr med = make_medium(*m, tilt_z);
+        for (uint64_t i = 0; i < n; ++i) {
+            const double a = abc[3 * i], b = abc[3 * i + 1], c = abc[3 * i + 2];
+            switch (what) {
+            case 0: out[i] = med->GetPhaseRefractiveIndex(layer)->GetValue(a); break;
+            case 1: out[i] = med->GetGroupRefractiveIndexOverride(layer)->GetValue(a); break;
+            case 2: out[i] = med->GetScatteringLength(layer)->GetValue(a); break;
+            case 3: out[i] = med->GetAbsorptionLength(layer)->GetValue(a); break;
+            case 4: out[i] = med->GetIceTiltZShift()->GetValue(a, b, c); break;
+            case 5: out[i] = med->GetDirectionalAbsorptionLengthCorrection()->GetValue(a, b, c); break;
+            case 8: case 9: {
+                // ApplyTransform of the pre (8) / post (9) scattering direction transform: out holds 3 values per triple
+                const std::vector<double> v = (what == 8 ? med->GetPreScatterDirectionTransform() : med->GetPostScatterDirectionTransform())
+                                                  ->ApplyTransform(std::vector<double>{a, b, c});
+                out[3 * i] = v[0]; out[3 * i + 1] = v[1]; out[3 * i + 2] = v[2];
+                break;
+            }
+            default: throw std::runtime_error("unknown quantity");
+            }
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 } // extern "C"
