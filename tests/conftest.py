@@ -36,6 +36,10 @@ def _built_libraries():
 
 
 def _has_gpu():
+    # tests/test_hostcheck.py runs GPU tests of the reference-order path in a subprocess against the CUDA sources compiled
+    # for the host (tests/hostcheck): there the "device" is the CPU
+    if os.environ.get("CLSIM_HOSTCHECK") == "1":
+        return True
     try:
         import torch
         return torch.cuda.is_available()

@@ -1,10 +1,22 @@
 """Shared scene builders for the tests (the five BASELINE configurations, small)."""
 import math
+import os
 
 import numpy as np
 
 from clsim_b200 import geometry, ice, steps
 from clsim_b200.description import KERNEL_FAST, KERNEL_REFERENCE, ConverterOptions  # noqa: F401
+
+
+# tests/test_hostcheck.py re-runs GPU tests of everything but the fast kernel in a subprocess against the CUDA sources compiled
+# for the host (tests/hostcheck): there the "device" is one CPU thread and holds no fast kernel, so the tests that only need SOME
+# kernel to make photons take the reference-order one, on smaller bunches.  On a GPU (the variable unset) nothing changes.
+HOSTCHECK = os.environ.get("CLSIM_HOSTCHECK") == "1"
+DEVICE_KERNEL = KERNEL_REFERENCE if HOSTCHECK else KERNEL_FAST
+
+
+def sized(on_gpu, on_host):
+    return on_host if HOSTCHECK else on_gpu
 
 
 class Scene(object):

@@ -13,19 +13,21 @@ from clsim_b200.converter import (I3CLSimStepToPhotonConverter_exception, I3CLSi
                                   initializeCUDA)
 from clsim_b200.description import KERNEL_FAST, KERNEL_REFERENCE, STEP_DTYPE
 from clsim_b200.sharding import merge_results
-from tests.scenes import make_scene
+from tests.scenes import HOSTCHECK, make_scene, sized
 
 pytestmark = pytest.mark.gpu
 
 
 def make_converter(sc, **kw):
+    if HOSTCHECK:
+        kw.setdefault("kernelMode", KERNEL_REFERENCE)   # (the host check build holds no fast kernel, tests/scenes.py)
     dev = configureCUDADevices(UseGPUs=True, UseOnlyDeviceNumber=0, OverrideApproximateNumberOfWorkItems=kw.pop("work_items", 8192))[0]
     return initializeCUDA(dev, 1, sc.geo, sc.medium, sc.bias, sc.generators, stopDetectedPhotons=True, pancakeFactor=sc.pancake, **kw)
 
 
 def test_life_cycle_and_errors():
     sc = make_scene("spice_mie", geo_kind="ring")
-    conv = I3CLSimStepToPhotonConverterCUDA(1)
+    conv = I3CLSimStepToPhotonConverterCUDA(1, useNativeMath=not HOSTCHECK)
     with pytest.raises(I3CLSimStepToPhotonConverter_exception, match="not initialized"):
         conv.EnqueueSteps(steps.muon_track_steps(8), 0)
     with pytest.raises(I3CLSimStepToPhotonConverter_exception, match="WlenGenerators not set"):
@@ -126,9 +128,9 @@ def test_five_workers_any_order_results(double_buffering):
 
 def test_destroy_with_pending_work_does_not_hang():
     sc = make_scene("spice_mie", geo_kind="ring")
-    conv = make_converter(sc, work_items=1 << 16)
+    conv = make_converter(sc, work_items=sized(1 << 16, 1 << 12))
     for i in range(4):
-        conv.EnqueueSteps(steps.muon_track_steps(1 << 15, seed=i), i)
+        conv.EnqueueSteps(steps.muon_track_steps(sized(1 << 15, 1 << 11), seed=i), i)
     done = threading.Event()
 
     def closer():

@@ -7,14 +7,16 @@ import numpy as np
 import pytest
 
 from clsim_b200 import capi, geometry, ice, mcpe, steps
-from clsim_b200.description import KERNEL_FAST, PHOTON_DTYPE
+from clsim_b200.description import PHOTON_DTYPE
 from oracle import mcpe_oracle
 from clsim_b200.sharding import mcpe_row_offset, stepgen_row_offset
-from tests.scenes import Scene, make_scene
+from tests.scenes import DEVICE_KERNEL, Scene, make_scene, sized
 from tests.test_mcpe_oracle import golden_angular, photons_on_sphere
 
 pytestmark = pytest.mark.gpu
 
+N_STEPS = sized(1 << 15, 1 << 12)     # steps per bunch where a test only needs detected photons
+MIN_HITS = sized(3000, 300)
 RATIO = (np.array([250.0, 400.0, 700.0]), np.array([1.30, 1.35, 1.40]))  # synthetic stand-in for ice-models' wv.rde
 
 
@@ -31,10 +33,10 @@ def detector(oversize=5.0, unshadowed=0.9):
     return sc, acc_of, mcpe.GetIceCubeDOMAngularSensitivity()
 
 
-def detected_photons(sc, n_steps=1 << 15, seed=21, pancake=None):
-    opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n_steps, rng_seed=5)
+def detected_photons(sc, n_steps=N_STEPS, seed=21, pancake=None):
+    opt = sc.options(kernel_mode=DEVICE_KERNEL, max_num_workitems=n_steps, rng_seed=5)
     if pancake is not None:
-        opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n_steps, rng_seed=5, pancake_factor=pancake)
+        opt = sc.options(kernel_mode=DEVICE_KERNEL, max_num_workitems=n_steps, rng_seed=5, pancake_factor=pancake)
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         eng.enqueue(steps.muon_track_steps(n_steps, seed=seed), 1)
         return eng.get_result().photons
@@ -56,7 +58,7 @@ def expected(photons, keep, time):
 def test_inloop_converter_on_propagated_photons_explicit_uniforms():
     sc, acc_of, ang = detector()
     photons = detected_photons(sc)
-    assert len(photons) > 3000
+    assert len(photons) > MIN_HITS
     # the propagation kernel leaves the photon on the surface of the real-size DOM (pancake undone)
     r = np.sqrt(photons["x"].astype(np.float64) ** 2 + photons["y"].astype(np.float64) ** 2 + photons["z"].astype(np.float64) ** 2)
     assert np.abs(r - 0.1651).max() < 0.005
@@ -160,8 +162,8 @@ def test_fatal_conditions_are_errors():
 
 def test_conversion_attached_to_the_engine():
     sc, acc_of, ang = detector()
-    n_steps = 1 << 15
-    opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=n_steps, rng_seed=5, enable_double_buffering=True)
+    n_steps = N_STEPS
+    opt = sc.options(kernel_mode=DEVICE_KERNEL, max_num_workitems=n_steps, rng_seed=5, enable_double_buffering=True)
     conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(77, acc_of, ang, rngFirstMultiplierRow=mcpe_row_offset(2))
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         conv.attach_to(eng, keep_photons=True)
@@ -172,7 +174,7 @@ def test_conversion_attached_to_the_engine():
             eng.enqueue(steps.muon_track_steps(n_steps, seed=40 + i), i)
         results = sorted((eng.get_result() for _ in range(3)), key=lambda r: r.identifier)  # launches run in enqueue order
         for res in results:
-            assert len(res.photons) > 3000 and res.num_hits_counted == len(res.photons)
+            assert len(res.photons) > MIN_HITS and res.num_hits_counted == len(res.photons)
             u, x = mcpe_oracle.mwc_uniforms(x, a, len(res.photons))
             keep, _, t = mcpe_oracle.convert_inloop(res.photons, acc_of, ang.coefficients, u)
             assert as_set(res.mcpes) == as_set(expected(res.photons, keep, t))
@@ -183,7 +185,7 @@ def test_conversion_attached_to_the_engine():
         conv.attach_to(eng)
         eng.enqueue(steps.muon_track_steps(n_steps, seed=40), 9)
         res = eng.get_result()
-        assert len(res.photons) == 0 and res.num_hits_counted > 3000
+        assert len(res.photons) == 0 and res.num_hits_counted > MIN_HITS
         frac = len(res.mcpes) / float(res.num_hits_counted)
         assert abs(frac - len(results[0].mcpes) / float(len(results[0].photons))) < 0.03
         assert np.all(res.mcpes["npe"] == 1) and np.all(res.mcpes["identifier"] < n_steps)
@@ -200,10 +202,10 @@ def test_attached_converter_errors_surface_through_the_engine():
     sc, acc_of, ang = detector()
     only_string_1 = {k: v for k, v in acc_of.items() if k[0] == 1}
     conv = mcpe.I3CLSimPhotonToMCPEConverterForDOMs(5, only_string_1, ang)
-    opt = sc.options(kernel_mode=KERNEL_FAST, max_num_workitems=1 << 14, rng_seed=5)
+    opt = sc.options(kernel_mode=DEVICE_KERNEL, max_num_workitems=sized(1 << 14, 1 << 11), rng_seed=5)
     with capi.Engine(sc.medium, sc.geo, sc.generators, sc.bias, opt) as eng:
         conv.attach_to(eng)
-        eng.enqueue(steps.muon_track_steps(1 << 14, seed=3), 1)
+        eng.enqueue(steps.muon_track_steps(sized(1 << 14, 1 << 11), seed=3), 1)
         with pytest.raises(capi.ClsimCudaError, match="No wavelength acceptance"):
             eng.get_result()
     conv.close()

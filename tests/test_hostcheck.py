@@ -1,0 +1,68 @@
+"""The CUDA sources of everything but the fast kernel, run on the CPU: engine.cu, kernel_reference.cu, mcpe.cu, stepgen.cu and
+tabulate.cu compiled for the host under a stand-in CUDA runtime (tests/hostcheck/: one syntax rewrite, the three `<<<>>>`
+launches), and the GPU tests of those units -- the same test files the B200 runs, unmodified -- executed against that build in a
+subprocess (CLSIMCU_LIB points clsim_b200.capi at it, CLSIM_HOSTCHECK=1 tells tests/conftest.py that the "device" is the CPU
+and tests/scenes.py to shrink the bunches and to take the reference-order kernel where a test only needs SOME kernel).
+
+What this shows without a GPU: the reference-order CUDA kernel's SOURCE gives the oracle's hit lists (on the device it differs
+from the oracle in the last bits of CUDA's libm; here both run on glibc), the engine's threads / staging / result assembly /
+error propagation work, the photon -> MCPE converter, the step generator and the reference-order table maker equal their
+oracles, and a step at infinity ends at once.  What it does not show: anything about the fast kernel (not in the build) or
+about the device.  This is a test of source text -- the product has no CPU path and `clsim_b200` never loads this library."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests import hostcheck
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SELECTION = {
+    # file: -k expression (None = the whole file)
+    "tests/test_gpu_reference_kernel.py": None,
+    "tests/test_gpu_tabulator.py": "spherical_table_equals or cylindrical_table_with or full_azimuth_table",      # the reference-order table maker
+    "tests/test_gpu_stepgen.py": "every_step_of_every or argument_errors or reference_shaped",
+    "tests/test_gpu_mcpe.py": "not device_rng_draw_assignment",      # (45 s of oracle work in Python; runs on the GPU box)
+    "tests/test_gpu_engine.py": "not two_converters_disjoint and not reference_mode_converter_history",      # (those name the fast kernel)
+    "tests/test_zz_gpu_steps_at_infinity.py": "1]",      # the reference-order kernel's parametrisation
+}
+
+
+def test_host_check_build_rewrites_only_the_launches():
+    lib = hostcheck.build()
+    assert os.path.isfile(lib)
+    with open(os.path.join(hostcheck.BUILD, "rewrite.log")) as f:
+        log = f.read().strip().split("\n")
+    assert log[-1] == "3 launches rewritten"
+    assert all("<<<" in line and "HOSTCHECK_LAUNCH(" in line for line in log[:-1])
+    # the product's loader knows nothing of it
+    from clsim_b200 import capi
+    assert "hostcheck" not in capi.LIB_PATH or os.environ.get("CLSIMCU_LIB")
+
+
+@pytest.fixture(scope="module")
+def runs():
+    """All selections at once, each in its own pytest process (they are independent; the wall time is the slowest one's)."""
+    lib = hostcheck.build()
+    env = dict(os.environ, CLSIM_HOSTCHECK="1", CLSIMCU_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
+               OMP_NUM_THREADS="2")
+    procs = {}
+    for path, expr in SELECTION.items():
+        cmd = [sys.executable, "-m", "pytest", path, "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"]
+        if expr:
+            cmd += ["-k", expr]
+        procs[path] = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    yield procs
+    for p in procs.values():
+        if p.poll() is None:
+            p.kill()
+
+
+@pytest.mark.parametrize("path", sorted(SELECTION))
+def test_gpu_tests_pass_on_the_host_compiled_sources(runs, path):
+    out, _ = runs[path].communicate(timeout=1500)
+    tail = out[-3000:]
+    assert runs[path].returncode == 0, tail
+    assert " passed" in tail and " failed" not in tail, tail
