@@ -27,6 +27,8 @@ SELECTION = {
     "tests/test_gpu_mcpe.py": "not device_rng_draw_assignment",      # (45 s of oracle work in Python; runs on the GPU box)
     "tests/test_gpu_engine.py": "not two_converters_disjoint and not reference_mode_converter_history",      # (those name the fast kernel)
     "tests/test_zz_gpu_steps_at_infinity.py": "1]",      # the reference-order kernel's parametrisation
+    # not a GPU test: the host-compiled kernel against the oracle, byte for byte (both on glibc)
+    "tests/hostcheck/check_bit_identity.py": None,
 }
 
 
