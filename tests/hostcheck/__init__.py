@@ -53,7 +53,15 @@ def rewrite_launches(text):
     return _LAUNCH.sub(rep, text), changed
 
 
-def build(force=False):
+def build(force=False, sanitize=False):
+    """sanitize=True: a second library, built with -fsanitize=address,undefined (tests/test_hostcheck.py runs the byte-identity
+    check and the engine tests under it)."""
+    global LIB
+    lib = os.path.join(BUILD, "libclsimcuda_hostcheck_asan.so") if sanitize else LIB
+    return _build(lib, force, ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if sanitize else ["-O2"])
+
+
+def _build(LIB, force, opt_flags):
     sources = [os.path.join(CSRC, u) for u in UNITS] + [os.path.join(CSRC, "tables.cpp"), os.path.join(HERE, "cuda_runtime.h"),
                                                         os.path.join(HERE, "fast_kernel_stub.cpp"), os.path.abspath(__file__)]
     sources += [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".h")]
@@ -65,14 +73,14 @@ def build(force=False):
         with open(os.path.join(CSRC, u)) as f:
             text, changed = rewrite_launches(f.read())
         log += ["%s: %s  ->  %s" % (u, a, b) for a, b in changed]
-        cpp = os.path.join(BUILD, u.replace(".cu", ".cpp"))
+        cpp = os.path.join(BUILD, ("asan_" if "-g" in opt_flags else "") + u.replace(".cu", ".cpp"))
         with open(cpp, "w") as f:
             f.write(text)
         cpps.append(cpp)
     with open(os.path.join(BUILD, "rewrite.log"), "w") as f:
         f.write("\n".join(log) + "\n%d launches rewritten\n" % len(log))
     # -ffp-contract=off: kernel_reference.cu is built with --fmad=false for the device as well (the exact twin)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-w", "-ffp-contract=off", "-fno-fast-math", "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
+    cmd = ["g++"] + opt_flags + ["-std=c++17", "-fPIC", "-w", "-ffp-contract=off", "-fno-fast-math", "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"),
            "-shared", "-o", LIB] + cpps + [os.path.join(CSRC, "tables.cpp"), os.path.join(HERE, "fast_kernel_stub.cpp"), "-lpthread", "-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     for cpp in cpps:
