@@ -57,6 +57,8 @@ def build(force=False, sanitize=False):
     """sanitize=True: a second library, built with -fsanitize=address,undefined (tests/test_hostcheck.py runs the byte-identity
     check and the engine tests under it)."""
     global LIB
+    if sanitize == "thread":
+        return _build(os.path.join(BUILD, "libclsimcuda_hostcheck_tsan.so"), force, ["-fsanitize=thread", "-fno-omit-frame-pointer", "-g", "-O1"])
     lib = os.path.join(BUILD, "libclsimcuda_hostcheck_asan.so") if sanitize else LIB
     return _build(lib, force, ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g", "-O1"] if sanitize else ["-O2"])
 
@@ -73,7 +75,7 @@ def _build(LIB, force, opt_flags):
         with open(os.path.join(CSRC, u)) as f:
             text, changed = rewrite_launches(f.read())
         log += ["%s: %s  ->  %s" % (u, a, b) for a, b in changed]
-        cpp = os.path.join(BUILD, ("asan_" if "-g" in opt_flags else "") + u.replace(".cu", ".cpp"))
+        cpp = os.path.join(BUILD, ("san_" if "-g" in opt_flags else "") + u.replace(".cu", ".cpp"))
         with open(cpp, "w") as f:
             f.write(text)
         cpps.append(cpp)
