@@ -132,7 +132,7 @@ static void test_on_device()
 {
     const std::size_t bunch = 4096;
     const uint32_t photons = 100;
-    I3CLSimCUDADevice dev = {0, bunch, true};
+    I3CLSimCUDADevice dev = {0, bunch, test_native_math()};
     I3CLSimMediumPropertiesConstPtr medium = make_medium(true);
     I3CLSimFunctionConstPtr bias = make_bias();
     std::vector<I3CLSimRandomValueConstPtr> gens(1, make_generator(bias, medium));
@@ -215,7 +215,7 @@ static void test_on_device()
 
     // photon history (on the fast kernel: native math requested)
     {
-        I3CLSimCUDADevice precise = {0, 1024, true};
+        I3CLSimCUDADevice precise = {0, 1024, test_native_math()};
         auto hc = I3CLSimModuleHelper::initializeCUDA(precise, 5, make_ring_geometry(5.0), medium, bias, gens, false, false, true, false, 0.01, NAN,
                                                       5.0, /*history*/ 4, 0);
         hc->EnqueueSteps(make_steps(1024, 200, 7, 77), 7);

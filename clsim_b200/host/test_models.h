@@ -5,12 +5,20 @@
 #define CLSIM_TEST_MODELS_H_INCLUDED
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
 #include "I3CLSimStepToPhotonConverterCUDA.h"
 
 static const double nm = 1e-9, deg = M_PI / 180.0;
+
+// tests/test_hostcheck.py runs these programs against the CUDA sources compiled for the host (tests/hostcheck), which hold no
+// fast kernel: with CLSIM_HOSTCHECK=1 in the environment the converters take the reference-order kernel and smaller bunches.
+// On a GPU (the variable unset) nothing changes.
+static inline bool test_on_host_check() { return std::getenv("CLSIM_HOSTCHECK") != nullptr; }
+static inline bool test_native_math() { return !test_on_host_check(); }
+static inline std::size_t test_sized(std::size_t on_gpu, std::size_t on_host) { return test_on_host_check() ? on_host : on_gpu; }
 
 // 24-DOM ring (resources/scripts/benchmark.py:63-114)
 static inline I3CLSimSimpleGeometryConstPtr make_ring_geometry(double oversize)

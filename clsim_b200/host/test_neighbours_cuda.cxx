@@ -85,7 +85,7 @@ static double reference_probability(const I3CLSimPhoton &p, const I3CLSimFunctio
 static void test_on_device()
 {
     const std::size_t bunch = 16384;
-    I3CLSimCUDADevice dev = {0, bunch, true};
+    I3CLSimCUDADevice dev = {0, bunch, test_native_math()};
     I3CLSimMediumPropertiesConstPtr medium = make_medium(false);
     // generation bias = envelope of the two DOM classes (python/traysegments/common.py:186-191)
     I3CLSimFunctionConstPtr plain = scaled(make_bias(), 0.9 * 0.75), high_qe = scaled(make_bias(), 0.9 * 0.75 * 1.35);

@@ -229,13 +229,13 @@ static void test_with_cuda_converters(int want)
     int devices = 0;
     CHECK(clsimcu_device_count(&devices) == CLSIMCU_OK && devices >= 1);
     if (devices < 1) return;
-    const std::size_t bunch = 8192;
+    const std::size_t bunch = test_sized(8192, 1024);
     I3CLSimMediumPropertiesConstPtr medium = make_medium(false);
     I3CLSimFunctionConstPtr bias = make_bias();
     std::vector<I3CLSimRandomValueConstPtr> gens(1, make_generator(bias, medium));
     std::vector<I3CLSimStepToPhotonConverterPtr> converters;
     for (int i = 0; i < want; ++i) {
-        I3CLSimCUDADevice dev = {i % devices, bunch, true};
+        I3CLSimCUDADevice dev = {i % devices, bunch, test_native_math()};
         // each converter its own slice of the safe-prime multiplier table: independent RNG streams
         converters.push_back(I3CLSimModuleHelper::initializeCUDA(dev, 1000 + i, make_ring_geometry(5.0), medium, bias, gens, true, false, true, false,
                                                                 0.01, NAN, 5.0, 0, 0, uint64_t(i) * 2u * 160u * 1024u));

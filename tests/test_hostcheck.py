@@ -44,8 +44,17 @@ def test_host_check_build_rewrites_only_the_launches():
     assert "hostcheck" not in capi.LIB_PATH or os.environ.get("CLSIMCU_LIB")
 
 
+# the C++ test programs of the drop-in classes (clsim_b200/host/test_*.cxx, built by __graft_entry__.build_host_class), with
+# the arguments tests/test_host_class.py gives them on a GPU box
+CXX_PROGRAMS = {
+    "test_converter_cuda": ["--gpu"],          # I3CLSimStepToPhotonConverterCUDA: 20 bunches, every setter's contract, history, destructor with work queued
+    "test_server_inprocess": ["--gpu", "2"],   # two converters behind I3CLSimServerInProcess, three clients, photon conservation
+    "test_neighbours_cuda": ["--gpu"],         # I3CLSimPhotonToMCPEConverterCUDA / I3CLSimStepGeneratorCUDA attached to a converter
+}
+
+
 @pytest.fixture(scope="module")
-def runs():
+def runs(tmp_path_factory):
     """All selections at once, each in its own pytest process (they are independent; the wall time is the slowest one's)."""
     lib = hostcheck.build()
     env = dict(os.environ, CLSIM_HOSTCHECK="1", CLSIMCU_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
@@ -56,6 +65,16 @@ def runs():
         if expr:
             cmd += ["-k", expr]
         procs[path] = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # the C++ programs link libclsimcuda.so by name (DT_RUNPATH, so LD_LIBRARY_PATH comes first): a directory in which that
+    # name is the host check build
+    import __graft_entry__ as entry
+    entry.build_host_class()
+    libdir = tmp_path_factory.mktemp("hostcheck_lib")
+    os.symlink(lib, os.path.join(str(libdir), "libclsimcuda.so"))
+    cxx_env = dict(env, LD_LIBRARY_PATH=str(libdir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    for name, args in CXX_PROGRAMS.items():
+        binary = os.path.join(ROOT, "clsim_b200", "host", "build", name)
+        procs[name] = subprocess.Popen([binary] + args, cwd=ROOT, env=cxx_env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     yield procs
     for p in procs.values():
         if p.poll() is None:
@@ -68,3 +87,11 @@ def test_gpu_tests_pass_on_the_host_compiled_sources(runs, path):
     tail = out[-3000:]
     assert runs[path].returncode == 0, tail
     assert " passed" in tail and " failed" not in tail, tail
+
+
+@pytest.mark.parametrize("name", sorted(CXX_PROGRAMS))
+def test_cxx_programs_of_the_drop_in_classes_pass_on_the_host_compiled_sources(runs, name):
+    out, _ = runs[name].communicate(timeout=1500)
+    tail = out[-3000:]
+    assert runs[name].returncode == 0, tail
+    assert " 0 failed" in tail, tail
