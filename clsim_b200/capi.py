@@ -13,7 +13,9 @@ import numpy as np
 from .description import PHOTON_DTYPE, STEP_DTYPE, ConfigStruct, ResultStruct, build_config
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CLSIMCU_LIB selects another build of the same library (tools/build_variants.py, A/B runs)
+# CLSIMCU_LIB selects another build of the same library: kernel variants for A/B runs (tools/build_variants.py), and -- in the
+# test suite only -- the CUDA sources compiled for the host (tests/hostcheck, a test of the source text that holds no fast kernel).
+# Unset, as in every product use, the one library there is is libclsimcuda.so, and it needs a CUDA device: no CPU fallback.
 LIB_PATH = os.environ.get("CLSIMCU_LIB") or os.path.join(_HERE, "libclsimcuda.so")
 _lib = None
 
