@@ -84,7 +84,8 @@ static double reference_probability(const I3CLSimPhoton &p, const I3CLSimFunctio
 
 static void test_on_device()
 {
-    const std::size_t bunch = 16384;
+    const std::size_t bunch = test_sized(16384, 8192);   // (the host check, tests/test_hostcheck.py, takes smaller bunches)
+    const std::size_t enough = test_sized(150, 60);
     I3CLSimCUDADevice dev = {0, bunch, test_native_math()};
     I3CLSimMediumPropertiesConstPtr medium = make_medium(false);
     // generation bias = envelope of the two DOM classes (python/traysegments/common.py:186-191)
@@ -101,7 +102,7 @@ static void test_on_device()
     auto conv = make_conv(11);
     conv->EnqueueSteps(make_steps(bunch, 200, 5, 5), 5);
     I3CLSimPhotonSeriesPtr photons = conv->GetConversionResult().photons;
-    CHECK(photons && photons->size() > 150);
+    CHECK(photons && photons->size() > enough);
     I3CLSimPhotonToMCPEConverterCUDA mcpe(21, acc, angular, 0, 2700000);
     std::mt19937 rng(3);
     std::uniform_real_distribution<float> uni(0.f, 1.f);
@@ -139,7 +140,7 @@ static void test_on_device()
     conv2->EnqueueSteps(make_steps(bunch, 200, 6, 6), 6);
     std::vector<clsimcu_mcpe> pes;
     I3CLSimStepToPhotonConverter::ConversionResult_t res = conv2->GetConversionResultWithMCPEs(pes);
-    CHECK(res.identifier == 6 && res.photons && res.photons->size() > 150);
+    CHECK(res.identifier == 6 && res.photons && res.photons->size() > enough);
     CHECK(!pes.empty() && pes.size() < res.photons->size());
     std::multiset<Key> photon_keys;
     for (const I3CLSimPhoton &p : *res.photons) photon_keys.insert(Key(p.GetStringID(), p.GetOMID(), p.GetTime(), p.GetID()));

@@ -58,7 +58,9 @@ def runs(tmp_path_factory):
     """All selections at once, each in its own pytest process (they are independent; the wall time is the slowest one's)."""
     lib = hostcheck.build()
     env = dict(os.environ, CLSIM_HOSTCHECK="1", CLSIMCU_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
-               OMP_NUM_THREADS="2")
+               OMP_NUM_THREADS="2",
+               # the MWC multiplier table is memoised next to the product library; the host check build lives elsewhere
+               CLSIMCU_SAFEPRIMES_CACHE=os.path.join(ROOT, "clsim_b200", "data", "safeprimes_base32.bin"))
     procs = {}
     for path, expr in SELECTION.items():
         cmd = [sys.executable, "-m", "pytest", path, "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"]

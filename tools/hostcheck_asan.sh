@@ -17,7 +17,7 @@ SELECT="(not two_converters_disjoint and not reference_mode_converter_history an
   echo "#        tests/test_zz_gpu_steps_at_infinity.py tests/hostcheck/check_bit_identity.py -m gpu -k \"$SELECT\""
 } > "$LOG"
 set +e
-CLSIM_HOSTCHECK=1 CLSIMCU_LIB="$LIB" LD_PRELOAD="$ASAN $STDCPP" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=0 \
+CLSIM_HOSTCHECK=1 CLSIMCU_LIB="$LIB" CLSIMCU_SAFEPRIMES_CACHE="$PWD/clsim_b200/data/safeprimes_base32.bin" LD_PRELOAD="$ASAN $STDCPP" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=0 \
   python -m pytest tests/test_gpu_reference_kernel.py tests/test_gpu_engine.py tests/test_gpu_mcpe.py tests/test_gpu_stepgen.py tests/test_gpu_tabulator.py \
   tests/test_zz_gpu_steps_at_infinity.py tests/hostcheck/check_bit_identity.py -q -m gpu -p no:cacheprovider -k "$SELECT" > /tmp/hostcheck_asan.out 2>&1
 RC=$?
