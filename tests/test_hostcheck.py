@@ -57,6 +57,10 @@ CXX_PROGRAMS = {
 def runs(tmp_path_factory):
     """All selections at once, each in its own pytest process (they are independent; the wall time is the slowest one's)."""
     lib = hostcheck.build()
+    # (the table is written once, here, by the product library's host-only entry -- not by ten processes at a time)
+    from clsim_b200 import capi
+    from clsim_b200.sharding import TOTAL_ROWS_RESERVED
+    capi.safeprime_multipliers(0, TOTAL_ROWS_RESERVED)
     env = dict(os.environ, CLSIM_HOSTCHECK="1", CLSIMCU_LIB=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
                OMP_NUM_THREADS="2",
                # the MWC multiplier table is memoised next to the product library; the host check build lives elsewhere
