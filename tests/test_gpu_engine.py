@@ -178,7 +178,12 @@ def test_reference_mode_converter_history():
         col = res.photonHistories[i, :min(int(scat[i]), 4), 3]
         assert np.all(np.diff(col) >= 0)
     conv.Close()
+
+
+def test_fast_kernel_converter_history_and_its_limit():
     # the same option on the fast kernel (the default of the converter class)
+    sc = make_scene("spice_mie", geo_kind="ring")
+    src = (sc.geo.posX[0] + 8.0, sc.geo.posY[0], sc.geo.posZ[0])
     conv = make_converter(sc, kernelMode=KERNEL_FAST, photonHistoryEntries=4, work_items=2048)
     conv.EnqueueSteps(steps.point_source_steps(2048, 100, pos=src, seed=9), 4)
     res = conv.GetConversionResult()

@@ -25,7 +25,7 @@ SELECTION = {
     "tests/test_gpu_tabulator.py": "spherical_table_equals or cylindrical_table_with or full_azimuth_table",      # the reference-order table maker
     "tests/test_gpu_stepgen.py": "every_step_of_every or argument_errors or reference_shaped",
     "tests/test_gpu_mcpe.py": "not device_rng_draw_assignment",      # (45 s of oracle work in Python; runs on the GPU box)
-    "tests/test_gpu_engine.py": "not two_converters_disjoint and not reference_mode_converter_history",      # (those name the fast kernel)
+    "tests/test_gpu_engine.py": "not two_converters_disjoint and not fast_kernel_converter_history",      # (those name the fast kernel)
     "tests/test_zz_gpu_steps_at_infinity.py": "1]",      # the reference-order kernel's parametrisation
     # not a GPU test: the host-compiled kernel against the oracle, byte for byte (both on glibc)
     "tests/hostcheck/check_bit_identity.py": None,

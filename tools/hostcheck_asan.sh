@@ -9,7 +9,7 @@ LOG=${1:-profiles/hostcheck_asan_r02.txt}
 LIB=$(PYTHONPATH=. python -c "from tests import hostcheck; print(hostcheck.build(sanitize=True))")
 ASAN=$(gcc -print-file-name=libasan.so)
 STDCPP=$(gcc -print-file-name=libstdc++.so)   # (preloaded as well: the interceptor of __cxa_throw needs it in a python process)
-SELECT="(not two_converters_disjoint and not reference_mode_converter_history and not device_rng_draw_assignment and not (steps_at_infinity and 0]) and not persistent_kernel and not bunches_generated_and_propagated and not converter_feeds_the_engine)"
+SELECT="(not two_converters_disjoint and not fast_kernel_converter_history and not device_rng_draw_assignment and not (steps_at_infinity and 0]) and not persistent_kernel and not bunches_generated_and_propagated and not converter_feeds_the_engine)"
 {
   echo "# $(date -u +%Y-%m-%dT%H:%MZ)  g++ $(g++ -dumpversion), -fsanitize=address,undefined -O1 -g; library: ${LIB#$PWD/}"
   echo "# LD_PRELOAD=libasan.so libstdc++.so  ASAN_OPTIONS=detect_leaks=0:halt_on_error=1  UBSAN_OPTIONS=print_stacktrace=1"
