@@ -323,3 +323,36 @@ def test_python_host_twins_against_the_references_host_methods():
             assert m.GetScatteringLength(layer, w) == pytest.approx(g.host_value(2, layer, w), rel=1e-13)
             assert m.GetAbsorptionLength(layer, w) == pytest.approx(g.host_value(3, layer, w), rel=1e-13)
     assert m.GetMinWavelength() == g.host_value(6) and m.GetMaxWavelength() == g.host_value(7)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the reference's own validation fixture (resources/scripts/compareToPPCredux): 24 DOMs on a ring of 120 m around
+# (257, 212, -399), a cascade at the centre, SpiceLea with tilt and anisotropy switched on and off -- its four ice
+# directories read where they lie.  The reference compares arrival-time histograms with ppc by eye (a PDF); here its own
+# program for each variant is held against the oracle, byte for byte.
+# ----------------------------------------------------------------------------------------------------------------
+PPC_FIXTURE = "/root/reference/resources/scripts/compareToPPCredux/test_ice_models"
+
+
+@pytest.mark.parametrize("variant", ["lea", "lea_notilt", "lea_noanisotropy", "lea_notilt_noanisotropy"])
+def test_whole_program_on_the_references_ppc_comparison_fixture(variant):
+    import os
+    from clsim_b200 import geometry, ice
+    from tests.scenes import Scene
+    directory = os.path.join(PPC_FIXTURE, variant)
+    if not os.path.isdir(directory):
+        pytest.skip("the reference's test ice models are not here")
+    medium = ice.MakeIceCubeMediumProperties(iceDataDirectory=directory, useTiltIfAvailable=True)
+    assert (medium.tilt is not None) == ("notilt" not in variant) and (medium.anisotropy is not None) == ("noanisotropy" not in variant)
+    centre = (257.0, 212.0, -399.0)
+    oversize = 5.0                                                                              # cfg.txt of the fixture: "over-R" 5
+    geo = geometry.make_ring_geometry(oversize=oversize, radius=120.0, center=centre)      # generateTestingGeometry.py
+    bias = ice.GetIceCubeDOMAcceptance(domRadius=geometry.DOM_RADIUS * oversize)
+    sc = Scene(medium, geo, [ice.makeCherenkovWavelengthGenerator(bias, False, medium)], bias, oversize, oversize)
+    opt = sc.options(max_num_workitems=1024)
+    prog = pyoracle.RefProgram(sc.medium, sc.geo, sc.generators, sc.bias, opt)
+    ora = pyoracle.Scene(sc.medium, sc.geo, sc.generators, sc.bias, opt)
+    bunch = steps.cascade_steps(6000, pos=centre, seed=21)       # (the fixture's source: an electron cascade at the centre of the ring)
+    got, want, _ = run_both(prog, ora, bunch)
+    assert got[1] > 5
+    assert_identical(got, want)
